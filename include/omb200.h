@@ -1,0 +1,351 @@
+/*
+ * omb200.h — C ABI of the B200-native OpenMeters DSP hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one method of the
+ * reference's three processors (all citations are into /root/reference/):
+ *
+ *   SpectrogramProcessor  src/visuals/spectrogram/processor.rs:187-223,490-543
+ *   SpectrumProcessor     src/visuals/spectrum/processor.rs:88-124,255-322
+ *   LoudnessProcessor     src/visuals/loudness/processor.rs:224-311
+ *
+ * which the reference drives through `VisualModule::ingest(&AudioBlock)`
+ * (src/visuals/registry.rs:106-115,247-256).  The reference crate is
+ * `#![forbid(unsafe_code)]` (src/main.rs:4), so the Rust binding lives in a
+ * separate `-sys` crate; see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the boundary.
+ *   - return value: OMB_OK (0), OMB_NO_DATA (1, the reference's `None`), or a
+ *     negative omb_status; omb_last_error() gives a thread-local message.
+ *   - handles are not thread-safe (the reference's processors are `!Send`,
+ *     registry.rs:23); distinct handles are independent.
+ *   - output structs point into library-owned host memory that stays valid
+ *     until the next call on the same handle (the reference moves an owned
+ *     SpectrogramUpdate / borrows &SpectrumSnapshot; the caller copies).
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     OMB_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef OMB200_H
+#define OMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMB_MAX_CHANNELS 8 /* dsp.rs:6 MAX_AUDIO_CHANNELS */
+
+typedef enum omb_status {
+  OMB_OK = 0,
+  OMB_NO_DATA = 1,          /* process_block returned None */
+  OMB_ERR_INVALID = -1,     /* null pointer / malformed argument */
+  OMB_ERR_UNSUPPORTED = -2, /* e.g. non power-of-two fft_size: no kernel, and no CPU fallback */
+  OMB_ERR_CUDA = -3,        /* CUDA runtime failure or no device */
+  OMB_ERR_NOMEM = -4
+} omb_status;
+
+/* util/audio/window.rs:9-18 WindowKind */
+typedef enum omb_window_kind {
+  OMB_WINDOW_RECTANGULAR = 0,
+  OMB_WINDOW_HANN = 1,
+  OMB_WINDOW_HAMMING = 2,
+  OMB_WINDOW_BLACKMAN = 3,
+  OMB_WINDOW_BLACKMAN_HARRIS = 4
+} omb_window_kind;
+
+/* util/audio/channel.rs:4-10 Channel */
+typedef enum omb_channel {
+  OMB_CHANNEL_LEFT = 0,
+  OMB_CHANNEL_RIGHT = 1,
+  OMB_CHANNEL_MID = 2,
+  OMB_CHANNEL_SIDE = 3,
+  OMB_CHANNEL_NONE = 4
+} omb_channel;
+
+/* dsp.rs:8-22 ChannelPosition, one byte per channel. Aux(n) = OMB_POS_AUX0 + n. */
+enum {
+  OMB_POS_FRONT_LEFT = 0,
+  OMB_POS_FRONT_RIGHT = 1,
+  OMB_POS_FRONT_CENTER = 2,
+  OMB_POS_LOW_FREQUENCY = 3,
+  OMB_POS_REAR_LEFT = 4,
+  OMB_POS_REAR_RIGHT = 5,
+  OMB_POS_SIDE_LEFT = 6,
+  OMB_POS_SIDE_RIGHT = 7,
+  OMB_POS_MONO = 8,
+  OMB_POS_UNKNOWN = 9,
+  OMB_POS_AUX0 = 16
+};
+
+/* spectrum/processor.rs:64-70 AveragingMode */
+typedef enum omb_averaging_mode {
+  OMB_AVG_NONE = 0,
+  OMB_AVG_EXPONENTIAL = 1, /* param = factor */
+  OMB_AVG_PEAK_HOLD = 2    /* param = decay_per_second */
+} omb_averaging_mode;
+
+/* ------------------------------------------------------------------------ */
+/* Library / device                                                          */
+/* ------------------------------------------------------------------------ */
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* omb_last_error(void);
+/* "omb200 <version> sm_100a" */
+const char* omb_version(void);
+/* Number of usable CUDA devices (0 if none; never fails). */
+int omb_device_count(void);
+/* Select the device used by handles/plans created afterwards on this thread. */
+int omb_set_device(int device);
+/* Total kernel launches issued by this library in this process (bench.py's gpu_launches). */
+uint64_t omb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* Plan set-up pieces (rows a2,a3,a5,a14,a15 of SURVEY.md §8) — host-side,    */
+/* exported so the parity tests can pin them against the oracle.              */
+/* ------------------------------------------------------------------------ */
+
+/* window.rs:20-43 — periodic cosine-sum window, f32. */
+int omb_window_coefficients(int kind, size_t len, float* out);
+/* window.rs:90-109 — out has fft_size/2+1 entries. */
+int omb_fft_bin_normalization(const float* window, size_t window_len, size_t fft_size, float* out);
+/* spectrogram/processor.rs:569-608 — derivative (dh) and time-ramp (t*h) windows. */
+int omb_reassignment_windows(const float* window, size_t len, float* derivative, float* time_weighted);
+/* spectrogram/processor.rs:111-117 */
+float omb_reassigned_power_scale(const float* window, size_t len, size_t fft_size);
+/* spectrogram/processor.rs:103-108 */
+uint16_t omb_pack_classic_db(float db);
+/* spectrum/processor.rs:410-425 */
+float omb_a_weight(float freq_hz);
+/* loudness/processor.rs:22-55 — b[5], a[5] of the 4th-order K-weighting section. */
+int omb_k_weighting_coefficients(double sample_rate, double* b, double* a);
+/* loudness/processor.rs:79-97 — factor 4: out[12*3] (tap-major), factor 2: out[24]. */
+int omb_true_peak_fir(int factor, float* out);
+/* dsp.rs:36-47 ChannelPosition::fallback(channels) -> positions[8]. */
+void omb_fallback_positions(uint32_t channels, uint8_t positions[OMB_MAX_CHANNELS]);
+/* dsp.rs:135-176 stereo fold-down matrix, out[8][2]. */
+void omb_stereo_matrix(uint32_t channels, const uint8_t positions[OMB_MAX_CHANNELS], float out[OMB_MAX_CHANNELS][2]);
+
+/* ------------------------------------------------------------------------ */
+/* AudioBlock down-mix (row a1): dsp.rs:190-257, channel.rs:12-21             */
+/* ------------------------------------------------------------------------ */
+
+/* Folds `frames` interleaved frames of `channels` channels to one projected
+ * mono lane on the GPU (host buffers in, host buffer out). Bit-exact with the
+ * reference fold order. */
+int omb_downmix_project(const float* interleaved, size_t frames, uint32_t channels,
+                        const uint8_t positions[OMB_MAX_CHANNELS], int channel /*omb_channel*/,
+                        float* out_lane);
+
+/* ------------------------------------------------------------------------ */
+/* SpectrogramProcessor (rows a4-a11)                                        */
+/* ------------------------------------------------------------------------ */
+
+/* spectrogram/processor.rs:45-56 SpectrogramConfig (defaults: 48000, 2048, 64, Hann, 0, true, 1) */
+typedef struct omb_spectrogram_config {
+  float sample_rate;
+  uint32_t window; /* omb_window_kind */
+  uint64_t fft_size;
+  uint64_t hop_size;
+  uint64_t history_length;
+  uint64_t zero_padding_factor;
+  int32_t use_reassignment;
+  int32_t _pad;
+} omb_spectrogram_config;
+
+/* spectrogram/processor.rs:37-43 SpectrogramPoint, #[repr(C)] 12 bytes */
+typedef struct omb_spectrogram_point {
+  float time_offset;
+  float freq_hz;
+  float power;
+} omb_spectrogram_point;
+
+enum { OMB_COLUMN_REASSIGNED = 0, OMB_COLUMN_CLASSIC = 1 };
+
+/* spectrogram/processor.rs:160-168 SpectrogramUpdate, flattened.
+ * Column c of a reassigned update is points[column_offsets[c] .. column_offsets[c+1])
+ * (ascending bin order); of a classic update, classic_db[c*bins .. (c+1)*bins). */
+typedef struct omb_spectrogram_update {
+  uint64_t fft_size; /* window * zero_padding_factor */
+  uint64_t hop_size;
+  uint64_t history_length;
+  float sample_rate;
+  float reassigned_power_scale;
+  int32_t reset;
+  int32_t kind; /* OMB_COLUMN_* */
+  uint32_t n_columns;
+  uint32_t bins;
+  const uint32_t* column_offsets;        /* n_columns + 1 */
+  const omb_spectrogram_point* points;   /* reassigned only */
+  const uint16_t* classic_db;            /* classic only */
+} omb_spectrogram_update;
+
+typedef struct omb_spectrogram omb_spectrogram;
+
+void omb_spectrogram_default_config(omb_spectrogram_config* out);
+/* ::new (processor.rs:188) — normalises the config, never rejects it (processor.rs:71-82). */
+int omb_spectrogram_create(const omb_spectrogram_config* cfg, omb_spectrogram** out);
+void omb_spectrogram_destroy(omb_spectrogram* h);
+/* ::config (processor.rs:208) */
+int omb_spectrogram_get_config(const omb_spectrogram* h, omb_spectrogram_config* out);
+/* ::update_config (processor.rs:518-543) */
+int omb_spectrogram_update_config(omb_spectrogram* h, const omb_spectrogram_config* cfg);
+/* ::prepare (processor.rs:219-223) */
+int omb_spectrogram_prepare(omb_spectrogram* h);
+/* ::reset_audio (processor.rs:212-217) */
+int omb_spectrogram_reset_audio(omb_spectrogram* h);
+/* ::process_block (processor.rs:490-516). `n_samples` = interleaved sample count
+ * (AudioBlock.samples.len()); positions may be NULL => ChannelPosition::fallback. */
+int omb_spectrogram_process_block(omb_spectrogram* h, const float* samples, size_t n_samples,
+                                  uint32_t channels, float sample_rate,
+                                  const uint8_t positions[OMB_MAX_CHANNELS],
+                                  omb_spectrogram_update* out);
+
+/* ------------------------------------------------------------------------ */
+/* SpectrumProcessor (rows a12-a14) + peak_bin (row f3)                      */
+/* ------------------------------------------------------------------------ */
+
+/* spectrum/processor.rs:39-51 SpectrumConfig (defaults: 48000, 16384, 1024, Hann, None, Mid, None, -100) */
+typedef struct omb_spectrum_config {
+  float sample_rate;
+  uint32_t window;          /* omb_window_kind */
+  uint64_t fft_size;
+  uint64_t hop_size;
+  uint32_t averaging;       /* omb_averaging_mode */
+  float averaging_param;    /* factor / decay_per_second */
+  uint32_t source;          /* omb_channel */
+  uint32_t secondary_source;/* omb_channel */
+  float floor_db;
+  int32_t _pad;
+} omb_spectrum_config;
+
+/* spectrum/processor.rs:33-37 SpectrumSnapshot; traces[t][0]=weighted, [t][1]=raw. */
+typedef struct omb_spectrum_snapshot {
+  uint32_t bins;
+  int32_t _pad;
+  const float* frequency_bins;
+  const float* traces[2][2];
+} omb_spectrum_snapshot;
+
+typedef struct omb_spectrum omb_spectrum;
+
+void omb_spectrum_default_config(omb_spectrum_config* out);
+int omb_spectrum_create(const omb_spectrum_config* cfg, omb_spectrum** out);       /* processor.rs:89 */
+void omb_spectrum_destroy(omb_spectrum* h);
+int omb_spectrum_get_config(const omb_spectrum* h, omb_spectrum_config* out);      /* :108 */
+int omb_spectrum_update_config(omb_spectrum* h, const omb_spectrum_config* cfg);   /* :300-322 */
+int omb_spectrum_prepare(omb_spectrum* h);                                          /* :120-124 */
+int omb_spectrum_reset_audio(omb_spectrum* h);                                      /* :112-118 */
+int omb_spectrum_process_block(omb_spectrum* h, const float* samples, size_t n_samples,
+                               uint32_t channels, float sample_rate,
+                               const uint8_t positions[OMB_MAX_CHANNELS],
+                               omb_spectrum_snapshot* out);                         /* :255-269 */
+
+/* ------------------------------------------------------------------------ */
+/* LoudnessProcessor (rows a15-a19)                                          */
+/* ------------------------------------------------------------------------ */
+
+typedef struct omb_loudness_config {
+  float sample_rate; /* default 48000 */
+  float floor_db;    /* default -99.9 */
+} omb_loudness_config;
+
+/* loudness/processor.rs:185-194 LoudnessSnapshot */
+typedef struct omb_loudness_snapshot {
+  float short_term_loudness;
+  float momentary_loudness;
+  float rms_fast_db[OMB_MAX_CHANNELS];
+  float rms_slow_db[OMB_MAX_CHANNELS];
+  float true_peak_db[OMB_MAX_CHANNELS];
+  uint32_t channel_count;
+  uint8_t positions[OMB_MAX_CHANNELS];
+} omb_loudness_snapshot;
+
+typedef struct omb_loudness omb_loudness;
+
+void omb_loudness_default_config(omb_loudness_config* out);
+int omb_loudness_create(const omb_loudness_config* cfg, omb_loudness** out);       /* processor.rs:225 */
+void omb_loudness_destroy(omb_loudness* h);
+int omb_loudness_get_config(const omb_loudness* h, omb_loudness_config* out);
+int omb_loudness_reset_audio(omb_loudness* h);                                      /* :234 */
+int omb_loudness_process_block(omb_loudness* h, const float* samples, size_t n_samples,
+                               uint32_t channels, float sample_rate,
+                               const uint8_t positions[OMB_MAX_CHANNELS],
+                               omb_loudness_snapshot* out);                         /* :253-311 */
+
+/* ------------------------------------------------------------------------ */
+/* Batched offline entry points — what the streaming calls are wrappers over. */
+/* Unit of work = (lane, frame).  `_device` variants take device pointers and */
+/* a cudaStream_t (as void*); `_host` variants take host pointers and include */
+/* the H2D / D2H copies.                                                      */
+/* ------------------------------------------------------------------------ */
+
+typedef struct omb_stft_plan omb_stft_plan;
+
+/* Columns produced for a lane of `samples` samples: processor.rs:294-299. */
+uint64_t omb_stft_frames_per_lane(const omb_spectrogram_config* cfg, uint64_t samples);
+
+/* Which kernel family a plan may use. AUTO picks the specialised sm_100a
+ * kernel when one exists for the size, else the generic one. */
+enum { OMB_KERNEL_AUTO = 0, OMB_KERNEL_GENERIC = 1, OMB_KERNEL_FAST = 2 };
+
+int omb_stft_plan_create(const omb_spectrogram_config* cfg, int kernel_choice, omb_stft_plan** out);
+void omb_stft_plan_destroy(omb_stft_plan* p);
+/* bins = fft_size*zp/2+1 */
+uint32_t omb_stft_plan_bins(const omb_stft_plan* p);
+/* 1 if the plan resolved to the specialised kernel, 0 generic. */
+int omb_stft_plan_is_fast(const omb_stft_plan* p);
+float omb_stft_plan_power_scale(const omb_stft_plan* p);
+
+/* lanes: n_lanes planar mono lanes, lane l at lanes + l*lane_stride (floats).
+ * Reassigned: out_points[(l*frames + f)*point_stride + i], i < out_counts[l*frames+f],
+ *             ascending bin; point_stride >= bins (in points).
+ * Classic:    out_classic[(l*frames + f)*bins + k].
+ * Exactly one of out_points / out_classic is used, by cfg.use_reassignment. */
+int omb_stft_execute_device(omb_stft_plan* p, const float* d_lanes, uint32_t n_lanes,
+                            uint64_t samples_per_lane, uint64_t lane_stride,
+                            omb_spectrogram_point* d_out_points, uint64_t point_stride,
+                            uint32_t* d_out_counts, uint16_t* d_out_classic, void* cuda_stream);
+int omb_stft_execute_host(omb_stft_plan* p, const float* h_lanes, uint32_t n_lanes,
+                          uint64_t samples_per_lane, uint64_t lane_stride,
+                          omb_spectrogram_point* h_out_points, uint64_t point_stride,
+                          uint32_t* h_out_counts, uint16_t* h_out_classic);
+
+typedef struct omb_spectrum_plan omb_spectrum_plan;
+
+/* Hops produced for a lane: hops = samples >= N ? (samples-N)/hop+1 : 0. */
+uint64_t omb_spectrum_hops_per_lane(const omb_spectrum_config* cfg, uint64_t samples);
+int omb_spectrum_plan_create(const omb_spectrum_config* cfg, omb_spectrum_plan** out);
+void omb_spectrum_plan_destroy(omb_spectrum_plan* p);
+/* Every lane is one trace with its own smoothing state (zero-initialised).
+ * out_weighted/out_raw: [(l*hops + h)*bins + k] f32; out_peak_bin (may be NULL):
+ * [(l*hops+h)] argmax of raw over bins 1..bins-2, last max wins (state.rs:321-325), -1 if none. */
+int omb_spectrum_execute_device(omb_spectrum_plan* p, const float* d_lanes, uint32_t n_lanes,
+                                uint64_t samples_per_lane, uint64_t lane_stride,
+                                float* d_out_weighted, float* d_out_raw, int32_t* d_out_peak_bin,
+                                void* cuda_stream);
+int omb_spectrum_execute_host(omb_spectrum_plan* p, const float* h_lanes, uint32_t n_lanes,
+                              uint64_t samples_per_lane, uint64_t lane_stride,
+                              float* h_out_weighted, float* h_out_raw, int32_t* h_out_peak_bin);
+
+typedef struct omb_loudness_plan omb_loudness_plan;
+
+int omb_loudness_plan_create(const omb_loudness_config* cfg, uint32_t channels,
+                             const uint8_t positions[OMB_MAX_CHANNELS], omb_loudness_plan** out);
+void omb_loudness_plan_destroy(omb_loudness_plan* p);
+/* n_streams interleaved streams of `frames` frames x `channels`; stream s at
+ * base + s*stream_stride (floats). One snapshot per `block_frames` frames
+ * (the process_block cadence, meter.rs:15-18): out[s*n_blocks + b],
+ * n_blocks = ceil(frames / block_frames). */
+int omb_loudness_execute_device(omb_loudness_plan* p, const float* d_interleaved, uint32_t n_streams,
+                                uint64_t frames, uint64_t stream_stride, uint64_t block_frames,
+                                omb_loudness_snapshot* d_out, void* cuda_stream);
+int omb_loudness_execute_host(omb_loudness_plan* p, const float* h_interleaved, uint32_t n_streams,
+                              uint64_t frames, uint64_t stream_stride, uint64_t block_frames,
+                              omb_loudness_snapshot* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMB200_H */
