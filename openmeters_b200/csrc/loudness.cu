@@ -1,0 +1,484 @@
+// loudness.cu — BS.1770 K-weighting, sliding mean squares and true peak (loudness/processor.rs, dsp.rs:264-371).
+//
+// Two implementations of the same arithmetic:
+//
+//  * k_loudness_stream — the streaming LoudnessProcessor::process_block: one thread per channel walks
+//    the block sample by sample with the reference's exact operation order (TDF-II in f64, Neumaier
+//    compensated window sums with periodic re-base, polyphase true-peak FIR in tap order).  A block is
+//    256-1024 frames (meter.rs:15-18), so the serial walk is microseconds; channels run in parallel.
+//
+//  * the batched plan — offline throughput path for long multi-channel streams (BASELINE cfg3).  The IIR
+//    is linear, so time is cut into 256-sample chunks: (1) zero-state end state per chunk, (2) a short
+//    serial scan propagating true chunk start states with A^256, (3) re-run each chunk from its true
+//    start state writing y (f32) and the chunk's sum of squares; window means are then sums of whole
+//    chunk sums plus two partial edges (all terms non-negative, f64: no cancellation, unlike a global
+//    prefix sum); true peak is a per-sample FIR with an 11/23-sample halo, max-reduced per block.
+#include "loudness.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace omb {
+
+double channel_weight_host(uint8_t p) {
+  switch (p) {
+    case OMB_POS_LOW_FREQUENCY: return 0.0;
+    case OMB_POS_REAR_LEFT: case OMB_POS_REAR_RIGHT: case OMB_POS_SIDE_LEFT: case OMB_POS_SIDE_RIGHT: return 1.41;
+    default: return 1.0;
+  }
+}
+
+namespace {
+
+// loudness/processor.rs:153-162 — separate mul/add roundings (Rust never contracts).
+__device__ __forceinline__ double kw_step(double x, double* s, const KWeight& kw) {
+  const double y = __dadd_rn(__dmul_rn(kw.b[0], x), s[0]);
+  s[0] = __dsub_rn(__dadd_rn(__dmul_rn(kw.b[1], x), s[1]), __dmul_rn(kw.a[1], y));
+  s[1] = __dsub_rn(__dadd_rn(__dmul_rn(kw.b[2], x), s[2]), __dmul_rn(kw.a[2], y));
+  s[2] = __dsub_rn(__dadd_rn(__dmul_rn(kw.b[3], x), s[3]), __dmul_rn(kw.a[3], y));
+  s[3] = __dsub_rn(__dmul_rn(kw.b[4], x), __dmul_rn(kw.a[4], y));
+  return y;
+}
+
+// dsp.rs:277-285 Kahan-Babuska-Neumaier
+__device__ __forceinline__ void neumaier_add(double& sum, double& corr, double v) {
+  const double next = __dadd_rn(sum, v);
+  corr = __dadd_rn(corr, fabs(sum) >= fabs(v) ? __dadd_rn(__dsub_rn(sum, next), v) : __dadd_rn(__dsub_rn(v, next), sum));
+  sum = next;
+}
+
+__device__ __forceinline__ float lufs_dev(double ms, float floor_db) {  // loudness/processor.rs:57-66
+  if (ms > 0.0) return (float)fmax(fma(log10(ms), 10.0, -0.691), (double)floor_db);
+  return floor_db;
+}
+
+__device__ __forceinline__ float power_to_db_f(float p, float floor_db) {
+  return p > 0.0f ? fmaxf(logf(p) * kLnToDb, floor_db) : floor_db;
+}
+
+__global__ void __launch_bounds__(32) k_loudness_stream(LoudStreamArgs a) {
+  const uint32_t c = threadIdx.x;
+  if (c < a.channels) {
+    LoudChannelState st = a.state[c];
+    double* ring = a.ring + (uint64_t)c * a.ring_len;
+    const uint32_t dl = a.tp_delay_len;
+    for (uint64_t f = 0; f < a.frames; ++f) {
+      const float s = a.block[f * a.channels + c];
+      if (!st.active) {  // lazy activation, loudness/processor.rs:264-274
+        if (__float_as_uint(s) == 0u) {
+          st.silent_frames += 1;
+          continue;
+        }
+        st.active = 1;
+        st.head = st.silent_frames % a.ring_len;  // WindowedMeans::with_leading_zeros, dsp.rs:359-365
+        st.count = st.silent_frames < a.ring_len ? st.silent_frames : a.ring_len;
+        for (int w = 0; w < kLoudWindows; ++w) {
+          st.refresh[w] = st.silent_frames % a.caps[w];
+          st.sums[w][0] = st.sums[w][1] = st.corr[w][0] = st.corr[w][1] = 0.0;
+        }
+        for (int i = 0; i < 4; ++i) st.filter[i] = 0.0;
+        for (int i = 0; i < 48; ++i) st.delay[i] = 0.0f;
+        st.write = dl;
+        st.peak = 0.0f;
+      }
+      const float yf = (float)kw_step((double)s, st.filter, a.kw);
+      double v = __dmul_rn((double)yf, (double)yf);
+      if (!isfinite(v)) v = 0.0;  // dsp.rs:324-333
+      // WindowedMeans::push, dsp.rs:334-357
+      for (int w = 0; w < kLoudWindows; ++w) {
+        const uint64_t cap = a.caps[w];
+        const bool has_old = st.count >= cap;
+        const double old = has_old ? ring[(st.head + a.ring_len - cap) % a.ring_len] : 0.0;
+        neumaier_add(st.sums[w][0], st.corr[w][0], v);
+        neumaier_add(st.sums[w][1], st.corr[w][1], v);
+        if (has_old) neumaier_add(st.sums[w][0], st.corr[w][0], -old);
+        if (++st.refresh[w] == cap) {  // CompensatedPair::refresh
+          st.sums[w][0] = st.sums[w][1];
+          st.sums[w][1] = 0.0;
+          st.corr[w][0] = st.corr[w][1];
+          st.corr[w][1] = 0.0;
+          st.refresh[w] = 0;
+        }
+      }
+      ring[st.head] = v;
+      st.head = (st.head + 1) % a.ring_len;
+      st.count = st.count + 1 < a.ring_len ? st.count + 1 : a.ring_len;
+      // TruePeakMeter::process, loudness/processor.rs:123-150
+      st.peak = fmaxf(st.peak, fabsf(s));
+      if (dl) {
+        st.write = (st.write == 0 ? dl : st.write) - 1;
+        const uint32_t pos = st.write;
+        st.delay[pos] = s;
+        st.delay[pos + dl] = s;
+        if (dl == 12) {
+          float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+          for (uint32_t i = 0; i < 12; ++i) {
+            const float d = st.delay[pos + i];
+            o0 = __fadd_rn(o0, __fmul_rn(d, a.fir.fir4[i][0]));
+            o1 = __fadd_rn(o1, __fmul_rn(d, a.fir.fir4[i][1]));
+            o2 = __fadd_rn(o2, __fmul_rn(d, a.fir.fir4[i][2]));
+          }
+          st.peak = fmaxf(fmaxf(fmaxf(st.peak, fabsf(o0)), fabsf(o1)), fabsf(o2));
+        } else {
+          float o = 0.0f;
+          for (uint32_t i = 0; i < 24; ++i) o = __fadd_rn(o, __fmul_rn(st.delay[pos + i], a.fir.fir2[i]));
+          st.peak = fmaxf(st.peak, fabsf(o));
+        }
+      }
+    }
+    if (st.active)
+      for (int i = 0; i < 4; ++i)
+        if (fabs(st.filter[i]) < 1.0e-30) st.filter[i] = 0.0;  // level.rs:14-18
+    a.state[c] = st;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // snapshot, loudness/processor.rs:287-310
+    omb_loudness_snapshot snap;
+    const float floor_db = a.floor_db;
+    for (int i = 0; i < OMB_MAX_CHANNELS; ++i) {
+      snap.rms_fast_db[i] = snap.rms_slow_db[i] = snap.true_peak_db[i] = floor_db;
+      snap.positions[i] = a.positions[i];
+    }
+    double wst = 0.0, wm = 0.0;
+    for (uint32_t ch = 0; ch < a.channels; ++ch) {
+      LoudChannelState& st = a.state[ch];
+      if (!st.active) continue;
+      double mean[kLoudWindows];
+      for (int w = 0; w < kLoudWindows; ++w) {
+        uint64_t n = st.count < a.caps[w] ? st.count : a.caps[w];
+        if (n < 1) n = 1;
+        mean[w] = (st.sums[w][0] + st.corr[w][0]) / (double)n;
+      }
+      wst = __dadd_rn(wst, __dmul_rn(mean[0], a.weights[ch]));
+      wm = __dadd_rn(wm, __dmul_rn(mean[1], a.weights[ch]));
+      snap.rms_fast_db[ch] = power_to_db_f((float)mean[2], floor_db);
+      snap.rms_slow_db[ch] = power_to_db_f((float)mean[3], floor_db);
+      const float peak = st.peak;
+      st.peak = 0.0f;
+      snap.true_peak_db[ch] = power_to_db_f(__fmul_rn(peak, peak), floor_db);
+    }
+    snap.short_term_loudness = lufs_dev(wst, floor_db);
+    snap.momentary_loudness = lufs_dev(wm, floor_db);
+    snap.channel_count = a.channels;
+    *a.out = snap;
+  }
+}
+
+// ---------------------------------------------------------------------------------- batched
+struct LoudBatchArgs {
+  const float* in;       // [stream][frame][channel]
+  uint64_t stream_stride, frames, n_chunks, block_frames, n_blocks;
+  uint32_t n_streams, channels, tp_delay_len;
+  KWeight kw;
+  double M[16];
+  double* end_state;     // [stream][chunk][channel][4]  zero-state end states
+  double* start_state;   // [stream][chunk][channel][4]  true start states
+  float* y;              // [stream][channel][frame]
+  double* csum;          // [stream][channel][chunk]
+  unsigned* peak;        // [stream][block][channel]  float bits (non-negative)
+  uint64_t caps[kLoudWindows];
+  double weights[OMB_MAX_CHANNELS];
+  uint8_t positions[OMB_MAX_CHANNELS];
+  float floor_db;
+  omb_loudness_snapshot* out;  // [stream][block]
+};
+
+// (1)/(3): one thread per (stream, chunk, channel); channel fastest so a warp reads whole frames.
+template <bool kApply>
+__global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = (uint64_t)a.n_streams * a.n_chunks * a.channels;
+  if (idx >= total) return;
+  const uint32_t c = (uint32_t)(idx % a.channels);
+  const uint64_t chunk = (idx / a.channels) % a.n_chunks;
+  const uint64_t stream = idx / ((uint64_t)a.channels * a.n_chunks);
+  const float* x = a.in + stream * a.stream_stride;
+  const uint64_t t0 = chunk * kKwChunk;
+  const uint64_t t1 = t0 + kKwChunk < a.frames ? t0 + kKwChunk : a.frames;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  const uint64_t sidx = ((stream * a.n_chunks + chunk) * a.channels + c) * 4;
+  if (kApply) {
+    s[0] = a.start_state[sidx + 0];
+    s[1] = a.start_state[sidx + 1];
+    s[2] = a.start_state[sidx + 2];
+    s[3] = a.start_state[sidx + 3];
+  }
+  float* y = kApply ? a.y + (stream * a.channels + c) * a.frames : nullptr;
+  double acc = 0.0;
+  for (uint64_t t = t0; t < t1; ++t) {
+    const double yy = kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
+    if (kApply) {
+      const float yf = (float)yy;
+      y[t] = yf;
+      const double v = (double)yf * (double)yf;
+      acc += isfinite(v) ? v : 0.0;
+    }
+  }
+  if (kApply) {
+    a.csum[(stream * a.channels + c) * a.n_chunks + chunk] = acc;
+  } else {
+    // a short final chunk still has to be advanced to a full chunk boundary? No: nothing follows it.
+    a.end_state[sidx + 0] = s[0];
+    a.end_state[sidx + 1] = s[1];
+    a.end_state[sidx + 2] = s[2];
+    a.end_state[sidx + 3] = s[3];
+  }
+}
+
+// (2): serial scan over chunks, one thread per (stream, channel): start[k+1] = M * start[k] + end0[k].
+__global__ void __launch_bounds__(64) k_kw_scan(LoudBatchArgs a) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint64_t)a.n_streams * a.channels) return;
+  const uint32_t c = (uint32_t)(idx % a.channels);
+  const uint64_t stream = idx / a.channels;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (uint64_t k = 0; k < a.n_chunks; ++k) {
+    const uint64_t sidx = ((stream * a.n_chunks + k) * a.channels + c) * 4;
+    a.start_state[sidx + 0] = s[0];
+    a.start_state[sidx + 1] = s[1];
+    a.start_state[sidx + 2] = s[2];
+    a.start_state[sidx + 3] = s[3];
+    double n[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      n[r] = a.M[r * 4 + 0] * s[0] + a.M[r * 4 + 1] * s[1] + a.M[r * 4 + 2] * s[2] + a.M[r * 4 + 3] * s[3] + a.end_state[sidx + r];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s[r] = n[r];
+  }
+}
+
+// true peak: one thread per frame of a (stream, block); all channels in the thread; warp max -> atomicMax.
+__global__ void __launch_bounds__(256) k_true_peak(LoudBatchArgs a, TruePeakFir fir) {
+  const uint64_t sb = blockIdx.x;  // stream * n_blocks + block
+  const uint64_t stream = sb / a.n_blocks, blk = sb % a.n_blocks;
+  const float* x = a.in + stream * a.stream_stride;
+  const uint64_t f0 = blk * a.block_frames;
+  const uint64_t f1 = f0 + a.block_frames < a.frames ? f0 + a.block_frames : a.frames;
+  const int lane = threadIdx.x & 31;
+  const int C = (int)a.channels;
+  for (uint64_t base = f0 + (uint64_t)blockIdx.y * blockDim.x; base < f1; base += (uint64_t)gridDim.y * blockDim.x) {
+    const uint64_t t = base + threadIdx.x;
+    for (int c = 0; c < C; ++c) {
+      float pk = 0.0f;
+      if (t < f1) {
+        pk = fabsf(__ldg(&x[t * C + c]));
+        if (a.tp_delay_len == 12) {
+          float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {  // delay[pos+i] == x[t-i], zeros before the stream start
+            const float d = t >= (uint64_t)i ? __ldg(&x[(t - i) * C + c]) : 0.0f;
+            o0 = __fadd_rn(o0, __fmul_rn(d, fir.fir4[i][0]));
+            o1 = __fadd_rn(o1, __fmul_rn(d, fir.fir4[i][1]));
+            o2 = __fadd_rn(o2, __fmul_rn(d, fir.fir4[i][2]));
+          }
+          pk = fmaxf(fmaxf(fmaxf(pk, fabsf(o0)), fabsf(o1)), fabsf(o2));
+        } else if (a.tp_delay_len == 24) {
+          float o = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 24; ++i) {
+            const float d = t >= (uint64_t)i ? __ldg(&x[(t - i) * C + c]) : 0.0f;
+            o = __fadd_rn(o, __fmul_rn(d, fir.fir2[i]));
+          }
+          pk = fmaxf(pk, fabsf(o));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+      // NaN input: fmaxf drops NaN exactly like Rust's f32::max in TruePeakMeter::process.
+      if (lane == 0) atomicMax(&a.peak[sb * C + c], __float_as_uint(pk));
+    }
+  }
+}
+
+// Sum of y^2 over frames [t0, t1) of one (stream, channel): whole chunk sums + two partial edges.
+__device__ double window_sum(const LoudBatchArgs& a, uint64_t stream, uint32_t c, uint64_t t0, uint64_t t1) {
+  if (t1 <= t0) return 0.0;
+  const float* y = a.y + (stream * a.channels + c) * a.frames;
+  const double* cs = a.csum + (stream * a.channels + c) * a.n_chunks;
+  const uint64_t k0 = (t0 + kKwChunk - 1) / kKwChunk;  // first chunk fully inside
+  const uint64_t k1 = t1 / kKwChunk;                   // one past the last chunk fully inside
+  double acc = 0.0;
+  if (k0 >= k1) {  // no whole chunk inside
+    for (uint64_t t = t0; t < t1; ++t) {
+      const double v = (double)y[t] * (double)y[t];
+      acc += isfinite(v) ? v : 0.0;
+    }
+    return acc;
+  }
+  for (uint64_t t = t0; t < k0 * kKwChunk; ++t) {
+    const double v = (double)y[t] * (double)y[t];
+    acc += isfinite(v) ? v : 0.0;
+  }
+  for (uint64_t k = k0; k < k1; ++k) acc += cs[k];
+  for (uint64_t t = k1 * kKwChunk; t < t1; ++t) {
+    const double v = (double)y[t] * (double)y[t];
+    acc += isfinite(v) ? v : 0.0;
+  }
+  return acc;
+}
+
+// One warp per snapshot: lane = channel*4 + window computes one sliding mean; lane 0 assembles.
+__global__ void __launch_bounds__(128) k_loud_snapshots(LoudBatchArgs a) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint64_t total = (uint64_t)a.n_streams * a.n_blocks;
+  const bool live = warp < total;
+  const uint64_t stream = live ? warp / a.n_blocks : 0, blk = live ? warp % a.n_blocks : 0;
+  const uint64_t t_end = (blk + 1) * a.block_frames < a.frames ? (blk + 1) * a.block_frames : a.frames;
+  const uint32_t c = (uint32_t)(lane >> 2);
+  const int w = lane & 3;
+  double mean = 0.0;
+  if (live && c < a.channels) {
+    // divisor: min(count, cap) with count = frames seen since the stream start (leading silence counts,
+    // dsp.rs:359-370), at least 1
+    uint64_t n = t_end < a.caps[w] ? t_end : a.caps[w];
+    if (n < 1) n = 1;
+    const uint64_t t0 = t_end > a.caps[w] ? t_end - a.caps[w] : 0;
+    mean = window_sum(a, stream, c, t0, t_end) / (double)n;
+  }
+  // gather the 4 means of every channel to lane 0
+  double m[OMB_MAX_CHANNELS][kLoudWindows];
+#pragma unroll
+  for (int ch = 0; ch < OMB_MAX_CHANNELS; ++ch)
+#pragma unroll
+    for (int ww = 0; ww < kLoudWindows; ++ww) m[ch][ww] = __shfl_sync(0xffffffffu, mean, ch * 4 + ww);
+  if (live && lane == 0) {
+    omb_loudness_snapshot snap;
+    const float floor_db = a.floor_db;
+    double wst = 0.0, wm = 0.0;
+    for (int ch = 0; ch < OMB_MAX_CHANNELS; ++ch) {
+      snap.rms_fast_db[ch] = snap.rms_slow_db[ch] = snap.true_peak_db[ch] = floor_db;
+      snap.positions[ch] = a.positions[ch];
+      if (ch < (int)a.channels) {
+        wst += m[ch][0] * a.weights[ch];
+        wm += m[ch][1] * a.weights[ch];
+        snap.rms_fast_db[ch] = power_to_db_f((float)m[ch][2], floor_db);
+        snap.rms_slow_db[ch] = power_to_db_f((float)m[ch][3], floor_db);
+        const float peak = __uint_as_float(a.peak[warp * a.channels + ch]);
+        snap.true_peak_db[ch] = power_to_db_f(__fmul_rn(peak, peak), floor_db);
+      }
+    }
+    snap.short_term_loudness = lufs_dev(wst, floor_db);
+    snap.momentary_loudness = lufs_dev(wm, floor_db);
+    snap.channel_count = a.channels;
+    a.out[warp] = snap;
+  }
+}
+
+void mat4_mul(const long double* A, const long double* B, long double* C) {
+  long double t[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      long double acc = 0;
+      for (int k = 0; k < 4; ++k) acc += A[r * 4 + k] * B[k * 4 + c];
+      t[r * 4 + c] = acc;
+    }
+  for (int i = 0; i < 16; ++i) C[i] = t[i];
+}
+
+}  // namespace
+
+int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s) {
+  OMB_LAUNCH(k_loudness_stream, dim3(1), dim3(32), 0, s, a);
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+LoudnessPlan::~LoudnessPlan() {
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int LoudnessPlan::init(const omb_loudness_config& c, uint32_t ch, const uint8_t* pos) {
+  cfg = c;
+  OMB_TRY(current_device(&dev));
+  sample_rate = sanitize_sample_rate(c.sample_rate);
+  channels = std::min<uint32_t>(std::max<uint32_t>(ch, 1), OMB_MAX_CHANNELS);
+  if (pos) std::memcpy(positions, pos, OMB_MAX_CHANNELS);
+  else fallback_positions_host(channels, positions);
+  k_weighting_host((double)sample_rate, kw.b, kw.a);
+  true_peak_fir4_host(fir.fir4);
+  true_peak_fir2_host(fir.fir2);
+  static const float kWindows[kLoudWindows] = {3.0f, 0.4f, 0.3f, 1.0f};  // loudness/processor.rs:13
+  for (int w = 0; w < kLoudWindows; ++w) caps[w] = std::max<uint64_t>(loudness_window_length(sample_rate, kWindows[w]), 1);
+  tp_delay_len = (double)sample_rate < 96000.0 ? 12 : ((double)sample_rate < 192000.0 ? 24 : 0);
+  // zero-input state transition of the TDF-II section, raised to the chunk length (kKwChunk = 2^8)
+  long double A[16] = {-(long double)kw.a[1], 1, 0, 0, -(long double)kw.a[2], 0, 1, 0, -(long double)kw.a[3], 0, 0, 1, -(long double)kw.a[4], 0, 0, 0};
+  static_assert(kKwChunk == 256, "chunk matrix uses 8 squarings");
+  for (int i = 0; i < 8; ++i) mat4_mul(A, A, A);
+  for (int i = 0; i < 16; ++i) chunk_matrix[i] = (double)A[i];
+  OMB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  return OMB_OK;
+}
+
+int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams, uint64_t frames, uint64_t stream_stride,
+                                 uint64_t block_frames, omb_loudness_snapshot* d_out_snap, cudaStream_t s) {
+  if (!n_streams || !frames) return OMB_OK;
+  if (!d_interleaved || !d_out_snap || block_frames == 0) return fail(OMB_ERR_INVALID, "invalid argument");
+  LoudBatchArgs a{};
+  a.in = d_interleaved;
+  a.stream_stride = stream_stride;
+  a.frames = frames;
+  a.n_chunks = (frames + kKwChunk - 1) / kKwChunk;
+  a.block_frames = block_frames;
+  a.n_blocks = (frames + block_frames - 1) / block_frames;
+  a.n_streams = n_streams;
+  a.channels = channels;
+  a.tp_delay_len = tp_delay_len;
+  a.kw = kw;
+  std::memcpy(a.M, chunk_matrix, sizeof a.M);
+  const uint64_t n_state = (uint64_t)n_streams * a.n_chunks * channels * 4;
+  OMB_TRY(d_end.reserve((size_t)n_state));
+  OMB_TRY(d_start.reserve((size_t)n_state));
+  OMB_TRY(d_y.reserve((size_t)((uint64_t)n_streams * channels * frames)));
+  OMB_TRY(d_csum.reserve((size_t)((uint64_t)n_streams * channels * a.n_chunks)));
+  OMB_TRY(d_peak.reserve((size_t)((uint64_t)n_streams * a.n_blocks * channels)));
+  a.end_state = d_end.ptr;
+  a.start_state = d_start.ptr;
+  a.y = d_y.ptr;
+  a.csum = d_csum.ptr;
+  a.peak = d_peak.ptr;
+  for (int w = 0; w < kLoudWindows; ++w) a.caps[w] = caps[w];
+  for (uint32_t c = 0; c < OMB_MAX_CHANNELS; ++c) {
+    a.weights[c] = channel_weight_host(positions[c]);
+    a.positions[c] = positions[c];
+  }
+  a.floor_db = cfg.floor_db;
+  a.out = d_out_snap;
+  OMB_CUDA_TRY(cudaMemsetAsync(d_peak.ptr, 0, sizeof(unsigned) * n_streams * a.n_blocks * channels, s));
+
+  const uint64_t n_items = (uint64_t)n_streams * a.n_chunks * channels;
+  const unsigned g1 = (unsigned)((n_items + 127) / 128);
+  auto k_zero = k_kw_chunks<false>;
+  auto k_apply = k_kw_chunks<true>;
+  OMB_LAUNCH(k_zero, dim3(g1), dim3(128), 0, s, a);
+  OMB_CHECK_LAUNCH();
+  OMB_LAUNCH(k_kw_scan, dim3((unsigned)(((uint64_t)n_streams * channels + 63) / 64)), dim3(64), 0, s, a);
+  OMB_CHECK_LAUNCH();
+  OMB_LAUNCH(k_apply, dim3(g1), dim3(128), 0, s, a);
+  OMB_CHECK_LAUNCH();
+  const unsigned gx = (unsigned)std::min<uint64_t>((block_frames + 255) / 256, 64);
+  OMB_LAUNCH(k_true_peak, dim3((unsigned)((uint64_t)n_streams * a.n_blocks), gx), dim3(256), 0, s, a, fir);
+  OMB_CHECK_LAUNCH();
+  const uint64_t n_snap = (uint64_t)n_streams * a.n_blocks;
+  OMB_LAUNCH(k_loud_snapshots, dim3((unsigned)((n_snap * 32 + 127) / 128)), dim3(128), 0, s, a);
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+int LoudnessPlan::execute_host(const float* h_interleaved, uint32_t n_streams, uint64_t frames, uint64_t stream_stride,
+                               uint64_t block_frames, omb_loudness_snapshot* h_out) {
+  if (!n_streams || !frames) return OMB_OK;
+  if (!h_interleaved || !h_out || block_frames == 0) return fail(OMB_ERR_INVALID, "invalid argument");
+  const uint64_t per = frames * channels;
+  OMB_TRY(d_in.reserve((size_t)(per * n_streams)));
+  for (uint32_t i = 0; i < n_streams; ++i)
+    OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + i * per, h_interleaved + i * stream_stride, sizeof(float) * per, cudaMemcpyHostToDevice, stream));
+  const uint64_t n_blocks = (frames + block_frames - 1) / block_frames;
+  OMB_TRY(d_out.reserve((size_t)(n_blocks * n_streams)));
+  OMB_TRY(execute_device(d_in.ptr, n_streams, frames, per, block_frames, d_out.ptr, stream));
+  OMB_CUDA_TRY(cudaMemcpyAsync(h_out, d_out.ptr, sizeof(omb_loudness_snapshot) * n_blocks * n_streams, cudaMemcpyDeviceToHost, stream));
+  OMB_CUDA_TRY(cudaStreamSynchronize(stream));
+  return OMB_OK;
+}
+
+}  // namespace omb

@@ -1,0 +1,82 @@
+// loudness.h — BS.1770 K-weighted loudness / true-peak.
+#pragma once
+#include "common.h"
+#include "tables.h"
+
+namespace omb {
+
+constexpr int kLoudWindows = 4;        // short-term 3 s, momentary 0.4 s, rms fast 0.3 s, rms slow 1 s
+constexpr int kKwChunk = 256;          // samples per chunk of the chunk-parallel IIR
+
+struct KWeight { double b[5], a[5]; };
+struct TruePeakFir { float fir4[12][3]; float fir2[24]; };
+
+// ---- streaming (exact, sequential per channel) state, one per channel, device resident
+struct LoudChannelState {
+  double filter[4];
+  double sums[kLoudWindows][2];
+  double corr[kLoudWindows][2];
+  unsigned long long refresh[kLoudWindows];
+  unsigned long long head, count;        // WindowedMeans ring cursor / fill (dsp.rs:298-305)
+  unsigned long long silent_frames;
+  float delay[48];
+  unsigned int write;
+  float peak;
+  int active;
+  int _pad;
+};
+
+struct LoudStreamArgs {
+  const float* block;                    // interleaved [frames][channels]
+  uint64_t frames;
+  uint32_t channels;
+  LoudChannelState* state;               // [channels]
+  double* ring;                          // [channels][ring_len] squared K-weighted samples
+  uint64_t ring_len;                     // longest window
+  uint64_t caps[kLoudWindows];
+  uint32_t tp_delay_len;                 // 12 (4x), 24 (2x) or 0
+  KWeight kw;
+  TruePeakFir fir;
+  float floor_db;
+  double weights[OMB_MAX_CHANNELS];      // channel_weight(position)
+  uint8_t positions[OMB_MAX_CHANNELS];
+  omb_loudness_snapshot* out;
+};
+
+struct LoudnessStreamCore {              // device objects behind omb_loudness (stream_loudness.cu)
+  DeviceBuffer<LoudChannelState> d_state;
+  DeviceBuffer<double> d_ring;
+  DeviceBuffer<float> d_block;
+  DeviceBuffer<omb_loudness_snapshot> d_snap;
+};
+int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s);
+
+// ---- batched plan
+struct LoudnessPlan {
+  omb_loudness_config cfg;
+  float sample_rate = kDefaultSampleRate;
+  uint32_t channels = 0;
+  uint8_t positions[OMB_MAX_CHANNELS];
+  DeviceInfo dev;
+  KWeight kw;
+  TruePeakFir fir;
+  double chunk_matrix[16];               // A^kKwChunk, row-major (state transition over one chunk)
+  uint64_t caps[kLoudWindows];
+  uint32_t tp_delay_len = 0;
+  DeviceBuffer<double> d_end, d_start, d_csum, d_cbase;
+  DeviceBuffer<float> d_y;
+  DeviceBuffer<unsigned> d_peak;
+  DeviceBuffer<float> d_in;
+  DeviceBuffer<omb_loudness_snapshot> d_out;
+  cudaStream_t stream = nullptr;
+  ~LoudnessPlan();
+  int init(const omb_loudness_config& c, uint32_t channels, const uint8_t* positions);
+  int execute_device(const float* d_interleaved, uint32_t n_streams, uint64_t frames, uint64_t stream_stride, uint64_t block_frames,
+                     omb_loudness_snapshot* d_out, cudaStream_t s);
+  int execute_host(const float* h_interleaved, uint32_t n_streams, uint64_t frames, uint64_t stream_stride, uint64_t block_frames,
+                   omb_loudness_snapshot* h_out);
+};
+
+double channel_weight_host(uint8_t position);  // loudness/processor.rs:174-183
+
+}  // namespace omb

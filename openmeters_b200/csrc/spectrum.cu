@@ -1,0 +1,318 @@
+// spectrum.cu — spectrum-analyzer kernels and plan (spectrum/processor.rs:179-253,332-425; state.rs:321-325).
+//
+//   k_spectrum_power_generic : per (lane, hop) CTA — DC-remove + window -> FFT -> |X|^2 * norm      (rows a4, a12)
+//   k_spectrum_smooth        : per (lane, bin) thread, sequential over hops — None / Exponential /
+//                              PeakHold smoothing, state floor, raw + A-weighted dB, fused arg-max      (rows a13, f3)
+//
+// The smoothing recurrence is sequential in time per bin, parallel over (lane, bin): coalesced over
+// bins, HBM-bound (4 B in, 8 B out per bin-hop).  Hops are processed in chunks sized so the power
+// scratch written by the first kernel is still L2-resident when the second one reads it.
+#include "device_math.cuh"
+#include "spectrum.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace omb {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ void block_fft_radix2_sp(float2* data, int n, int logn, const float2* __restrict__ tw) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (n <= 1) return;
+  for (int i = tid; i < n; i += nt) {
+    const int j = (int)(__brev((unsigned)i) >> (32 - logn));
+    if (i < j) {
+      const float2 a = data[i], b = data[j];
+      data[i] = b;
+      data[j] = a;
+    }
+  }
+  __syncthreads();
+  for (int s = 1; s <= logn; ++s) {
+    const int half = 1 << (s - 1), step = n >> s;
+    for (int i = tid; i < (n >> 1); i += nt) {
+      const int k = i & (half - 1);
+      const int base = ((i >> (s - 1)) << s) + k;
+      const float2 w = __ldg(&tw[k * step]);
+      const float2 a = data[base], b = data[base + half];
+      const float2 t = cmul(b, w);
+      data[base] = cadd(a, t);
+      data[base + half] = csub(a, t);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_spectrum_power_generic(SpectrumPowerArgs a) {
+  __shared__ float red[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  float2* work = a.scratch + (uint64_t)blockIdx.x * a.scratch_stride;
+  const uint64_t total = a.hops * a.n_lanes;
+  const int N = (int)a.fft_size;
+  for (uint64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const uint64_t lane = item / a.hops, h = item % a.hops;
+    const float* x = a.lanes + lane * a.lane_stride + h * a.hop;
+    float part = 0.0f;
+    for (int i = tid; i < N; i += nt) part += __ldg(&x[i]);
+    const float mean = block_sum(part, red) / (float)N;
+    for (int i = tid; i < N; i += nt) work[i] = make_float2((__ldg(&x[i]) - mean) * __ldg(&a.win[i]), 0.0f);
+    __syncthreads();
+    block_fft_radix2_sp(work, N, (int)a.log2_fft, a.tw);
+    float* out = a.power + item * a.bins;
+    for (int k = tid; k < (int)a.bins; k += nt) {
+      const float2 z = work[k];
+      out[k] = (z.x * z.x + z.y * z.y) * __ldg(&a.bin_norm[k]);
+    }
+    __syncthreads();
+  }
+}
+
+// Monotone map float -> uint so that unsigned compare == float compare (finite values).
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct SmoothLayout {
+  uint64_t out_hops_total, out_hop0;  // where this chunk's hops land in the caller's [lane][hop][bin] arrays
+};
+
+__global__ void __launch_bounds__(kThreads) k_spectrum_smooth(SpectrumSmoothArgs a, SmoothLayout lay) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = blockIdx.y;
+  const bool live = k < (int)a.bins;
+  const int lane_id = threadIdx.x & 31;
+  float st = 0.0f;
+  if (live && a.state && a.mode != OMB_AVG_NONE) st = a.state[(uint64_t)lane * a.bins + k];
+  const float aw = live ? __ldg(&a.a_db[k]) : 0.0f;
+  const float one_minus_alpha = __fsub_rn(1.0f, a.alpha);
+  for (uint64_t h = 0; h < a.hops; ++h) {
+    float raw = a.floor_db, weighted = a.floor_db;
+    if (live) {
+      const float p = __ldg(&a.power[((uint64_t)lane * a.hops + h) * a.bins + k]);
+      float v = p;
+      if (a.mode == OMB_AVG_EXPONENTIAL) {  // spectrum/processor.rs:366-377 (re-seed when the average hit zero)
+        st = st <= 0.0f ? p : __fadd_rn(__fmul_rn(st, a.alpha), __fmul_rn(p, one_minus_alpha));
+        if (st < a.state_floor) st = 0.0f;
+        v = st;
+      } else if (a.mode == OMB_AVG_PEAK_HOLD) {  // :380-388
+        st = fmaxf(__fmul_rn(st, a.decay), p);
+        if (st < a.state_floor) st = 0.0f;
+        v = st;
+      }
+      if (!(v < a.state_floor)) {  // :392-401
+        const float db = __fmul_rn(logf(v), kLnToDb);
+        raw = fmaxf(db, a.floor_db);
+        weighted = fmaxf(__fadd_rn(db, aw), a.floor_db);
+      }
+      const uint64_t o = a.write_all ? (((uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h) * a.bins + k)
+                                     : ((uint64_t)lane * a.bins + k);
+      if (a.write_all || h + 1 == a.hops) {
+        a.out_weighted[o] = weighted;
+        a.out_raw[o] = raw;
+      }
+    }
+    if (a.peak_keys) {  // spectrum/state.rs:321-325: bins 1..len-2, finite, last maximum wins
+      unsigned long long key = 0ull;
+      if (live && k >= 1 && k + 1 < (int)a.bins && isfinite(raw))
+        key = ((unsigned long long)ordered_bits(raw) << 32) | (unsigned)k;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      if (lane_id == 0 && key) atomicMax(&a.peak_keys[(uint64_t)lane * a.hops + h], key);
+    }
+  }
+  if (live && a.state && a.mode != OMB_AVG_NONE) a.state[(uint64_t)lane * a.bins + k] = st;
+}
+
+__global__ void k_peak_keys_to_bins(const unsigned long long* keys, uint32_t n_lanes, uint64_t hops, uint64_t hops_total,
+                                    uint64_t hop0, int32_t* out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hops * n_lanes) return;
+  const uint64_t lane = i / hops, h = i % hops;
+  const unsigned long long key = keys[i];
+  out[lane * hops_total + hop0 + h] = key ? (int32_t)(key & 0xffffffffu) : -1;
+}
+
+}  // namespace
+
+SpectrumConfigN SpectrumConfigN::from_c(const omb_spectrum_config& c) {
+  SpectrumConfigN o;
+  o.sample_rate = sanitize_sample_rate(c.sample_rate);
+  o.window_kind = c.window <= OMB_WINDOW_BLACKMAN_HARRIS ? c.window : (uint32_t)OMB_WINDOW_RECTANGULAR;
+  o.fft_size = std::max<uint64_t>(c.fft_size, 1);
+  o.hop = c.hop_size == 0 ? std::max<uint64_t>(o.fft_size / 16, 1) : c.hop_size;
+  o.averaging = c.averaging <= OMB_AVG_PEAK_HOLD ? c.averaging : (uint32_t)OMB_AVG_NONE;
+  o.averaging_param = c.averaging_param;
+  o.source = c.source <= OMB_CHANNEL_NONE ? c.source : (uint32_t)OMB_CHANNEL_NONE;
+  o.secondary = c.secondary_source <= OMB_CHANNEL_NONE ? c.secondary_source : (uint32_t)OMB_CHANNEL_NONE;
+  o.floor_db = sanitize_negative_db(c.floor_db, -100.0f);
+  return o;
+}
+
+void SpectrumConfigN::to_c(omb_spectrum_config* out) const {
+  std::memset(out, 0, sizeof *out);
+  out->sample_rate = sample_rate;
+  out->window = window_kind;
+  out->fft_size = fft_size;
+  out->hop_size = hop;
+  out->averaging = averaging;
+  out->averaging_param = averaging_param;
+  out->source = source;
+  out->secondary_source = secondary;
+  out->floor_db = floor_db;
+}
+
+SpectrumPlan::~SpectrumPlan() {
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int SpectrumPlan::init(const omb_spectrum_config& c) {
+  cfg = SpectrumConfigN::from_c(c);
+  OMB_TRY(current_device(&dev));
+  const uint64_t N = cfg.fft_size;
+  if (!is_pow2(N) || N > (1ull << 24))
+    return fail(OMB_ERR_UNSUPPORTED, "spectrum fft_size %llu: only power-of-two lengths have kernels (no CPU fallback)", (unsigned long long)N);
+  h_win = make_window((int)cfg.window_kind, (size_t)N);
+  h_norm = make_bin_norm(h_win.data(), (size_t)N, (size_t)N);
+  const size_t bins = (size_t)cfg.bins();
+  const float bin_hz = cfg.sample_rate / (float)N;  // spectrum/processor.rs:138-146
+  h_freq.resize(bins);
+  h_adb.resize(bins);
+  for (size_t b = 0; b < bins; ++b) {
+    h_freq[b] = (float)b * bin_hz;
+    h_adb[b] = a_weight_host(h_freq[b]);
+  }
+  state_floor = smoothing_state_floor_host(h_adb, cfg.floor_db);
+  OMB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  OMB_TRY(d_win.upload(h_win, stream));
+  OMB_TRY(d_norm.upload(h_norm, stream));
+  OMB_TRY(d_adb.upload(h_adb, stream));
+  OMB_TRY(d_tw.upload(make_twiddles((size_t)N, (size_t)std::max<uint64_t>(N / 2, 1)), stream));
+  OMB_CUDA_TRY(cudaStreamSynchronize(stream));
+  return OMB_OK;
+}
+
+int SpectrumPlan::power_device(const float* d_lanes, uint32_t n_lanes, uint64_t hops, uint64_t lane_stride, float* d_power_out,
+                               cudaStream_t s) {
+  const uint64_t total = hops * n_lanes;
+  if (!total) return OMB_OK;
+  SpectrumPowerArgs a{};
+  a.lanes = d_lanes;
+  a.lane_stride = lane_stride;
+  a.n_lanes = n_lanes;
+  a.hops = hops;
+  a.fft_size = (uint32_t)cfg.fft_size;
+  a.hop = (uint32_t)cfg.hop;
+  a.bins = (uint32_t)cfg.bins();
+  a.log2_fft = (uint32_t)ilog2(cfg.fft_size);
+  a.win = d_win.ptr;
+  a.bin_norm = d_norm.ptr;
+  a.tw = d_tw.ptr;
+  a.power = d_power_out;
+  const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(dev.sm_count, 1) * 4);
+  a.scratch_stride = cfg.fft_size;
+  OMB_TRY(d_scratch.reserve((size_t)(a.scratch_stride * grid)));
+  a.scratch = d_scratch.ptr;
+  OMB_LAUNCH(k_spectrum_power_generic, dim3(grid), dim3(kThreads), 0, s, a);
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+static int smooth_launch(SpectrumPlan& p, const float* d_power_in, uint32_t n_lanes, uint64_t hops, float* d_state, float* d_weighted,
+                         float* d_raw, int32_t* d_peak_bin, bool write_all, uint64_t hops_total, uint64_t hop0, cudaStream_t s) {
+  if (!hops || !n_lanes) return OMB_OK;
+  const SpectrumConfigN& cfg = p.cfg;
+  SpectrumSmoothArgs a{};
+  a.power = d_power_in;
+  a.n_lanes = n_lanes;
+  a.hops = hops;
+  a.bins = (uint32_t)cfg.bins();
+  a.mode = (int)cfg.averaging;
+  a.alpha = std::min(std::max(cfg.averaging_param, 0.0f), 0.9999f);
+  const float dt = (float)cfg.hop / cfg.sample_rate;  // spectrum/processor.rs:184
+  a.decay = db_to_power_host(-std::fmax(cfg.averaging_param, 0.0f) * dt);
+  a.state_floor = p.state_floor;
+  a.floor_db = cfg.floor_db;
+  a.a_db = p.d_adb.ptr;
+  a.state = d_state;
+  a.out_weighted = d_weighted;
+  a.out_raw = d_raw;
+  a.write_all = write_all ? 1 : 0;
+  a.peak_keys = nullptr;
+  if (d_peak_bin && !write_all) return fail(OMB_ERR_INVALID, "peak bins are only produced together with per-hop outputs");
+  if (d_peak_bin) {
+    OMB_TRY(p.d_keys.reserve((size_t)(hops * n_lanes)));
+    OMB_CUDA_TRY(cudaMemsetAsync(p.d_keys.ptr, 0, sizeof(unsigned long long) * hops * n_lanes, s));
+    a.peak_keys = p.d_keys.ptr;
+  }
+  SmoothLayout lay{hops_total, hop0};
+  const dim3 grid((unsigned)((a.bins + kThreads - 1) / kThreads), n_lanes);
+  OMB_LAUNCH(k_spectrum_smooth, grid, dim3(kThreads), 0, s, a, lay);
+  OMB_CHECK_LAUNCH();
+  if (d_peak_bin) {
+    const uint64_t n = hops * n_lanes;
+    OMB_LAUNCH(k_peak_keys_to_bins, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p.d_keys.ptr, n_lanes, hops, hops_total, hop0,
+               d_peak_bin);
+    OMB_CHECK_LAUNCH();
+  }
+  return OMB_OK;
+}
+
+int SpectrumPlan::smooth_device(const float* d_power_in, uint32_t n_lanes, uint64_t hops, float* d_state_io, float* d_weighted,
+                                float* d_raw, int32_t* d_peak_bin, bool write_all, cudaStream_t s) {
+  return smooth_launch(*this, d_power_in, n_lanes, hops, d_state_io, d_weighted, d_raw, d_peak_bin, write_all, hops, 0, s);
+}
+
+int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
+                                 float* d_weighted, float* d_raw, int32_t* d_peak_bin, cudaStream_t s) {
+  const uint64_t hops = cfg.hops_for(samples_per_lane);
+  if (!hops || !n_lanes) return OMB_OK;
+  if (!d_lanes || !d_weighted || !d_raw) return fail(OMB_ERR_INVALID, "null argument");
+  const uint64_t bins = cfg.bins();
+  // chunk of hops whose power scratch (n_lanes*chunk*bins*4 B) stays comfortably inside the 126 MB L2
+  const uint64_t budget_floats = (48ull << 20) / 4;
+  uint64_t chunk = std::max<uint64_t>(1, budget_floats / std::max<uint64_t>(1, (uint64_t)n_lanes * bins));
+  chunk = std::min(chunk, hops);
+  OMB_TRY(d_power.reserve((size_t)((uint64_t)n_lanes * chunk * bins)));
+  float* state = nullptr;
+  if (cfg.averaging != OMB_AVG_NONE) {
+    OMB_TRY(d_state.reserve((size_t)((uint64_t)n_lanes * bins)));
+    OMB_CUDA_TRY(cudaMemsetAsync(d_state.ptr, 0, sizeof(float) * n_lanes * bins, s));
+    state = d_state.ptr;
+  }
+  for (uint64_t h0 = 0; h0 < hops; h0 += chunk) {
+    const uint64_t n = std::min(chunk, hops - h0);
+    OMB_TRY(power_device(d_lanes + h0 * cfg.hop, n_lanes, n, lane_stride, d_power.ptr, s));
+    OMB_TRY(smooth_launch(*this, d_power.ptr, n_lanes, n, state, d_weighted, d_raw, d_peak_bin, true, hops, h0, s));
+  }
+  return OMB_OK;
+}
+
+int SpectrumPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
+                               float* h_weighted, float* h_raw, int32_t* h_peak_bin) {
+  const uint64_t hops = cfg.hops_for(samples_per_lane);
+  if (!hops || !n_lanes) return OMB_OK;
+  if (!h_lanes || !h_weighted || !h_raw) return fail(OMB_ERR_INVALID, "null argument");
+  OMB_TRY(d_in.reserve((size_t)(samples_per_lane * n_lanes)));
+  for (uint32_t l = 0; l < n_lanes; ++l)
+    OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + l * samples_per_lane, h_lanes + l * lane_stride, sizeof(float) * samples_per_lane,
+                                 cudaMemcpyHostToDevice, stream));
+  const uint64_t n = hops * n_lanes * cfg.bins();
+  OMB_TRY(d_w.reserve((size_t)n));
+  OMB_TRY(d_r.reserve((size_t)n));
+  if (h_peak_bin) OMB_TRY(d_peak.reserve((size_t)(hops * n_lanes)));
+  OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, d_w.ptr, d_r.ptr, h_peak_bin ? d_peak.ptr : nullptr, stream));
+  OMB_CUDA_TRY(cudaMemcpyAsync(h_weighted, d_w.ptr, sizeof(float) * n, cudaMemcpyDeviceToHost, stream));
+  OMB_CUDA_TRY(cudaMemcpyAsync(h_raw, d_r.ptr, sizeof(float) * n, cudaMemcpyDeviceToHost, stream));
+  if (h_peak_bin) OMB_CUDA_TRY(cudaMemcpyAsync(h_peak_bin, d_peak.ptr, sizeof(int32_t) * hops * n_lanes, cudaMemcpyDeviceToHost, stream));
+  OMB_CUDA_TRY(cudaStreamSynchronize(stream));
+  return OMB_OK;
+}
+
+}  // namespace omb

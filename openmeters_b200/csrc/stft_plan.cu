@@ -1,0 +1,160 @@
+// stft_plan.cu — batched STFT plan: table set-up, kernel selection, device/host execution.
+#include "stft.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace omb {
+
+StftConfig StftConfig::from_c(const omb_spectrogram_config& c) {
+  StftConfig o;  // spectrogram/processor.rs:71-82 normalize()
+  o.sample_rate = sanitize_sample_rate(c.sample_rate);
+  o.window_kind = c.window <= OMB_WINDOW_BLACKMAN_HARRIS ? c.window : (uint32_t)OMB_WINDOW_RECTANGULAR;
+  o.window = c.fft_size == 0 ? 2048 : c.fft_size;
+  o.hop = c.hop_size == 0 ? std::max<uint64_t>(std::min<uint64_t>(64, o.window), 1) : c.hop_size;
+  o.history_length = c.history_length;
+  o.zero_pad = std::max<uint64_t>(c.zero_padding_factor, 1);
+  o.reassign = c.use_reassignment != 0;
+  return o;
+}
+
+void StftConfig::to_c(omb_spectrogram_config* out) const {
+  std::memset(out, 0, sizeof *out);
+  out->sample_rate = sample_rate;
+  out->window = window_kind;
+  out->fft_size = window;
+  out->hop_size = hop;
+  out->history_length = history_length;
+  out->zero_padding_factor = zero_pad;
+  out->use_reassignment = reassign ? 1 : 0;
+}
+
+StftPlan::~StftPlan() {
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int StftPlan::init(const omb_spectrogram_config& c, int choice) {
+  cfg = StftConfig::from_c(c);
+  kernel_choice = choice;
+  OMB_TRY(current_device(&dev));
+  const uint64_t N = cfg.window, F = cfg.fft_len(), H = cfg.hilbert_len();
+  if (!is_pow2(N) || !is_pow2(F))
+    return fail(OMB_ERR_UNSUPPORTED,
+                "fft_size %llu x zero_padding %llu: only power-of-two transform lengths have kernels (no CPU fallback)",
+                (unsigned long long)N, (unsigned long long)cfg.zero_pad);
+  if (F > (1ull << 24) || H > (1ull << 24)) return fail(OMB_ERR_UNSUPPORTED, "transform length %llu too large", (unsigned long long)F);
+
+  h_win = make_window((int)cfg.window_kind, (size_t)N);
+  h_norm = make_bin_norm(h_win.data(), (size_t)N, (size_t)F);
+  power_scale = 1.0f;
+  if (cfg.reassign) {
+    const float inv_h = 1.0f / (float)H;  // spectrogram/processor.rs:263-266: IFFT left unnormalised
+    for (auto& v : h_norm) v *= inv_h * inv_h;
+    h_dwin = make_derivative_window(h_win.data(), (size_t)N);
+    h_twin = make_time_weighted_window(h_win.data(), (size_t)N);
+    power_scale = make_power_scale(h_win.data(), (size_t)N, (size_t)F);
+  }
+  OMB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  OMB_TRY(d_win.upload(h_win, stream));
+  OMB_TRY(d_norm.upload(h_norm, stream));
+  if (cfg.reassign) {
+    OMB_TRY(d_dwin.upload(h_dwin, stream));
+    OMB_TRY(d_twin.upload(h_twin, stream));
+    OMB_TRY(d_tw_hil.upload(make_twiddles((size_t)H, (size_t)std::max<uint64_t>(H / 2, 1)), stream));
+  }
+  OMB_TRY(d_tw_fft.upload(make_twiddles((size_t)F, (size_t)std::max<uint64_t>(F / 2, 1)), stream));
+
+  fast = false;
+  if (choice != OMB_KERNEL_GENERIC && stft_fast_supported(cfg, dev)) {
+    OMB_TRY(stft_fast_prepare(*this));
+    fast = true;
+  } else if (choice == OMB_KERNEL_FAST) {
+    return fail(OMB_ERR_UNSUPPORTED, "no specialised kernel for window %llu hop %llu zp %llu reassign %d",
+                (unsigned long long)N, (unsigned long long)cfg.hop, (unsigned long long)cfg.zero_pad, (int)cfg.reassign);
+  }
+  OMB_CUDA_TRY(cudaStreamSynchronize(stream));
+  return OMB_OK;
+}
+
+int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
+                             omb_spectrogram_point* out_points, uint64_t point_stride, uint32_t* out_counts,
+                             uint16_t* out_classic, cudaStream_t s, uint64_t first_frame) {
+  const uint64_t frames = cfg.frames_for(samples_per_lane);
+  if (frames == 0 || n_lanes == 0 || first_frame >= frames) return OMB_OK;
+  if (!d_lanes) return fail(OMB_ERR_INVALID, "null lanes pointer");
+  if (cfg.reassign) {
+    if (!out_points || !out_counts) return fail(OMB_ERR_INVALID, "reassigned plan needs out_points and out_counts");
+    if (point_stride < cfg.bins()) return fail(OMB_ERR_INVALID, "point_stride %llu < bins %llu", (unsigned long long)point_stride, (unsigned long long)cfg.bins());
+  } else if (!out_classic) {
+    return fail(OMB_ERR_INVALID, "classic plan needs out_classic");
+  }
+  StftKernelArgs a{};
+  a.lanes = d_lanes;
+  a.lane_stride = lane_stride;
+  a.n_lanes = n_lanes;
+  a.frames_per_lane = frames;
+  a.first_frame = first_frame;
+  a.window = (uint32_t)cfg.window;
+  a.fft_len = (uint32_t)cfg.fft_len();
+  a.hilbert_len = (uint32_t)cfg.hilbert_len();
+  a.hop = (uint32_t)cfg.hop;
+  a.bins = (uint32_t)cfg.bins();
+  a.log2_fft = (uint32_t)ilog2(a.fft_len);
+  a.log2_hilbert = (uint32_t)ilog2(a.hilbert_len);
+  a.win = d_win.ptr;
+  a.dwin = d_dwin.ptr;
+  a.twin = d_twin.ptr;
+  a.bin_norm = d_norm.ptr;
+  a.tw_fft = d_tw_fft.ptr;
+  a.tw_hil = d_tw_hil.ptr;
+  // spectrogram/processor.rs:446-450 — all f32
+  const float sr = cfg.sample_rate;
+  a.bin_hz = sr / (float)a.fft_len;
+  a.max_hz = sr * 0.5f;
+  a.inv_2pi = sr / 6.28318530717958647692f;
+  a.inv_hop = 1.0f / (float)cfg.hop;
+  a.latency_hops = (float)((a.hilbert_len - a.window) / 2) * a.inv_hop;
+  a.out_points = out_points;
+  a.point_stride = point_stride;
+  a.out_counts = out_counts;
+  a.out_classic = out_classic;
+  if (fast) return launch_stft_fast(*this, a, s);
+  return launch_stft_generic(*this, a, s, d_scratch);
+}
+
+int StftPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
+                           omb_spectrogram_point* h_points, uint64_t point_stride, uint32_t* h_counts,
+                           uint16_t* h_classic) {
+  const uint64_t frames = cfg.frames_for(samples_per_lane);
+  if (frames == 0 || n_lanes == 0) return OMB_OK;
+  if (!h_lanes) return fail(OMB_ERR_INVALID, "null lanes pointer");
+  // H2D (one copy per lane when the caller's stride is not dense)
+  OMB_TRY(d_in.reserve((size_t)(samples_per_lane * n_lanes)));
+  if (lane_stride == samples_per_lane) {
+    OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr, h_lanes, sizeof(float) * samples_per_lane * n_lanes, cudaMemcpyHostToDevice, stream));
+  } else {
+    for (uint32_t l = 0; l < n_lanes; ++l)
+      OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + l * samples_per_lane, h_lanes + l * lane_stride, sizeof(float) * samples_per_lane,
+                                   cudaMemcpyHostToDevice, stream));
+  }
+  const uint64_t slots = frames * n_lanes;
+  if (cfg.reassign) {
+    if (!h_points || !h_counts) return fail(OMB_ERR_INVALID, "reassigned plan needs out_points and out_counts");
+    OMB_TRY(d_points.reserve((size_t)(slots * point_stride)));
+    OMB_TRY(d_counts.reserve((size_t)slots));
+    OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, d_points.ptr, point_stride, d_counts.ptr,
+                           nullptr, stream));
+    OMB_CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts.ptr, sizeof(uint32_t) * slots, cudaMemcpyDeviceToHost, stream));
+    OMB_CUDA_TRY(cudaMemcpyAsync(h_points, d_points.ptr, sizeof(omb_spectrogram_point) * slots * point_stride,
+                                 cudaMemcpyDeviceToHost, stream));
+  } else {
+    if (!h_classic) return fail(OMB_ERR_INVALID, "classic plan needs out_classic");
+    OMB_TRY(d_classic.reserve((size_t)(slots * cfg.bins())));
+    OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, nullptr, 0, nullptr, d_classic.ptr, stream));
+    OMB_CUDA_TRY(cudaMemcpyAsync(h_classic, d_classic.ptr, sizeof(uint16_t) * slots * cfg.bins(), cudaMemcpyDeviceToHost, stream));
+  }
+  OMB_CUDA_TRY(cudaStreamSynchronize(stream));
+  return OMB_OK;
+}
+
+}  // namespace omb

@@ -93,3 +93,14 @@ def product_backend():
     from openmeters_b200 import _lib
 
     return _backend(_lib.api(), "product")
+
+
+def emu_backend():
+    """The product's kernel sources executed thread-for-thread by the CPU emulator (tests/emu).
+    Development aid: validates kernel logic without a GPU. Not a product path."""
+    import ctypes
+
+    from tests.emu import build_emu
+
+    lib = ctypes.CDLL(build_emu.build(), mode=ctypes.RTLD_LOCAL)
+    return _backend(capi.bind(lib, "omb_"), "emu")

@@ -26,3 +26,11 @@ def product():
     from tests.backends import product_backend
 
     return product_backend()
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """Kernel sources under the CPU emulator (tests/emu) — development aid, not a product path."""
+    from tests.backends import emu_backend
+
+    return emu_backend()

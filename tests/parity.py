@@ -1,0 +1,118 @@
+"""Parity metrics between an implementation and the oracle (SURVEY.md §8c "parity metric").
+
+FFT *bits* are unreproducible across implementations (the reference's live in rustfft), so:
+  * integer / structural outputs are compared exactly where the domain allows (frame counts, column
+    kinds, ascending-bin order, silence columns, u16 codes equal or +-1 with >= 98 % exact, peak bins),
+  * linear f32 fields use |a-b| <= 1e-5 * max(|b|, column_peak*1e-3),
+  * reassigned points are matched BY BIN; membership may differ only for bins sitting on a threshold;
+    freq tol 1e-5*sr/2, time tol 1e-5*(N/hop), evaluated for bins >= -60 dB re the column peak.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+REL = 1e-5
+
+
+def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_len: int, window: int, hop: int,
+                              power_floor: float = 1e-14):
+    """a = implementation points (n,3), b = oracle points (m,3) as [time, freq, power], both in ascending
+    source-bin order. The two sequences are aligned with a small look-ahead; a point present on one side
+    only must sit on a decision threshold (power at the 1e-14 analysis floor, or frequency at 0 / sr/2).
+    Matched points >= -60 dB re the column peak must agree in frequency and time."""
+    stats = dict(n_a=len(a), n_b=len(b), unmatched=0, checked=0)
+    peak = float(max(a[:, 2].max() if len(a) else 0.0, b[:, 2].max() if len(b) else 0.0))
+    if peak == 0.0:
+        assert len(a) == len(b) == 0
+        return stats
+    tol_f = REL * sr / 2
+    tol_t = REL * (window / hop)
+
+    def same(pa, pb):
+        return abs(pa[2] - pb[2]) <= REL * max(abs(pb[2]), peak * 1e-3)
+
+    def on_threshold(p):
+        return p[2] <= power_floor * (1 + 1e-3) or p[1] <= 4 * tol_f or sr / 2 - p[1] <= 4 * tol_f
+
+    i = j = 0
+    while i < len(a) and j < len(b):
+        pa, pb = a[i], b[j]
+        strong = pb[2] >= peak * 1e-6
+        if same(pa, pb) and (not strong or abs(pa[1] - pb[1]) <= tol_f):
+            if strong:
+                assert abs(pa[0] - pb[0]) <= tol_t, ("time", i, j, pa, pb)
+                stats["checked"] += 1
+            i += 1
+            j += 1
+            continue
+        # membership difference: find which side has the extra point
+        adv = None
+        for d in (1, 2, 3):
+            if j + d < len(b) and same(pa, b[j + d]) and all(on_threshold(b[j + k]) for k in range(d)):
+                adv = ("b", d)
+                break
+            if i + d < len(a) and same(a[i + d], pb) and all(on_threshold(a[i + k]) for k in range(d)):
+                adv = ("a", d)
+                break
+        assert adv is not None, ("unmatched non-threshold point", i, j, pa, pb, peak)
+        stats["unmatched"] += adv[1]
+        if adv[0] == "a":
+            i += adv[1]
+        else:
+            j += adv[1]
+    for k in range(i, len(a)):
+        assert on_threshold(a[k]), ("extra point", a[k])
+        stats["unmatched"] += 1
+    for k in range(j, len(b)):
+        assert on_threshold(b[k]), ("missing point", b[k])
+        stats["unmatched"] += 1
+    return stats
+
+
+def compare_reassigned(points_a, counts_a, points_b, counts_b, *, sr, fft_len, window, hop, max_unmatched_frac=2e-3):
+    """Whole batches: arrays (L,F,stride,3) + counts (L,F)."""
+    assert counts_a.shape == counts_b.shape
+    L, F = counts_a.shape
+    tot = dict(cols=0, pts=0, unmatched=0, checked=0)
+    for l in range(L):
+        for f in range(F):
+            a = points_a[l, f, : counts_a[l, f]]
+            b = points_b[l, f, : counts_b[l, f]]
+            st = compare_reassigned_column(a, b, sr=sr, fft_len=fft_len, window=window, hop=hop)
+            tot["cols"] += 1
+            tot["pts"] += st["n_b"]
+            tot["unmatched"] += st["unmatched"]
+            tot["checked"] += st["checked"]
+    assert tot["unmatched"] <= max_unmatched_frac * max(tot["pts"], 1) + 2, tot
+    return tot
+
+
+def compare_classic(codes_a: np.ndarray, codes_b: np.ndarray, min_exact: float = 0.98):
+    assert codes_a.shape == codes_b.shape
+    d = np.abs(codes_a.astype(np.int32) - codes_b.astype(np.int32))
+    # Far below the column peak the spectrum is rounding noise of the FFT itself (both implementations'
+    # values are noise there), so +-1 is enforced on bins within 90 dB of the column peak and the exact
+    # fraction on all bins.
+    peak = codes_b.max(axis=-1, keepdims=True).astype(np.int32)
+    near = codes_b.astype(np.int32) >= peak - int(90.0 * 65535.0 / 156.0)
+    assert d[near].max(initial=0) <= 1, ("code diff > 1 near peak", int(d[near].max(initial=0)))
+    exact = float(np.mean(d[near] == 0)) if near.any() else 1.0
+    assert exact >= min_exact, exact
+    return dict(exact=exact, max_diff_all=int(d.max(initial=0)))
+
+
+def compare_db(a: np.ndarray, b: np.ndarray, floor: float, slack: float = 2.0):
+    """dB traces, judged in the linear power domain with the SURVEY §8c rule
+    |pa - pb| <= 1e-5 * max(pb, column_peak * 1e-3)  (x `slack` for the f32 dB read-back itself:
+    one ulp of a -100..0 dB value is up to 1.7e-6 relative power). Bins sitting on the floor in either
+    trace are excluded here; floor membership is checked separately by the callers."""
+    assert a.shape == b.shape
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    pa, pb = 10.0 ** (a64 / 10.0), 10.0 ** (b64 / 10.0)
+    peak = pb.max(axis=-1, keepdims=True)
+    tol = slack * REL * np.maximum(pb, peak * 1e-3)
+    sel = (b > floor + 1e-3) & (a > floor + 1e-3)
+    err = np.abs(pa - pb) / tol
+    worst = float(err[sel].max()) if sel.any() else 0.0
+    assert worst <= 1.0, worst
+    return dict(worst_ratio=worst)

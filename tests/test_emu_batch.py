@@ -1,0 +1,46 @@
+"""Batched entry points of the product's kernel sources (under the CPU emulator) vs the oracle, on small
+seeded inputs.  Development aid; the -m gpu suite repeats these at full size on the real build."""
+import numpy as np
+import pytest
+
+from openmeters_b200 import _capi as capi
+from openmeters_b200 import synth
+from openmeters_b200.processors import LoudnessConfig, SpectrogramConfig, SpectrumConfig
+from tests import cases
+
+
+@pytest.mark.parametrize("window,n,hop,zp", [(capi.WINDOW_HANN, 64, 16, 1), (capi.WINDOW_BLACKMAN_HARRIS, 256, 64, 2),
+                                             (capi.WINDOW_HAMMING, 128, 200, 1)])
+def test_classic_batch(emu, window, n, hop, zp):
+    cfg = SpectrogramConfig(fft_size=n, hop_size=hop, window=window, use_reassignment=False, zero_padding_factor=zp)
+    lanes = synth.cfg2_lanes(3, 0.05)
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_GENERIC)
+    assert st["exact"] >= 0.98
+
+
+@pytest.mark.parametrize("window,n,hop,zp", [(capi.WINDOW_HANN, 64, 16, 1), (capi.WINDOW_BLACKMAN_HARRIS, 256, 64, 1),
+                                             (capi.WINDOW_BLACKMAN, 128, 32, 4)])
+def test_reassigned_batch(emu, window, n, hop, zp):
+    cfg = SpectrogramConfig(fft_size=n, hop_size=hop, window=window, use_reassignment=True, zero_padding_factor=zp)
+    lanes = synth.cfg2_lanes(2, 0.04)
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_GENERIC)
+    assert st["checked"] > 100
+
+
+@pytest.mark.parametrize("mode,param", [(capi.AVG_NONE, 0.0), (capi.AVG_EXPONENTIAL, 0.5), (capi.AVG_PEAK_HOLD, 12.0)])
+def test_spectrum_batch(emu, mode, param):
+    cfg = SpectrumConfig(fft_size=256, hop_size=64, averaging=mode, averaging_param=param, floor_db=-100.0)
+    lanes = synth.cfg4_streams(2, 0.05)[:, 0, :]
+    cases.spectrum_parity(emu.api, cfg, lanes)
+
+
+def test_loudness_batch(emu):
+    x = synth.cfg3_surround(0.62)  # 29760 frames: crosses the 0.5 s lazy-activation edge and two window lengths
+    st = cases.loudness_parity(emu.api, LoudnessConfig(), 8, capi.SURROUND, x[None, :], 1024)
+    assert st["short_term"] < 5e-5
+
+
+def test_loudness_batch_two_streams_stereo(emu):
+    a = synth.cfg1_stereo(0.2)
+    b = (a * np.float32(0.25)).astype(np.float32)
+    cases.loudness_parity(emu.api, LoudnessConfig(), 2, None, np.stack([a, b]), 500)
