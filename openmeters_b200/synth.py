@@ -24,13 +24,18 @@ def cfg1_stereo(seconds: float = 10.0, sr: float = 48000.0) -> np.ndarray:
     return np.stack([left, right], 1).astype(np.float32).reshape(-1)
 
 
+def lane_signal(n: int, sr: float, f1: float, seed: int) -> np.ndarray:
+    """0.4*chirp(20 Hz -> f1) + 0.05*uniform[-1,1) noise from default_rng(seed); n samples, f32."""
+    rng = np.random.default_rng(seed)
+    return (chirp(n, sr, 20.0, f1, 0.4) + 0.05 * rng.uniform(-1.0, 1.0, n)).astype(np.float32)
+
+
 def cfg2_lanes(n_lanes: int = 8, seconds: float = 60.0, sr: float = 48000.0, seed0: int = 1000) -> np.ndarray:
     """lane c: 0.4*chirp(20 Hz -> (c%8+1)*2.5 kHz) + 0.05*uniform[-1,1) (default_rng(seed0+c)). (L, S) f32."""
-    n = int(seconds * sr)
+    n = int(round(seconds * sr))
     out = np.empty((n_lanes, n), np.float32)
     for c in range(n_lanes):
-        rng = np.random.default_rng(seed0 + c)
-        out[c] = (chirp(n, sr, 20.0, (c % 8 + 1) * 2500.0, 0.4) + 0.05 * rng.uniform(-1.0, 1.0, n)).astype(np.float32)
+        out[c] = lane_signal(n, sr, (c % 8 + 1) * 2500.0, seed0 + c)
     return out
 
 

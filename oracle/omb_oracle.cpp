@@ -171,9 +171,9 @@ static const FftPlan& fft_plan(size_t n) {
   return ref;
 }
 
-static void fft_inplace(cf* x, size_t n, bool inverse) {
+static void fft_inplace(cf* x, size_t n, bool inverse, const FftPlan* plan = nullptr) {
   if (n <= 1) return;
-  const FftPlan& p = fft_plan(n);
+  const FftPlan& p = plan ? *plan : fft_plan(n);  // hot loops pass a cached plan (the lookup takes a lock)
   if (!p.pow2) {  // tiny non power-of-two sizes only: direct DFT, f64 accumulation
     std::vector<cf> out(n);
     for (size_t k = 0; k < n; ++k) {
@@ -209,10 +209,10 @@ static void fft_inplace(cf* x, size_t n, bool inverse) {
 }
 
 // realfft::RealToComplex stand-in: n real -> n/2+1 complex.
-static void real_fft(const float* in, size_t n, cf* out, std::vector<cf>& scratch) {
+static void real_fft(const float* in, size_t n, cf* out, std::vector<cf>& scratch, const FftPlan* plan = nullptr) {
   scratch.resize(n);
   for (size_t i = 0; i < n; ++i) scratch[i] = cf(in[i], 0.0f);
-  fft_inplace(scratch.data(), n, false);
+  fft_inplace(scratch.data(), n, false, plan);
   for (size_t k = 0; k < n / 2 + 1; ++k) out[k] = scratch[k];
 }
 
@@ -424,8 +424,10 @@ struct ColumnEngine {
   std::vector<float> window, dwin, twin, bin_norm;
   float power_scale = 1.0f;
   // scratch
-  std::vector<cf> analytic, spectra, scratch;
+  std::vector<cf> analytic, spectra, scratch, spec;
   std::vector<float> real;
+  const FftPlan* plan_f = nullptr;  // cached transform plans (rustfft's Arc<dyn Fft>)
+  const FftPlan* plan_h = nullptr;
 
   void rebuild(const SpectrogramConfig& c) {  // rebuild_fft :229-279 (buffers part)
     cfg = c;
@@ -433,6 +435,9 @@ struct ColumnEngine {
     fft_size = ws * cfg.zero_padding_factor;
     hilbert_len = hilbert_len_for(ws);
     bins = fft_size / 2 + 1;
+    plan_f = fft_size > 1 ? &fft_plan(fft_size) : nullptr;
+    plan_h = hilbert_len > 1 ? &fft_plan(hilbert_len) : nullptr;
+    spec.assign(bins, cf(0, 0));
     window = window_coefficients(cfg.window, ws);
     bin_norm = compute_fft_bin_normalization(window.data(), ws, fft_size);
     if (cfg.use_reassignment) {
@@ -456,8 +461,7 @@ struct ColumnEngine {
     const size_t ws = cfg.fft_size;
     copy_dc_removed_windowed(real.data(), frame, window.data(), ws);
     std::fill(real.begin() + ws, real.end(), 0.0f);
-    std::vector<cf> spec(bins);
-    real_fft(real.data(), fft_size, spec.data(), scratch);
+    real_fft(real.data(), fft_size, spec.data(), scratch, plan_f);
     for (size_t k = 0; k < bins; ++k) {
       const float p = (spec[k].real() * spec[k].real() + spec[k].imag() * spec[k].imag()) * bin_norm[k];
       out[k] = pack_classic_db(power_to_db(p, DB_FLOOR));
@@ -470,10 +474,10 @@ struct ColumnEngine {
     const size_t center_offset = (H - ws) / 2;
     for (size_t i = 0; i < H; ++i) analytic[i] = cf(frame[i], 0.0f);
     // hilbert_transform :546-557
-    fft_inplace(analytic.data(), H, false);
+    fft_inplace(analytic.data(), H, false, plan_h);
     analytic[0] = cf(0, 0);
     for (size_t i = H / 2 + 1; i < H; ++i) analytic[i] = cf(0, 0);
-    fft_inplace(analytic.data(), H, true);
+    fft_inplace(analytic.data(), H, true, plan_h);
     const cf* a = analytic.data() + center_offset;
     cf* S = spectra.data();
     cf* D = S + F;
@@ -484,9 +488,9 @@ struct ColumnEngine {
       T[i] = a[i] * twin[i];
     }
     for (size_t i = ws; i < F; ++i) S[i] = D[i] = T[i] = cf(0, 0);
-    fft_inplace(S, F, false);
-    fft_inplace(D, F, false);
-    fft_inplace(T, F, false);
+    fft_inplace(S, F, false, plan_f);
+    fft_inplace(D, F, false, plan_f);
+    fft_inplace(T, F, false, plan_f);
     // reassigned_points :439-488
     const float sr = cfg.sample_rate;
     const float bin_hz = sr / (float)F;
@@ -743,6 +747,7 @@ struct SpectrumProcessor {
   bool prepared = false;
   std::vector<float> window, real, bin_norm, freq_bins, a_db;
   std::vector<cf> spec, scratch;
+  const FftPlan* plan = nullptr;
   std::deque<float> pcm[2];
   size_t pending_skip = 0;
   SpectrumLevelBuffers levels[2];
@@ -778,6 +783,7 @@ struct SpectrumProcessor {
     window = window_coefficients(config.window, n);
     real.assign(n, 0.0f);
     spec.assign(n / 2 + 1, cf(0, 0));
+    plan = n > 1 ? &fft_plan(n) : nullptr;
     prepared = true;
     bin_norm = compute_fft_bin_normalization(window.data(), n, n);
     reset_buffers();
@@ -792,7 +798,7 @@ struct SpectrumProcessor {
     const size_t n = config.fft_size;
     std::vector<float> frame(pcm[trace].begin(), pcm[trace].begin() + (ptrdiff_t)n);
     copy_dc_removed_windowed(real.data(), frame.data(), window.data(), n);
-    real_fft(real.data(), n, spec.data(), scratch);
+    real_fft(real.data(), n, spec.data(), scratch, plan);
     auto& lvl = levels[trace];
     for (size_t k = 0; k < spec.size(); ++k)
       lvl.scratch_power[k] = (spec[k].real() * spec[k].real() + spec[k].imag() * spec[k].imag()) * bin_norm[k];

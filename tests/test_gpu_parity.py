@@ -1,0 +1,213 @@
+"""`-m gpu`: CUDA path vs the CPU oracle on the BASELINE configs (same seeded input bytes), through the C ABI,
+plus size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+
+from openmeters_b200 import _capi as capi
+from openmeters_b200 import batch, synth
+from openmeters_b200.processors import AudioBlock, LoudnessConfig, SpectrogramConfig, SpectrumConfig
+from tests import cases, parity
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [capi.KERNEL_GENERIC, capi.KERNEL_AUTO]
+
+
+# ---------------------------------------------------------------- cfg1: classic, streaming, stereo -> Mid
+def test_cfg1_streaming_classic_stereo(product, oracle):
+    x = synth.cfg1_stereo(10.0)
+    cfg = SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False, history_length=8192)
+    cols = {}
+    for b in (product, oracle):
+        p = b.Spectrogram(cfg)
+        out = []
+        first_reset = None
+        for s in range(0, x.size, 2 * 1024):
+            up = p.process_block(AudioBlock(x[s:s + 2 * 1024], 2, 48000.0))
+            if up is not None:
+                if first_reset is None:
+                    first_reset = up.reset
+                assert up.kind == capi.COLUMN_CLASSIC
+                out.extend(up.new_columns)
+        assert first_reset is True
+        cols[b.name] = np.stack(out)
+    assert cols["product"].shape == cols["oracle"].shape == (936, 513)
+    st = parity.compare_classic(cols["product"][None], cols["oracle"][None])
+    assert st["exact"] >= 0.98
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg1_batch_classic(product, kernel):
+    st2 = synth.cfg1_stereo(10.0).reshape(-1, 2)
+    mid = ((st2[:, 0] + st2[:, 1]) * np.float32(0.5)).astype(np.float32)
+    cfg = SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False)
+    st = cases.stft_parity(product.api, cfg, mid[None, :], kernel=kernel)
+    assert st["exact"] >= 0.98
+
+
+# ---------------------------------------------------------------- cfg2: the metric path
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg2_reassigned_batch(product, kernel):
+    lanes = synth.cfg2_lanes(8, 12.0)
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    st = cases.stft_parity(product.api, cfg, lanes, kernel=kernel)
+    assert st["cols"] == 8 * 555 and st["checked"] > 0.5 * st["pts"]
+
+
+def test_cfg2_streaming_matches_batch(product):
+    """The streaming processor is a thin wrapper over the batch kernel: same columns, block-partition independent."""
+    lane = synth.cfg2_lanes(1, 3.0)[0]
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True, history_length=8192)
+    plan = batch.StftPlan(cfg, api=product.api)
+    pts, cnt = plan.execute_host(lane[None, :])
+    for block in (1024, 3000):
+        p = product.Spectrogram(cfg)
+        cols = []
+        for s in range(0, lane.size, block):
+            up = p.process_block(AudioBlock(lane[s:s + block], 1, 48000.0))
+            if up is not None:
+                cols.extend(up.new_columns)
+        assert len(cols) == cnt.shape[1]
+        for f, c in enumerate(cols):
+            assert np.array_equal(c, pts[0, f, :cnt[0, f]])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg2_properties_large(product, kernel):
+    """Size-independent properties on a batch the oracle would take minutes for:
+    frame independence (a frame's result does not depend on where it sits in the batch), exact power-of-two
+    scaling (x2 input -> x4 power bit-exactly, same time/frequency), physical ranges."""
+    L, S = 16, 1 << 20
+    lanes = synth.cfg2_lanes(L, S / 48000.0)[:, :S]
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    plan = batch.StftPlan(cfg, kernel=kernel, api=product.api)
+    pts, cnt = plan.execute_host(lanes)
+    F = cnt.shape[1]
+    assert F == (S - 8192) // 1024 + 1
+    assert cnt.max() <= 2049 and cnt.min() > 0
+    # frame independence: recompute a shifted sub-batch
+    sub = np.ascontiguousarray(lanes[3:5, 100 * 1024: 100 * 1024 + 8192 + 49 * 1024])
+    p2, c2 = plan.execute_host(sub)
+    assert np.array_equal(c2, cnt[3:5, 100:150])
+    for l in range(2):
+        for f in range(50):
+            assert np.array_equal(p2[l, f, :c2[l, f]], pts[3 + l, 100 + f, :cnt[3 + l, 100 + f]])
+    # scaling
+    p4, c4 = plan.execute_host((sub * np.float32(2.0)).astype(np.float32))
+    same = c4 == c2
+    assert same.mean() > 0.99
+    for l, f in zip(*np.nonzero(same)):
+        n = c2[l, f]
+        assert np.array_equal(p4[l, f, :n, :2], p2[l, f, :n, :2])
+        assert np.array_equal(p4[l, f, :n, 2], p2[l, f, :n, 2] * np.float32(4.0))
+    # ranges
+    for l in range(0, L, 5):
+        for f in range(0, F, 97):
+            q = pts[l, f, :cnt[l, f]]
+            assert np.all(q[:, 1] > 0) and np.all(q[:, 1] < 24000.0) and np.all(q[:, 2] >= 1e-14) and np.all(np.isfinite(q))
+
+
+def test_generic_and_fast_kernels_agree(product):
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    fast = batch.StftPlan(cfg, kernel=capi.KERNEL_AUTO, api=product.api)
+    if not fast.is_fast:
+        pytest.skip("no specialised kernel for this size in this build")
+    gen = batch.StftPlan(cfg, kernel=capi.KERNEL_GENERIC, api=product.api)
+    lanes = synth.cfg2_lanes(4, 4.0, seed0=77)
+    pa, ca = fast.execute_host(lanes)
+    pb, cb = gen.execute_host(lanes)
+    parity.compare_reassigned(pa, ca, pb, cb, sr=48000.0, fft_len=4096, window=4096, hop=1024)
+
+
+# ---------------------------------------------------------------- cfg3: loudness
+def test_cfg3_loudness_batch(product):
+    x = synth.cfg3_surround(30.0)
+    st = cases.loudness_parity(product.api, LoudnessConfig(), 8, capi.SURROUND, x[None, :], 1024)
+    assert max(st.values()) <= 5e-5
+
+
+def test_cfg3_loudness_streaming(product, oracle):
+    x = synth.cfg3_surround(8.0)
+    snaps = {}
+    for b in (product, oracle):
+        p = b.Loudness(LoudnessConfig())
+        out = []
+        for s in range(0, x.size, 8 * 1024):
+            out.append(p.process_block(AudioBlock(x[s:s + 8 * 1024], 8, 48000.0, capi.SURROUND)))
+        snaps[b.name] = out
+    for a, o in zip(snaps["product"], snaps["oracle"]):
+        assert abs(a.short_term_loudness - o.short_term_loudness) <= 5e-5
+        assert abs(a.momentary_loudness - o.momentary_loudness) <= 5e-5
+        assert np.max(np.abs(a.rms_fast_db - o.rms_fast_db)) <= 5e-5 and np.max(np.abs(a.rms_slow_db - o.rms_slow_db)) <= 5e-5
+        assert np.array_equal(a.true_peak_db, o.true_peak_db) or np.max(np.abs(a.true_peak_db - o.true_peak_db)) <= 1e-5
+        assert a.channel_count == 8 and a.positions == o.positions
+
+
+def test_loudness_rates_and_layouts(product):
+    for sr, ch in ((44100.0, 2), (96000.0, 6), (192000.0, 1)):
+        x = synth.cfg3_surround(1.5, sr).reshape(-1, 8)[:, :ch].reshape(-1)
+        cases.loudness_parity(product.api, LoudnessConfig(sample_rate=sr), ch, None, x[None, :], 777)
+
+
+# ---------------------------------------------------------------- cfg4: spectrum analyzer
+def test_cfg4_spectrum_batch(product):
+    lanes = synth.cfg4_streams(6, 5.0).reshape(12, -1)
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=capi.AVG_PEAK_HOLD,
+                         averaging_param=12.0, floor_db=-100.0)
+    cases.spectrum_parity(product.api, cfg, lanes)
+
+
+@pytest.mark.parametrize("mode,param", [(capi.AVG_NONE, 0.0), (capi.AVG_EXPONENTIAL, 0.5)])
+def test_spectrum_modes(product, mode, param):
+    lanes = synth.cfg4_streams(2, 1.5).reshape(4, -1)
+    cfg = SpectrumConfig(fft_size=4096, hop_size=512, window=capi.WINDOW_BLACKMAN, averaging=mode, averaging_param=param)
+    cases.spectrum_parity(product.api, cfg, lanes)
+
+
+def test_cfg4_streaming_two_sources(product, oracle):
+    x = synth.cfg4_streams(1, 3.0)[0]  # (2, S) planar
+    inter = np.stack([x[0], x[1]], 1).reshape(-1).astype(np.float32)
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0,
+                         source=capi.CHANNEL_LEFT, secondary_source=capi.CHANNEL_RIGHT)
+    last = {}
+    for b in (product, oracle):
+        p = b.Spectrum(cfg)
+        snap = None
+        for s in range(0, inter.size, 2 * 1024):
+            r = p.process_block(AudioBlock(inter[s:s + 2 * 1024], 2, 48000.0))
+            snap = r if r is not None else snap
+        last[b.name] = snap
+    a, o = last["product"], last["oracle"]
+    assert np.array_equal(a.frequency_bins, o.frequency_bins)
+    for t in range(2):
+        for w in range(2):
+            parity.compare_db(a.traces[t][w][None], o.traces[t][w][None], -100.0)
+
+
+# ---------------------------------------------------------------- cfg5: 8192-pt reassigned at 96 kHz
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_cfg5_reassigned_batch(product, kernel):
+    lanes = synth.cfg5_lanes(4, 96000 * 2)
+    cfg = SpectrogramConfig(sample_rate=96000.0, fft_size=8192, hop_size=2048, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    st = cases.stft_parity(product.api, cfg, lanes, kernel=kernel)
+    assert st["cols"] == 4 * ((96000 * 2 - 16384) // 2048 + 1)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_edge_cases(product):
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    plan = batch.StftPlan(cfg, api=product.api)
+    # too short: no frames, no launch, no error
+    pts, cnt = plan.execute_host(np.zeros((2, 8191), np.float32))
+    assert cnt.shape == (2, 0)
+    # exactly one frame; all-zero lane -> empty column; DC lane -> empty column (bin 0 removed by the Hilbert mask)
+    lanes = np.zeros((3, 8192), np.float32)
+    lanes[1] = 0.25
+    lanes[2] = synth.cfg2_lanes(1, 8192 / 48000.0)[0, :8192]
+    pts, cnt = plan.execute_host(lanes)
+    assert cnt.shape == (3, 1) and cnt[0, 0] == 0 and cnt[1, 0] == 0 and cnt[2, 0] > 1000
+    # ragged stride
+    big = np.zeros((2, 20000), np.float32)
+    big[:, :8192 + 1024] = lanes[2:3, :1].repeat(2, 0) * 0 + synth.cfg2_lanes(2, 0.2)[:, :8192 + 1024]
+    p1, c1 = plan.execute_host(np.ascontiguousarray(big[:, :8192 + 1024]))
+    assert c1.shape == (2, 2)
