@@ -1,0 +1,85 @@
+// fft16.cuh — in-register radix-16 butterfly and the shared-memory layout helpers of the
+// specialised STFT kernels.
+//
+// A length-M complex FFT (M = 256*R3, here R3 = 16 -> M = 4096) is three in-place radix-16 passes over a
+// padded shared-memory buffer, T = M/16 threads, 16 elements per thread per pass:
+//
+//   access A (stride T)  : thread b owns logical indices b + T*j            (DIF pass 1 / DIT pass 3)
+//   access B (stride 16) : thread u = (blk, o) owns blk*T + o + 16*j        (pass 2 in both directions)
+//   access C (contiguous): thread t owns base(t)*16 + j, base(t) = digit swap so that after a DIF
+//                          transform thread t holds frequencies t + 256*j   (DIF pass 3 / DIT pass 1)
+//
+// phys(i) = i + i/16 + i/256 (in float2 units) makes all three patterns bank-conflict free for 64-bit
+// accesses (each half-warp touches 16 distinct 8-byte bank pairs).
+#pragma once
+#include "common.h"
+
+namespace omb {
+namespace f16 {
+
+constexpr float kC1 = 0.92387953251128673848f;  // cos(pi/8)
+constexpr float kS1 = 0.38268343236508978178f;  // sin(pi/8)
+constexpr float kH = 0.70710678118654752440f;   // sqrt(1/2)
+
+template <bool INV>
+__device__ __forceinline__ float2 rot_mj(float2 a) {  // a * (-j) forward, a * (+j) inverse
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// a * (c - j s) forward, a * (c + j s) inverse
+template <bool INV>
+__device__ __forceinline__ float2 mul_cs(float2 a, float c, float s) {
+  return INV ? make_float2(a.x * c - a.y * s, a.y * c + a.x * s) : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+// a * w forward, a * conj(w) inverse, w = (cos, -sin) table entry
+template <bool INV>
+__device__ __forceinline__ float2 mul_tw(float2 a, float2 w) {
+  return INV ? make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y) : make_float2(a.x * w.x - a.y * w.y, a.y * w.x + a.x * w.y);
+}
+
+template <bool INV>
+__device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+  const float2 s1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+  const float2 s2 = make_float2(a1.x + a3.x, a1.y + a3.y);
+  const float2 s3 = rot_mj<INV>(make_float2(a1.x - a3.x, a1.y - a3.y));
+  a0 = make_float2(s0.x + s2.x, s0.y + s2.y);
+  a2 = make_float2(s0.x - s2.x, s0.y - s2.y);
+  a1 = make_float2(s1.x + s3.x, s1.y + s3.y);
+  a3 = make_float2(s1.x - s3.x, s1.y - s3.y);
+}
+
+// v[q] <- sum_j v[j] * W16^{+-jq}; natural order in, natural order out.
+template <bool INV>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  // step 1: radix-4 over j1 for each j0 (elements j0, j0+4, j0+8, j0+12) -> t[j0][q0] left in v[j0 + 4*q0]
+#pragma unroll
+  for (int j0 = 0; j0 < 4; ++j0) radix4<INV>(v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12]);
+  // step 2: t[j0][q0] *= W16^{j0*q0}
+  v[1 + 4 * 1] = mul_cs<INV>(v[1 + 4 * 1], kC1, kS1);                 // W^1
+  v[1 + 4 * 2] = mul_cs<INV>(v[1 + 4 * 2], kH, kH);                   // W^2
+  v[1 + 4 * 3] = mul_cs<INV>(v[1 + 4 * 3], kS1, kC1);                 // W^3
+  v[2 + 4 * 1] = mul_cs<INV>(v[2 + 4 * 1], kH, kH);                   // W^2
+  v[2 + 4 * 2] = rot_mj<INV>(v[2 + 4 * 2]);                           // W^4 = -j
+  v[2 + 4 * 3] = mul_cs<INV>(v[2 + 4 * 3], -kH, kH);                  // W^6
+  v[3 + 4 * 1] = mul_cs<INV>(v[3 + 4 * 1], kS1, kC1);                 // W^3
+  v[3 + 4 * 2] = mul_cs<INV>(v[3 + 4 * 2], -kH, kH);                  // W^6
+  v[3 + 4 * 3] = mul_cs<INV>(v[3 + 4 * 3], -kC1, -kS1);               // W^9
+  // step 3: radix-4 over j0 for each q0: inputs v[j0 + 4*q0], outputs X[q0 + 4*q1] land in v[q1 + 4*q0]
+#pragma unroll
+  for (int q0 = 0; q0 < 4; ++q0) radix4<INV>(v[4 * q0], v[4 * q0 + 1], v[4 * q0 + 2], v[4 * q0 + 3]);
+  // transpose the 4x4 index (q1 + 4*q0 -> q0 + 4*q1) so the result is in natural order
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      const float2 t = v[a + 4 * b];
+      v[a + 4 * b] = v[b + 4 * a];
+      v[b + 4 * a] = t;
+    }
+}
+
+__device__ __forceinline__ int phys(int i) { return i + (i >> 4) + (i >> 8); }
+constexpr int phys_size(int m) { return m + (m >> 4) + (m >> 8); }
+
+}  // namespace f16
+}  // namespace omb
