@@ -1,0 +1,162 @@
+// omb200.hpp — C++17 host-side mirror of the reference's processor surface over the C ABI (omb200.h).
+//
+// Same names and meaning as src/visuals/{spectrogram,spectrum,loudness}/processor.rs and dsp.rs:108-262:
+// Processor::new(config) -> constructor; config(); update_config(); prepare(); process_block(block) ->
+// std::optional<snapshot> (nullopt = the reference's None); reset_audio().  A failing CUDA call throws
+// omb::Error (the reference would panic=abort).  Header-only; link with -lomb200.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "omb200.h"
+
+namespace omb {
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int s, const std::string& what) : std::runtime_error(what + ": " + omb_last_error()), status(s) {}
+};
+inline int check(int rc, const char* what) {
+  if (rc < 0) throw Error(rc, what);
+  return rc;
+}
+
+// dsp.rs:108-115 — a borrowed interleaved block. positions empty => ChannelPosition::fallback(channels).
+struct AudioBlock {
+  const float* samples = nullptr;
+  size_t len = 0;  // interleaved sample count
+  uint32_t channels = 1;
+  float sample_rate = 48000.0f;
+  std::optional<std::array<uint8_t, OMB_MAX_CHANNELS>> positions;
+  size_t frame_count() const { return len / (channels ? channels : 1); }
+  bool is_empty() const { return len < (channels ? channels : 1); }
+  const uint8_t* pos_ptr() const { return positions ? positions->data() : nullptr; }
+};
+
+using SpectrogramConfig = omb_spectrogram_config;
+using SpectrogramPoint = omb_spectrogram_point;
+
+struct SpectrogramColumn {  // spectrogram/processor.rs:124-127
+  std::vector<SpectrogramPoint> reassigned;
+  std::vector<uint16_t> classic;
+};
+struct SpectrogramUpdate {  // spectrogram/processor.rs:160-168
+  size_t fft_size, hop_size;
+  float sample_rate;
+  size_t history_length;
+  bool reset;
+  float reassigned_power_scale;
+  bool is_reassigned;
+  std::vector<SpectrogramColumn> new_columns;
+};
+
+class SpectrogramProcessor {
+ public:
+  static SpectrogramConfig default_config() { SpectrogramConfig c; omb_spectrogram_default_config(&c); return c; }
+  explicit SpectrogramProcessor(const SpectrogramConfig& cfg = default_config()) { check(omb_spectrogram_create(&cfg, &h_), "omb_spectrogram_create"); }
+  ~SpectrogramProcessor() { omb_spectrogram_destroy(h_); }
+  SpectrogramProcessor(const SpectrogramProcessor&) = delete;
+  SpectrogramProcessor& operator=(const SpectrogramProcessor&) = delete;
+  SpectrogramConfig config() const { SpectrogramConfig c; check(omb_spectrogram_get_config(h_, &c), "get_config"); return c; }
+  void update_config(const SpectrogramConfig& c) { check(omb_spectrogram_update_config(h_, &c), "update_config"); }
+  void prepare() { check(omb_spectrogram_prepare(h_), "prepare"); }
+  void reset_audio() { check(omb_spectrogram_reset_audio(h_), "reset_audio"); }
+  std::optional<SpectrogramUpdate> process_block(const AudioBlock& b) {
+    omb_spectrogram_update up{};
+    if (check(omb_spectrogram_process_block(h_, b.samples, b.len, b.channels, b.sample_rate, b.pos_ptr(), &up), "process_block") == OMB_NO_DATA)
+      return std::nullopt;
+    SpectrogramUpdate u{(size_t)up.fft_size, (size_t)up.hop_size, up.sample_rate, (size_t)up.history_length, up.reset != 0,
+                        up.reassigned_power_scale, up.kind == OMB_COLUMN_REASSIGNED, {}};
+    u.new_columns.resize(up.n_columns);
+    for (uint32_t c = 0; c < up.n_columns; ++c) {
+      if (u.is_reassigned) u.new_columns[c].reassigned.assign(up.points + up.column_offsets[c], up.points + up.column_offsets[c + 1]);
+      else u.new_columns[c].classic.assign(up.classic_db + (size_t)c * up.bins, up.classic_db + (size_t)(c + 1) * up.bins);
+    }
+    return u;
+  }
+
+ private:
+  omb_spectrogram* h_ = nullptr;
+};
+
+using SpectrumConfig = omb_spectrum_config;
+struct SpectrumSnapshot {  // spectrum/processor.rs:33-37; traces[trace][0] weighted, [trace][1] raw
+  std::vector<float> frequency_bins;
+  std::array<std::array<std::vector<float>, 2>, 2> traces;
+};
+
+class SpectrumProcessor {
+ public:
+  static SpectrumConfig default_config() { SpectrumConfig c; omb_spectrum_default_config(&c); return c; }
+  explicit SpectrumProcessor(const SpectrumConfig& cfg = default_config()) { check(omb_spectrum_create(&cfg, &h_), "omb_spectrum_create"); }
+  ~SpectrumProcessor() { omb_spectrum_destroy(h_); }
+  SpectrumProcessor(const SpectrumProcessor&) = delete;
+  SpectrumProcessor& operator=(const SpectrumProcessor&) = delete;
+  SpectrumConfig config() const { SpectrumConfig c; check(omb_spectrum_get_config(h_, &c), "get_config"); return c; }
+  void update_config(const SpectrumConfig& c) { check(omb_spectrum_update_config(h_, &c), "update_config"); }
+  void prepare() { check(omb_spectrum_prepare(h_), "prepare"); }
+  void reset_audio() { check(omb_spectrum_reset_audio(h_), "reset_audio"); }
+  // The reference returns Option<&SpectrumSnapshot> borrowed from the processor; so does this.
+  const SpectrumSnapshot* process_block(const AudioBlock& b) {
+    omb_spectrum_snapshot s{};
+    if (check(omb_spectrum_process_block(h_, b.samples, b.len, b.channels, b.sample_rate, b.pos_ptr(), &s), "process_block") == OMB_NO_DATA)
+      return nullptr;
+    snap_.frequency_bins.assign(s.frequency_bins, s.frequency_bins + s.bins);
+    for (int t = 0; t < 2; ++t)
+      for (int w = 0; w < 2; ++w) snap_.traces[t][w].assign(s.traces[t][w], s.traces[t][w] + s.bins);
+    return &snap_;
+  }
+
+ private:
+  omb_spectrum* h_ = nullptr;
+  SpectrumSnapshot snap_;
+};
+
+using LoudnessConfig = omb_loudness_config;
+using LoudnessSnapshot = omb_loudness_snapshot;  // loudness/processor.rs:185-194 (Copy)
+
+class LoudnessProcessor {
+ public:
+  static LoudnessConfig default_config() { LoudnessConfig c; omb_loudness_default_config(&c); return c; }
+  explicit LoudnessProcessor(const LoudnessConfig& cfg = default_config()) { check(omb_loudness_create(&cfg, &h_), "omb_loudness_create"); }
+  ~LoudnessProcessor() { omb_loudness_destroy(h_); }
+  LoudnessProcessor(const LoudnessProcessor&) = delete;
+  LoudnessProcessor& operator=(const LoudnessProcessor&) = delete;
+  LoudnessConfig config() const { LoudnessConfig c; check(omb_loudness_get_config(h_, &c), "get_config"); return c; }
+  void reset_audio() { check(omb_loudness_reset_audio(h_), "reset_audio"); }
+  std::optional<LoudnessSnapshot> process_block(const AudioBlock& b) {
+    LoudnessSnapshot s{};
+    if (check(omb_loudness_process_block(h_, b.samples, b.len, b.channels, b.sample_rate, b.pos_ptr(), &s), "process_block") == OMB_NO_DATA)
+      return std::nullopt;
+    return s;
+  }
+
+ private:
+  omb_loudness* h_ = nullptr;
+};
+
+// registry.rs:247-256 VisualModule — the trait the reference drives its visuals through.
+struct VisualModule {
+  virtual ~VisualModule() = default;
+  virtual void ingest(const AudioBlock& block) = 0;
+  virtual void reset_audio() = 0;
+  virtual void prepare() {}
+};
+
+// registry.rs:106-118: `if let Some(snap) = processor.process_block(block) { state.apply_snapshot(snap) }`
+template <class Processor, class State>
+struct Visual final : VisualModule {
+  Processor processor;
+  State state;
+  void ingest(const AudioBlock& block) override {
+    if (auto snap = processor.process_block(block)) state.apply_snapshot(*snap);
+  }
+  void reset_audio() override { processor.reset_audio(); state.reset_audio(); }
+  void prepare() override { if constexpr (requires(Processor& p) { p.prepare(); }) processor.prepare(); }
+};
+
+}  // namespace omb

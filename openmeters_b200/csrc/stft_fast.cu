@@ -34,6 +34,16 @@ constexpr int kWarps = kT / 32;
 constexpr int kWSize = f16::phys_size(kM);  // float2 elements of the padded work buffer
 constexpr int kGroups = 9;           // bins t + 256*j for j = 0..7, plus bin 2048 (thread 0, j = 8)
 
+// cos / sin of 2*pi*j/32, j = 0..15 (W_32^j = c - i s)
+__device__ constexpr float kW32c[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128673848f, 0.83146961230254523708f,
+                                        0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508978178f, 0.19509032201612826785f,
+                                        0.0f, -0.19509032201612826785f, -0.38268343236508978178f, -0.55557023301960222474f,
+                                        -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128673848f, -0.98078528040323044913f};
+__device__ constexpr float kW32s[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508978178f, 0.55557023301960222474f,
+                                        0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128673848f, 0.98078528040323044913f,
+                                        1.0f, 0.98078528040323044913f, 0.92387953251128673848f, 0.83146961230254523708f,
+                                        0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508978178f, 0.19509032201612826785f};
+
 struct FastArgs {
   StftKernelArgs a;
   const float2* tw1;   // [15][256]  W_4096^{b*q}, q = 1..15
@@ -79,69 +89,107 @@ __device__ __forceinline__ void ring_fetch(float* ring, int pos, const float* sr
 
 __device__ __forceinline__ int ring_wrap(int i, int ring_len) { return i >= ring_len ? i - ring_len : i; }
 
-template <bool INV>
+// Per-thread shared-memory bases of the three access patterns (fft16.cuh). With phys(i) = i + i/16 + i/256:
+//   A: phys(t + 256 q)              = pA + 273 q,   pA = t + t/16
+//   B: phys(blk*256 + o + 16 j)     = pB + 17 j,    pB = 273*blk + o        (blk = t/16, o = t%16)
+//   C: phys(q1*256 + q2*16 + j)     = pC + j,       pC = 273*q1 + 17*q2     (q1 = t%16, q2 = t/16)
+// so every element address is a per-thread base plus a compile-time constant (immediate offsets in LDS/STS).
+struct Addr {
+  int pA, pB, pC;
+};
+__device__ __forceinline__ Addr make_addr(int t) {
+  Addr a;
+  a.pA = t + (t >> 4);
+  a.pB = 273 * (t >> 4) + (t & 15);
+  a.pC = 273 * (t & 15) + 17 * (t >> 4);
+  return a;
+}
+
+// External twiddles of one pass: v[q] *= W^{idx*q} (conjugated for the inverse), q = 1..15.
+// kTw = 0: 15 table loads.  kTw = 1: 4 loads (q = 1, 2, 4, 8) + 11 products (each derived value is at most two
+// multiplications away from a correctly rounded table entry).
+template <bool INV, int kTw>
 __device__ __forceinline__ void twiddle15(float2 (&v)[16], const float2* __restrict__ tab, int stride, int idx) {
+  if (kTw == 0) {
 #pragma unroll
-  for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], __ldg(&tab[(q - 1) * stride + idx]));
+    for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], __ldg(&tab[(q - 1) * stride + idx]));
+  } else {
+    float2 w[16];
+    w[1] = __ldg(&tab[0 * stride + idx]);
+    w[2] = __ldg(&tab[1 * stride + idx]);
+    w[4] = __ldg(&tab[3 * stride + idx]);
+    w[8] = __ldg(&tab[7 * stride + idx]);
+    w[3] = cmul(w[1], w[2]);
+    w[5] = cmul(w[1], w[4]);
+    w[6] = cmul(w[2], w[4]);
+    w[7] = cmul(w[3], w[4]);
+#pragma unroll
+    for (int q = 9; q < 16; ++q) w[q] = cmul(w[q - 8], w[8]);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], w[q]);
+  }
 }
 
 // DIF forward passes 1..3 over W. Input already in v (access A: element b + 256 j in v[j]).
 // On return thread t holds frequencies t + 256*j in v[j].
-__device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const FastArgs& fa) {
+template <int kTw>
+__device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const FastArgs& fa, const Addr& ad) {
   const int t = threadIdx.x;
   // pass 1: butterfly over j (stride 256), twiddle W_M^{t*q}, store in place
   f16::dft16<false>(v);
-  twiddle15<false>(v, fa.tw1, kT, t);
+  twiddle15<false, kTw>(v, fa.tw1, kT, t);
+  float2* wa = W + ad.pA;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) W[f16::phys(t + kT * q)] = v[q];
+  for (int q = 0; q < 16; ++q) wa[273 * q] = v[q];
   __syncthreads();
   // pass 2: thread (blk = t>>4, o = t&15): elements blk*256 + o + 16 j, twiddle W_256^{o*q}
-  const int blk = t >> 4, o = t & 15;
+  float2* wb = W + ad.pB;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = W[f16::phys(blk * kT + o + 16 * j)];
+  for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
   f16::dft16<false>(v);
-  twiddle15<false>(v, fa.tw2, 16, o);
+  twiddle15<false, kTw>(v, fa.tw2, 16, t & 15);
 #pragma unroll
-  for (int q = 0; q < 16; ++q) W[f16::phys(blk * kT + o + 16 * q)] = v[q];
+  for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
   __syncthreads();
-  // pass 3 (access C): thread t owns the group whose outputs are frequencies t + 256*q:
-  // positions (q1 = t&15, q2 = t>>4): q1*256 + q2*16 + j
-  const int gbase = (t & 15) * kT + (t >> 4) * 16;
+  // pass 3 (access C): thread t owns the group whose outputs are frequencies t + 256*q
+  const float2* wc = W + ad.pC;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = W[f16::phys(gbase + j)];
+  for (int j = 0; j < 16; ++j) v[j] = wc[j];
   f16::dft16<false>(v);
 }
 
 // DIT inverse passes 1..3. Input: thread t holds Q[t + 256*j] in v[j]. Output (in W, natural order):
 // q[m] at phys(m); thread t wrote m = t + 256*j.
-__device__ __forceinline__ void fft_inverse_to_smem(float2 (&v)[16], float2* W, const FastArgs& fa) {
+template <int kTw>
+__device__ __forceinline__ void fft_inverse_to_smem(float2 (&v)[16], float2* W, const FastArgs& fa, const Addr& ad) {
   const int t = threadIdx.x;
   // pass 1 (access C), no twiddles
   f16::dft16<true>(v);
-  const int gbase = (t & 15) * kT + (t >> 4) * 16;
+  float2* wc = W + ad.pC;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) W[f16::phys(gbase + q)] = v[q];
+  for (int q = 0; q < 16; ++q) wc[q] = v[q];
   __syncthreads();
   // pass 2 (access B): thread (q1 = t>>4, m0 = t&15): elements q1*256 + m0 + 16*q2, pre-twiddle conj W_256^{m0*q2}
-  const int blk = t >> 4, o = t & 15;
+  float2* wb = W + ad.pB;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = W[f16::phys(blk * kT + o + 16 * j)];
-  twiddle15<true>(v, fa.tw2, 16, o);
+  for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
+  twiddle15<true, kTw>(v, fa.tw2, 16, t & 15);
   f16::dft16<true>(v);
 #pragma unroll
-  for (int q = 0; q < 16; ++q) W[f16::phys(blk * kT + o + 16 * q)] = v[q];
+  for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
   __syncthreads();
   // pass 3 (access A): thread b: elements b + 256*q1, pre-twiddle conj W_M^{b*q1}
+  float2* wa = W + ad.pA;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = W[f16::phys(t + kT * j)];
-  twiddle15<true>(v, fa.tw1, kT, t);
+  for (int j = 0; j < 16; ++j) v[j] = wa[273 * j];
+  twiddle15<true, kTw>(v, fa.tw1, kT, t);
   f16::dft16<true>(v);
 #pragma unroll
-  for (int q = 0; q < 16; ++q) W[f16::phys(t + kT * q)] = v[q];
+  for (int q = 0; q < 16; ++q) wa[273 * q] = v[q];
   __syncthreads();
 }
 
-template <int kMinBlocks>
+template <int kMinBlocks, int kTw>
 __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa) {
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -155,6 +203,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
   const float2 wh = __ldg(&fa.twh[t]);  // W_8192^t
   const ReassignConsts rc{a.bin_hz, a.max_hz, a.inv_2pi, a.inv_hop, a.latency_hops};
   const float sign = (t & 1) ? -1.0f : 1.0f;  // (-1)^(off + n), off even, n = t + 256 j
+  const Addr ad = make_addr(t);
 
   for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
     const uint64_t lane = run / fa.runs_per_lane;
@@ -186,14 +235,13 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
       // ---- F: z[n] = x[2n] + j x[2n+1], n = t + 256 j  -> sample 2t + 512 j
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int s = ring_wrap(r0 + 2 * t + 2 * kT * j, ring_len);
-        v[j] = *reinterpret_cast<const float2*>(ring + s);
+        const int sj = ring_wrap(r0 + 2 * kT * j, ring_len);  // CTA-uniform: r0, ring_len are multiples of 512
+        v[j] = *reinterpret_cast<const float2*>(ring + sj + 2 * t);
       }
-      fft_forward(v, sm.W, fa);
+      fft_forward<kTw>(v, sm.W, fa, ad);
       // thread t holds Z[t + 256 j]. Publish for the pair step (in place, access C) and X[0], X[H/2].
-      const int gbase = (t & 15) * kT + (t >> 4) * 16;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) sm.W[f16::phys(gbase + q)] = v[q];
+      for (int q = 0; q < 16; ++q) sm.W[ad.pC + q] = v[q];
       if (t == 0) {
         sm.x0_xm[0] = v[0].x + v[0].y;  // X[0]   = Re Z0 + Im Z0
         sm.x0_xm[1] = v[0].x - v[0].y;  // X[H/2] = Re Z0 - Im Z0
@@ -203,12 +251,14 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
       //         and 256 (16 - j) for t = 0 (j = 0 pairs with itself: Q[0] = 0).
       {
         const int pt = (kT - t) & (kT - 1);
-        const int pbase = (pt & 15) * kT + (pt >> 4) * 16;
+        const float2* wp = sm.W + 273 * (pt & 15) + 17 * (pt >> 4);
         float2 zp[16];
+        if (t == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int pj = (t == 0) ? ((16 - j) & 15) : (15 - j);
-          zp[j] = sm.W[f16::phys(pbase + pj)];
+          for (int j = 0; j < 16; ++j) zp[j] = wp[(16 - j) & 15];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) zp[j] = wp[15 - j];
         }
         __syncthreads();  // everyone has read its partner values; W may be overwritten
 #pragma unroll
@@ -218,9 +268,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
           const float2 E = make_float2(0.5f * (z.x + c.x), 0.5f * (z.y + c.y));
           const float2 d = make_float2(z.x - c.x, z.y - c.y);
           const float2 O = make_float2(0.5f * d.y, -0.5f * d.x);  // d / (2j)
-          // W_32^j = exp(-2 pi i j / 32): compile-time constants after unrolling
-          const float ang = -6.28318530717958647692f * (float)j / 32.0f;
-          const float2 w32 = make_float2(cosf(ang), sinf(ang));
+          const float2 w32 = make_float2(kW32c[j], -kW32s[j]);  // W_32^j, literal constants after unrolling
           const float2 w = cmul(wh, w32);
           const float2 P1 = cmul_conj(E, w);                      // conj(w) * E
           const float2 wO = cmul(w, O);
@@ -230,26 +278,27 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
         if (t == 0) v[0] = make_float2(0.0f, 0.0f);                // Q[0] = 0 (DC removed)
       }
       // ---- I: q = IFFT_M(Q) (unnormalised), natural order in W
-      fft_inverse_to_smem(v, sm.W, fa);
+      fft_inverse_to_smem<kTw>(v, sm.W, fa, ad);
       // ---- G0: c[n] for n = t + 256 j. Re = (H x[off+n] - X0 + (-1)^n XM) / 2, Im = y[off+n],
       //          y[2m] = Re q[m], y[2m+1] = Im q[m]
       float2 c[16];
       {
         const float half_x0 = 0.5f * sm.x0_xm[0], half_xm = 0.5f * sm.x0_xm[1];
         const float bias = sign * half_xm - half_x0;
-        const float* Wf = reinterpret_cast<const float*>(sm.W);
+        // q[m], m = (off + n)/2 = 1024 + 128 j + u, u = t/2: phys(m) = (1092 + u + u/16) + 136 j + j/2
+        const int u = t >> 1;
+        const float* Wf = reinterpret_cast<const float*>(sm.W) + 2 * (1092 + u + (u >> 4)) + (t & 1);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int n = t + kT * j;
-          const int s = ring_wrap(r0 + off + n, ring_len);
-          const int m = (off + n) >> 1;
-          c[j].x = fmaf((float)kM, ring[s], bias);  // H/2 = M
-          c[j].y = Wf[2 * f16::phys(m) + (t & 1)];
+          const int sj = ring_wrap(r0 + off + kT * j, ring_len);  // CTA-uniform
+          c[j].x = fmaf((float)kM, ring[sj + t], bias);           // H/2 = M
+          c[j].y = Wf[2 * (136 * j + (j >> 1))];
         }
       }
       __syncthreads();  // all q reads done before the first window transform overwrites W
       // ---- G: three windowed transforms; keep bins t + 256 j (j < 8) and bin 2048 (j = 8, thread 0)
-      float2 S[kGroups], D[kGroups];
+      float2 S[kGroups];
+      float nd[kGroups];  // Im(D conj S) = D.im S.re - D.re S.im, spectrogram/processor.rs:470
 #pragma unroll 1
       for (int wsel = 0; wsel < 3; ++wsel) {
         const float* win = wsel == 1 ? a.dwin : a.win;
@@ -260,13 +309,13 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
           if (wsel == 2) wv = ((float)n - (float)(kM - 1) * 0.5f) * wv;  // t*h, spectrogram/processor.rs:601-608
           v[j] = make_float2(c[j].x * wv, c[j].y * wv);
         }
-        fft_forward(v, sm.W, fa);
+        fft_forward<kTw>(v, sm.W, fa, ad);
         if (wsel == 0) {
 #pragma unroll
           for (int j = 0; j < kGroups; ++j) S[j] = v[j];
         } else if (wsel == 1) {
 #pragma unroll
-          for (int j = 0; j < kGroups; ++j) D[j] = v[j];
+          for (int j = 0; j < kGroups; ++j) nd[j] = v[j].y * S[j].x - v[j].x * S[j].y;
         }
         __syncthreads();  // pass-3 reads done before the next transform's pass-1 stores
       }
@@ -278,7 +327,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
       for (int j = 0; j < kGroups; ++j) {
         const int bin = t + kT * j;
         bool k = (j < 8 || t == 0);
-        if (k) k = reassign_bin(S[j], D[j], v[j], __ldg(&a.bin_norm[bin < (int)a.bins ? bin : 0]), bin, rc, &pts[j]);
+        if (k) k = reassign_bin_nd(S[j], nd[j], v[j], __ldg(&a.bin_norm[bin < (int)a.bins ? bin : 0]), bin, rc, &pts[j]);
         const unsigned m = __ballot_sync(0xffffffffu, k);
         if (lane_id == 0) sm.warp_cnt[j * kWarps + warp] = __popc(m);
         if (k) keep |= 1u << j;
@@ -324,7 +373,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) k_reassigned_fast(FastArgs fa)
 bool stft_fast_supported(const StftConfig& cfg, const DeviceInfo& dev) {
   if (!cfg.reassign || cfg.window != (uint64_t)kM || cfg.zero_pad != 1) return false;
   const uint64_t H = 2 * (uint64_t)kM;
-  if (cfg.hop < 256 || cfg.hop > (uint64_t)kM || (H % cfg.hop) != 0 || (cfg.hop % 4) != 0) return false;
+  if (cfg.hop < 512 || cfg.hop > (uint64_t)kM || (H % cfg.hop) != 0 || (cfg.hop % 512) != 0) return false;  // ring spans stay contiguous
   const size_t smem = sizeof(Smem) + (size_t)(H + cfg.hop) * sizeof(float);
   return dev.max_smem_optin == 0 || smem <= (size_t)dev.max_smem_optin;
 }
@@ -349,8 +398,14 @@ int stft_fast_prepare(StftPlan& plan) {
   }
   OMB_TRY(plan.d_fast_tables.upload(tab, plan.stream));
   const size_t smem = sizeof(Smem) + (size_t)(2 * kM + plan.cfg.hop) * sizeof(float);
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto k10 = k_reassigned_fast<1, 0>;
+  auto k20 = k_reassigned_fast<2, 0>;
+  auto k11 = k_reassigned_fast<1, 1>;
+  auto k21 = k_reassigned_fast<2, 1>;
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k10, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k20, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k11, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k21, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return OMB_OK;
 }
 
@@ -377,12 +432,19 @@ int launch_stft_fast(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   const size_t smem = sizeof(Smem) + (size_t)fa.ring_len * sizeof(float);
   // tuning knob (measurement only): OMB_FAST_MINB=1 trades occupancy (1 CTA/SM, no register cap) for zero spills
   static const int minb = [] { const char* e = getenv("OMB_FAST_MINB"); return e ? atoi(e) : 2; }();
-  auto k1 = k_reassigned_fast<1>;
-  auto k2 = k_reassigned_fast<2>;
-  if (minb == 1) {
-    OMB_LAUNCH(k1, dim3(grid), dim3(kT), smem, s, fa);
+  static const int twmode = [] { const char* e = getenv("OMB_FAST_TW"); return e ? atoi(e) : 0; }();
+  auto k10 = k_reassigned_fast<1, 0>;
+  auto k20 = k_reassigned_fast<2, 0>;
+  auto k11 = k_reassigned_fast<1, 1>;
+  auto k21 = k_reassigned_fast<2, 1>;
+  if (minb == 1 && twmode == 0) {
+    OMB_LAUNCH(k10, dim3(grid), dim3(kT), smem, s, fa);
+  } else if (minb == 1) {
+    OMB_LAUNCH(k11, dim3(grid), dim3(kT), smem, s, fa);
+  } else if (twmode == 0) {
+    OMB_LAUNCH(k20, dim3(grid), dim3(kT), smem, s, fa);
   } else {
-    OMB_LAUNCH(k2, dim3(grid), dim3(kT), smem, s, fa);
+    OMB_LAUNCH(k21, dim3(grid), dim3(kT), smem, s, fa);
   }
   OMB_CHECK_LAUNCH();
   return OMB_OK;
