@@ -21,6 +21,16 @@ constexpr float kC1 = 0.92387953251128673848f;  // cos(pi/8)
 constexpr float kS1 = 0.38268343236508978178f;  // sin(pi/8)
 constexpr float kH = 0.70710678118654752440f;   // sqrt(1/2)
 
+// cos / sin of 2*pi*j/32, j = 0..15
+__device__ constexpr float kCos32[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128673848f, 0.83146961230254523708f,
+                                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508978178f, 0.19509032201612826785f,
+                                         0.0f, -0.19509032201612826785f, -0.38268343236508978178f, -0.55557023301960222474f,
+                                         -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128673848f, -0.98078528040323044913f};
+__device__ constexpr float kSin32[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508978178f, 0.55557023301960222474f,
+                                         0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128673848f, 0.98078528040323044913f,
+                                         1.0f, 0.98078528040323044913f, 0.92387953251128673848f, 0.83146961230254523708f,
+                                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508978178f, 0.19509032201612826785f};
+
 template <bool INV>
 __device__ __forceinline__ float2 rot_mj(float2 a) {  // a * (-j) forward, a * (+j) inverse
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
@@ -68,6 +78,57 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 #pragma unroll
   for (int q0 = 0; q0 < 4; ++q0) radix4<INV>(v[4 * q0], v[4 * q0 + 1], v[4 * q0 + 2], v[4 * q0 + 3]);
   // transpose the 4x4 index (q1 + 4*q0 -> q0 + 4*q1) so the result is in natural order
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      const float2 t = v[a + 4 * b];
+      v[a + 4 * b] = v[b + 4 * a];
+      v[b + 4 * a] = t;
+    }
+}
+
+// Pruned variants: same transform, but only a subset of the 16 outputs is produced (the others are left
+// undefined).  kFirst9: outputs 0..8 (bins <= Nyquist of the analysis transforms);  kMid8: outputs 4..11
+// (the centre half of the inverse transform).  Only step 3 differs: X[q0 + 4 q1] needs q1 in {0,1} (+ q1 = 2 for
+// q0 = 0) resp. q1 in {1,2}.
+enum Prune { kAll = 0, kFirst9 = 1, kMid8 = 2 };
+
+template <bool INV, int kPrune>
+__device__ __forceinline__ void radix4_part(float2& a0, float2& a1, float2& a2, float2& a3, bool want2) {
+  const float2 s0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+  const float2 s1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+  const float2 s2 = make_float2(a1.x + a3.x, a1.y + a3.y);
+  const float2 s3 = rot_mj<INV>(make_float2(a1.x - a3.x, a1.y - a3.y));
+  if (kPrune == kFirst9) {
+    a0 = make_float2(s0.x + s2.x, s0.y + s2.y);
+    a1 = make_float2(s1.x + s3.x, s1.y + s3.y);
+    if (want2) a2 = make_float2(s0.x - s2.x, s0.y - s2.y);
+  } else {  // kMid8
+    a1 = make_float2(s1.x + s3.x, s1.y + s3.y);
+    a2 = make_float2(s0.x - s2.x, s0.y - s2.y);
+  }
+}
+
+template <bool INV, int kPrune>
+__device__ __forceinline__ void dft16p(float2 (&v)[16]) {
+  if (kPrune == kAll) {
+    dft16<INV>(v);
+    return;
+  }
+#pragma unroll
+  for (int j0 = 0; j0 < 4; ++j0) radix4<INV>(v[j0], v[j0 + 4], v[j0 + 8], v[j0 + 12]);
+  v[1 + 4 * 1] = mul_cs<INV>(v[1 + 4 * 1], kC1, kS1);
+  v[1 + 4 * 2] = mul_cs<INV>(v[1 + 4 * 2], kH, kH);
+  v[1 + 4 * 3] = mul_cs<INV>(v[1 + 4 * 3], kS1, kC1);
+  v[2 + 4 * 1] = mul_cs<INV>(v[2 + 4 * 1], kH, kH);
+  v[2 + 4 * 2] = rot_mj<INV>(v[2 + 4 * 2]);
+  v[2 + 4 * 3] = mul_cs<INV>(v[2 + 4 * 3], -kH, kH);
+  v[3 + 4 * 1] = mul_cs<INV>(v[3 + 4 * 1], kS1, kC1);
+  v[3 + 4 * 2] = mul_cs<INV>(v[3 + 4 * 2], -kH, kH);
+  v[3 + 4 * 3] = mul_cs<INV>(v[3 + 4 * 3], -kC1, -kS1);
+#pragma unroll
+  for (int q0 = 0; q0 < 4; ++q0) radix4_part<INV, kPrune>(v[4 * q0], v[4 * q0 + 1], v[4 * q0 + 2], v[4 * q0 + 3], q0 == 0);
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll

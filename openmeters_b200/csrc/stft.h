@@ -57,6 +57,7 @@ struct StftPlan {
   DeviceInfo dev;
   int kernel_choice = OMB_KERNEL_AUTO;
   bool fast = false;
+  int fast_kind = 0;  // 0 generic, 1 = stft_fast.cu, 2 = stft_fast2.cu
   float power_scale = 1.0f;
   std::vector<float> h_win, h_dwin, h_twin, h_norm;
   DeviceBuffer<float> d_win, d_dwin, d_twin, d_norm;
@@ -84,5 +85,8 @@ int launch_stft_generic(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s,
 bool stft_fast_supported(const StftConfig& cfg, const DeviceInfo& dev);
 int stft_fast_prepare(StftPlan& plan);
 int launch_stft_fast(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
+bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev);
+int stft_fast2_prepare(StftPlan& plan);
+int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
 
 }  // namespace omb

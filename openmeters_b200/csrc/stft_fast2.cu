@@ -1,0 +1,372 @@
+// stft_fast2.cu — second-generation specialised kernel for the reassigned STFT at N = 4096 (BASELINE configs[1]).
+//
+// Same mathematics as stft_fast.cu (5 complex 4096-point FFTs per frame: packed real forward FFT, fused
+// Hilbert pair step, one inverse, three windowed forward FFTs; see that file and DESIGN.md §4.1).  What changed
+// is the mapping onto the SM, driven by the round-1 ncu captures of the first kernel (issue-slot bound at 56 %
+// issue utilisation: L1 misses on the twiddle/window tables, register spills at 2 CTAs/SM):
+//
+//   * ONE 512-thread CTA per SM = two 256-thread groups, each running its own frame with its own named
+//     barrier (bar.sync 1+g, 256) — 16 warps/SM like 2 CTAs, but
+//   * the two groups work on CONSECUTIVE frames of the same lane and share one staging ring (H + 3*hop floats:
+//     frames f, f+1 in flight, two hops prefetched by 16-byte async copies one iteration ahead),
+//   * every table the inner loops read (W_4096 twiddles 30 KB, W_256 twiddles, window h, derivative window dh)
+//     lives in shared memory, loaded once per CTA: no global loads in the frame loop except the ring prefetch,
+//   * Im(c) of the analytic signal is parked in a 16 KB buffer Y straight from the pruned last inverse pass
+//     (only its centre half is needed); Re(c) is rebuilt from the ring where it is used, so the 32-register
+//     c[] array of the first kernel is gone,
+//   * the pair step uses Q[k] = cos(th_k) conj(Z[M-k]) + j sin(th_k) Z[k], th_k = 2 pi k / H (8 flops per bin),
+//   * last passes are pruned to the outputs that are used (9 of 16 bins per thread <= Nyquist; centre 8 of 16
+//     of the inverse).
+#include <cstdlib>
+
+#include "device_math.cuh"
+#include "fft16.cuh"
+#include "stft.h"
+
+namespace omb {
+
+namespace {
+
+constexpr int kM = 4096;
+constexpr int kT = 256;                  // threads per group
+constexpr int kGroupsPerCta = 2;
+constexpr int kThreads = kT * kGroupsPerCta;
+constexpr int kWarps = kT / 32;          // warps per group
+constexpr int kWSize = f16::phys_size(kM);
+constexpr int kBinGroups = 9;            // bins t + 256 j, j < 8, and bin 2048 (t = 0, j = 8)
+
+struct Fast2Args {
+  StftKernelArgs a;
+  const float2* tw1;   // global: [15][256] W_4096^{b q}
+  const float2* tw2;   // global: [15][16]  W_256^{o q}
+  uint32_t frames_per_run, runs_per_lane, ring_len;
+  float norm_ac, norm_dc;  // bin_norm[k] for 0 < k < N/2 and for k in {0, N/2} (window.rs:100-108)
+};
+
+struct GroupSmem {
+  float2 W[kWSize];
+  float Y[kM];                           // y[off + n] = Im c[n]
+  int warp_cnt[kBinGroups * kWarps];
+  int offs[kBinGroups * kWarps + 1];
+  float x0_xm[2];
+};
+
+struct Smem2 {
+  float2 tw1[15 * kT];
+  float2 tw2[15 * 16];
+  float h[kM];
+  float dh[kM];
+  GroupSmem g[kGroupsPerCta];
+  // float ring[ring_len] follows
+};
+
+__device__ __forceinline__ void group_sync(int g) {
+#ifdef OMB_EMU
+  omb_emu::named_sync(1 + g, kT);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kT) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void async_copy16(float* dst_smem, const float* src_gmem) {
+#ifdef OMB_EMU
+  for (int i = 0; i < 4; ++i) dst_smem[i] = src_gmem[i];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem));
+#endif
+}
+__device__ __forceinline__ void async_commit() {
+#ifndef OMB_EMU
+  asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+__device__ __forceinline__ void async_wait_all() {
+#ifndef OMB_EMU
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
+// Copies lane samples [s0, s1) (multiples of 4) into the ring at (sample index mod ring_len); all CTA threads.
+__device__ __forceinline__ void ring_fetch(float* ring, int ring_len, const float* x, uint64_t s0, uint64_t s1) {
+  for (uint64_t s = s0 + 4ull * threadIdx.x; s < s1; s += 4ull * kThreads) async_copy16(ring + (int)(s % (uint64_t)ring_len), x + s);
+}
+
+__device__ __forceinline__ int wrap(int i, int ring_len) { return i >= ring_len ? i - ring_len : i; }
+
+template <bool INV>
+__device__ __forceinline__ void twiddle15(float2 (&v)[16], const float2* tab, int stride) {
+#pragma unroll
+  for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], tab[(q - 1) * stride]);
+}
+
+struct Addr {
+  int pA, pB, pC;
+};
+
+// DIF forward: v holds elements t + 256 j (access A). On return v[j] = X[t + 256 j] (only the kPrune subset).
+template <int kPrune>
+__device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const float2* tw1t, const float2* tw2o, const Addr& ad, int g) {
+  f16::dft16<false>(v);
+  twiddle15<false>(v, tw1t, kT);
+  float2* wa = W + ad.pA;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wa[273 * q] = v[q];
+  group_sync(g);
+  float2* wb = W + ad.pB;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
+  f16::dft16<false>(v);
+  twiddle15<false>(v, tw2o, 16);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
+  group_sync(g);
+  const float2* wc = W + ad.pC;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = wc[j];
+  f16::dft16p<false, kPrune>(v);
+}
+
+template <int kVariant>
+__global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
+  OMB_DYN_SMEM(unsigned char, smem_raw);
+  Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
+  float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
+  const StftKernelArgs& a = fa.a;
+  const int tid = threadIdx.x, g = tid >> 8, t = tid & (kT - 1), lane_id = t & 31, warp = t >> 5;
+  GroupSmem& gs = sm.g[g];
+  const int hop = (int)a.hop, H = 2 * kM, ring_len = (int)fa.ring_len;
+  const int off = (H - kM) / 2;
+  const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
+  const ReassignConsts rc{a.bin_hz, a.max_hz, a.inv_2pi, a.inv_hop, a.latency_hops};
+
+  // ---- one-off: tables into shared memory
+  for (int i = tid; i < 15 * kT; i += kThreads) sm.tw1[i] = __ldg(&fa.tw1[i]);
+  for (int i = tid; i < 15 * 16; i += kThreads) sm.tw2[i] = __ldg(&fa.tw2[i]);
+  for (int i = tid; i < kM; i += kThreads) {
+    sm.h[i] = __ldg(&a.win[i]);
+    sm.dh[i] = __ldg(&a.dwin[i]);
+  }
+  // per-thread constants
+  Addr ad;
+  ad.pA = t + (t >> 4);
+  ad.pB = 273 * (t >> 4) + (t & 15);
+  ad.pC = 273 * (t & 15) + 17 * (t >> 4);
+  const float2* tw1t = sm.tw1 + t;
+  const float2* tw2o = sm.tw2 + (t & 15);
+  float cos_t, sin_t;  // th_t = 2 pi t / H
+  {
+    sincospif((float)t / (float)kM, &sin_t, &cos_t);  // th_t = 2 pi t / 8192 = pi * (t / 4096); one-off per thread
+  }
+  const float sign = (t & 1) ? -1.0f : 1.0f;
+  const float ramp0 = (float)t - (float)(kM - 1) * 0.5f;  // n - (N-1)/2 at j = 0
+  const int pt = (kT - t) & (kT - 1);
+  const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
+  __syncthreads();
+
+  for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
+    const uint64_t lane = run / fa.runs_per_lane;
+    const uint64_t f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
+    const uint64_t f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+    const float* x = a.lanes + lane * a.lane_stride;
+    const uint64_t s_end = (f_end - 1) * (uint64_t)hop + (uint64_t)H;  // one past the last sample this run reads
+    // prime: everything frames f_begin and f_begin+1 read
+    {
+      const uint64_t s0 = f_begin * (uint64_t)hop;
+      const uint64_t s1 = s0 + (uint64_t)H + (uint64_t)hop < s_end ? s0 + (uint64_t)H + (uint64_t)hop : s_end;
+      ring_fetch(ring, ring_len, x, s0, s1);
+      async_commit();
+    }
+    for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kGroupsPerCta) {
+      async_wait_all();
+      __syncthreads();  // ring holds frames fa0, fa0+1; both groups are done with the previous pair
+      {                 // prefetch what the next pair adds: two hops
+        const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)hop;
+        const uint64_t s1 = s0 + 2ull * hop < s_end ? s0 + 2ull * hop : s_end;
+        if (s0 < s1) ring_fetch(ring, ring_len, x, s0, s1);
+        async_commit();
+      }
+      const uint64_t f = fa0 + g;
+      if (f < f_end) {
+        const int r0 = (int)((f * (uint64_t)hop) % (uint64_t)ring_len);
+        float2 v[16];
+        // ---- F: z[n] = x[2n] + j x[2n+1], n = t + 256 j
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int sj = wrap(r0 + 2 * kT * j, ring_len);  // group-uniform (multiples of 512)
+          v[j] = *reinterpret_cast<const float2*>(ring + sj + 2 * t);
+        }
+        fft_forward<f16::kAll>(v, gs.W, tw1t, tw2o, ad, g);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) gs.W[ad.pC + q] = v[q];
+        if (t == 0) {
+          gs.x0_xm[0] = v[0].x + v[0].y;
+          gs.x0_xm[1] = v[0].x - v[0].y;
+        }
+        group_sync(g);
+        // ---- X: Q[k] = cos(th_k) conj(Z[M-k]) + j sin(th_k) Z[k], k = t + 256 j, th_k = th_t + 2 pi j / 32
+        {
+          const float2* wp = gs.W + pPartner;
+          float2 zp[16];
+          if (t == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) zp[j] = wp[(16 - j) & 15];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) zp[j] = wp[15 - j];
+          }
+          group_sync(g);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float cj = f16::kCos32[j], sj = f16::kSin32[j];
+            const float ck = cos_t * cj - sin_t * sj;
+            const float sk = sin_t * cj + cos_t * sj;
+            const float2 z = v[j];
+            v[j] = make_float2(ck * zp[j].x - sk * z.y, sk * z.x - ck * zp[j].y);
+          }
+          if (t == 0) v[0] = make_float2(0.0f, 0.0f);
+        }
+        // ---- I: inverse, DIT, thread t holds Q[t + 256 j]; result y -> gs.Y
+        {
+          f16::dft16<true>(v);
+          float2* wc = gs.W + ad.pC;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) wc[q] = v[q];
+          group_sync(g);
+          float2* wb = gs.W + ad.pB;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
+          twiddle15<true>(v, tw2o, 16);
+          f16::dft16<true>(v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
+          group_sync(g);
+          const float2* wa = gs.W + ad.pA;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = wa[273 * j];
+          twiddle15<true>(v, tw1t, kT);
+          f16::dft16p<true, f16::kMid8>(v);
+          // q[m], m = t + 256 m2, m2 = 4..11 -> Y as float2[m - 1024]
+          float2* y2 = reinterpret_cast<float2*>(gs.Y) + t;
+#pragma unroll
+          for (int q = 4; q < 12; ++q) y2[kT * (q - 4)] = v[q];
+          group_sync(g);
+        }
+        // ---- G: three windowed transforms of c[n] = (M x[off+n] + bias) + j Y[n]
+        const float bias = sign * 0.5f * gs.x0_xm[1] - 0.5f * gs.x0_xm[0];
+        float2 S[kBinGroups];
+        float nd[kBinGroups];
+#pragma unroll 1
+        for (int wsel = 0; wsel < 3; ++wsel) {
+          const float* win = (wsel == 1 ? sm.dh : sm.h) + t;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int sj = wrap(r0 + off + kT * j, ring_len);  // group-uniform
+            float wv = win[kT * j];
+            if (wsel == 2) wv *= ramp0 + (float)(kT * j);       // t*h window, processor.rs:601-608
+            const float cx = fmaf((float)kM, ring[sj + t], bias);
+            v[j] = make_float2(cx * wv, gs.Y[t + kT * j] * wv);
+          }
+          fft_forward<f16::kFirst9>(v, gs.W, tw1t, tw2o, ad, g);
+          if (wsel == 0) {
+#pragma unroll
+            for (int j = 0; j < kBinGroups; ++j) S[j] = v[j];
+          } else if (wsel == 1) {
+#pragma unroll
+            for (int j = 0; j < kBinGroups; ++j) nd[j] = v[j].y * S[j].x - v[j].x * S[j].y;
+          }
+          group_sync(g);  // pass-3 reads done before the next pass-1 stores (and before warp_cnt reuse)
+        }
+        // ---- R: reassignment + ordered compaction
+        omb_spectrogram_point pts[kBinGroups];
+        int rank[kBinGroups];
+        unsigned keep = 0;
+#pragma unroll
+        for (int j = 0; j < kBinGroups; ++j) {
+          const int bin = t + kT * j;
+          bool k = (j < 8 || t == 0);
+          const float norm = (bin == 0 || j == 8) ? fa.norm_dc : fa.norm_ac;
+          if (k) k = reassign_bin_nd(S[j], nd[j], v[j], norm, bin, rc, &pts[j]);
+          const unsigned m = __ballot_sync(0xffffffffu, k);
+          if (lane_id == 0) gs.warp_cnt[j * kWarps + warp] = __popc(m);
+          if (k) keep |= 1u << j;
+          rank[j] = __popc(m & ((1u << lane_id) - 1u));
+        }
+        group_sync(g);
+        if (warp == 0) {
+          int c0 = 0, c1 = 0, c2 = 0;
+          const int i0 = lane_id * 3;
+          if (i0 + 0 < kBinGroups * kWarps) c0 = gs.warp_cnt[i0 + 0];
+          if (i0 + 1 < kBinGroups * kWarps) c1 = gs.warp_cnt[i0 + 1];
+          if (i0 + 2 < kBinGroups * kWarps) c2 = gs.warp_cnt[i0 + 2];
+          const int tot = c0 + c1 + c2;
+          int incl = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane_id >= o) incl += n;
+          }
+          const int excl = incl - tot;
+          if (i0 + 0 < kBinGroups * kWarps) gs.offs[i0 + 0] = excl;
+          if (i0 + 1 < kBinGroups * kWarps) gs.offs[i0 + 1] = excl + c0;
+          if (i0 + 2 < kBinGroups * kWarps) gs.offs[i0 + 2] = excl + c0 + c1;
+          if (lane_id == 31) gs.offs[kBinGroups * kWarps] = incl;
+        }
+        group_sync(g);
+        {
+          const uint64_t slot = lane * a.frames_per_lane + f;
+          omb_spectrogram_point* out = a.out_points + slot * a.point_stride;
+#pragma unroll
+          for (int j = 0; j < kBinGroups; ++j)
+            if (keep & (1u << j)) out[gs.offs[j * kWarps + warp] + rank[j]] = pts[j];
+          if (t == 0) a.out_counts[slot] = (uint32_t)gs.offs[kBinGroups * kWarps];
+        }
+      }
+    }
+    async_wait_all();
+    __syncthreads();
+  }
+}
+
+size_t smem_bytes(uint64_t hop) { return sizeof(Smem2) + (size_t)(2 * kM + 3 * hop) * sizeof(float); }
+
+}  // namespace
+
+bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev) {
+  if (!cfg.reassign || cfg.window != (uint64_t)kM || cfg.zero_pad != 1) return false;
+  if (cfg.hop < 512 || (cfg.hop % 512) != 0 || ((2 * (uint64_t)kM + 3 * cfg.hop) % 512) != 0) return false;
+  return dev.max_smem_optin == 0 || smem_bytes(cfg.hop) <= (size_t)dev.max_smem_optin;
+}
+
+int stft_fast2_prepare(StftPlan& plan) {
+  auto k0 = k_reassigned_fast2<0>;
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(plan.cfg.hop)));
+  return OMB_OK;
+}
+
+int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  if (per_lane == 0 || a.n_lanes == 0) return OMB_OK;
+  if ((reinterpret_cast<uintptr_t>(a.lanes) & 15u) != 0 || (a.lane_stride % 4) != 0)
+    return fail(OMB_ERR_INVALID, "specialised STFT kernel needs 16-byte aligned lanes (pointer and lane_stride % 4 == 0)");
+  Fast2Args fa{};
+  fa.a = a;
+  fa.tw1 = plan.d_fast_tables.ptr;
+  fa.tw2 = fa.tw1 + 15 * kT;
+  fa.ring_len = (uint32_t)(2 * kM + 3 * a.hop);
+  fa.norm_ac = plan.h_norm.size() > 1 ? plan.h_norm[1] : plan.h_norm[0];
+  fa.norm_dc = plan.h_norm[0];
+  const uint64_t ctas = (uint64_t)std::max(plan.dev.sm_count, 1);
+  uint64_t run = 128;  // even, so both groups stay busy; long enough to amortise the ring prime
+  while (run > 16 && ((per_lane + run - 1) / run) * a.n_lanes < ctas * 6) run >>= 1;
+  fa.frames_per_run = (uint32_t)std::min<uint64_t>(run, per_lane);
+  fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
+  const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
+  const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  auto k0 = k_reassigned_fast2<0>;
+  OMB_LAUNCH(k0, dim3(grid), dim3(kThreads), smem_bytes(a.hop), s, fa);
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+}  // namespace omb

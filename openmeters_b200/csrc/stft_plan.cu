@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace omb {
 
@@ -65,9 +66,18 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
   OMB_TRY(d_tw_fft.upload(make_twiddles((size_t)F, (size_t)std::max<uint64_t>(F / 2, 1)), stream));
 
   fast = false;
+  fast_kind = 0;
+  // OMB_FAST_KERNEL=1|2 pins the specialised kernel generation (measurement / cross-checks); default: newest that fits
+  const char* pin = getenv("OMB_FAST_KERNEL");
+  const int want = pin ? atoi(pin) : 2;
   if (choice != OMB_KERNEL_GENERIC && stft_fast_supported(cfg, dev)) {
-    OMB_TRY(stft_fast_prepare(*this));
+    OMB_TRY(stft_fast_prepare(*this));  // uploads the twiddle tables both generations use
     fast = true;
+    fast_kind = 1;
+    if (want >= 2 && stft_fast2_supported(cfg, dev)) {
+      OMB_TRY(stft_fast2_prepare(*this));
+      fast_kind = 2;
+    }
   } else if (choice == OMB_KERNEL_FAST) {
     return fail(OMB_ERR_UNSUPPORTED, "no specialised kernel for window %llu hop %llu zp %llu reassign %d",
                 (unsigned long long)N, (unsigned long long)cfg.hop, (unsigned long long)cfg.zero_pad, (int)cfg.reassign);
@@ -118,6 +128,7 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   a.point_stride = point_stride;
   a.out_counts = out_counts;
   a.out_classic = out_classic;
+  if (fast_kind == 2) return launch_stft_fast2(*this, a, s);
   if (fast) return launch_stft_fast(*this, a, s);
   return launch_stft_generic(*this, a, s, d_scratch);
 }

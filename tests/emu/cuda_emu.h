@@ -81,7 +81,10 @@ struct WarpState {
   int gen = 0;
 };
 
+struct NamedBar { int arrived = 0; int gen = 0; };
+
 struct BlockState {
+  NamedBar named[16];
   dim3 grid, block;
   uint3 bidx{0, 0, 0};
   unsigned nthreads = 0;
@@ -115,6 +118,18 @@ inline void syncthreads() {
     b.gen++;
   } else {
     while (b.gen == gen) yield();
+  }
+}
+
+// bar.sync id, count
+inline void named_sync(int id, int count) {
+  NamedBar& nb = blk().named[id & 15];
+  const int gen = nb.gen;
+  if (++nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+  } else {
+    while (nb.gen == gen) yield();
   }
 }
 
@@ -174,6 +189,7 @@ inline void run_block(BlockState& b) {
   b.arrived = 0;
   b.gen = 0;
   for (auto& w : b.warps) { w.arrived = 0; w.gen = 0; }
+  for (auto& n : b.named) { n.arrived = 0; n.gen = 0; }
   const size_t stack_bytes = 192 * 1024;
   unsigned lin = 0;
   for (unsigned z = 0; z < b.block.z; ++z)
@@ -309,6 +325,7 @@ static inline double __fma_rn(double a, double b, double c) { return std::fma(a,
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(3.14159265358979323846 * (double)x); *c = (float)std::cos(3.14159265358979323846 * (double)x); }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }

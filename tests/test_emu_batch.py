@@ -44,3 +44,21 @@ def test_loudness_batch_two_streams_stereo(emu):
     a = synth.cfg1_stereo(0.2)
     b = (a * np.float32(0.25)).astype(np.float32)
     cases.loudness_parity(emu.api, LoudnessConfig(), 2, None, np.stack([a, b]), 500)
+
+
+@pytest.mark.parametrize("gen", ["1", "2"])
+def test_specialised_reassigned_kernels(emu, gen, monkeypatch):
+    """Both generations of the specialised N=4096 kernel (stft_fast.cu / stft_fast2.cu) under the emulator:
+    multi-run work split, odd frame counts (one idle group in the last pair), 3 lanes."""
+    monkeypatch.setenv("OMB_FAST_KERNEL", gen)
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    lanes = synth.cfg2_lanes(3, (8192 + 40 * 1024) / 48000.0)  # 41 frames per lane
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 3 * 41 and st["unmatched"] <= 4
+
+
+def test_specialised_kernel_other_hops_and_windows(emu):
+    for hop, win in ((512, capi.WINDOW_HANN), (2048, capi.WINDOW_BLACKMAN)):
+        cfg = SpectrogramConfig(fft_size=4096, hop_size=hop, window=win, use_reassignment=True)
+        lanes = synth.cfg2_lanes(1, (8192 + 6 * hop) / 48000.0)
+        cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
