@@ -94,10 +94,28 @@ __device__ __forceinline__ void ring_fetch(float* ring, int ring_len, const floa
 
 __device__ __forceinline__ int wrap(int i, int ring_len) { return i >= ring_len ? i - ring_len : i; }
 
-template <bool INV>
+// kTw = 0: 15 table loads (shared memory).  kTw = 1: 4 loads (q = 1, 2, 4, 8) + 11 products — trades 11
+// shared-memory loads for 44 flops (each derived twiddle is at most two multiplications from a table entry).
+template <bool INV, int kTw>
 __device__ __forceinline__ void twiddle15(float2 (&v)[16], const float2* tab, int stride) {
+  if (kTw == 0) {
 #pragma unroll
-  for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], tab[(q - 1) * stride]);
+    for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], tab[(q - 1) * stride]);
+  } else {
+    float2 w[16];
+    w[1] = tab[0 * stride];
+    w[2] = tab[1 * stride];
+    w[4] = tab[3 * stride];
+    w[8] = tab[7 * stride];
+    w[3] = cmul(w[1], w[2]);
+    w[5] = cmul(w[1], w[4]);
+    w[6] = cmul(w[2], w[4]);
+    w[7] = cmul(w[3], w[4]);
+#pragma unroll
+    for (int q = 9; q < 16; ++q) w[q] = cmul(w[q - 8], w[8]);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], w[q]);
+  }
 }
 
 struct Addr {
@@ -105,10 +123,10 @@ struct Addr {
 };
 
 // DIF forward: v holds elements t + 256 j (access A). On return v[j] = X[t + 256 j] (only the kPrune subset).
-template <int kPrune>
+template <int kPrune, int kTw1, int kTw2>
 __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const float2* tw1t, const float2* tw2o, const Addr& ad, int g) {
   f16::dft16<false>(v);
-  twiddle15<false>(v, tw1t, kT);
+  twiddle15<false, kTw1>(v, tw1t, kT);
   float2* wa = W + ad.pA;
 #pragma unroll
   for (int q = 0; q < 16; ++q) wa[273 * q] = v[q];
@@ -117,7 +135,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const fl
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
   f16::dft16<false>(v);
-  twiddle15<false>(v, tw2o, 16);
+  twiddle15<false, kTw2>(v, tw2o, 16);
 #pragma unroll
   for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
   group_sync(g);
@@ -127,13 +145,16 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const fl
   f16::dft16p<false, kPrune>(v);
 }
 
+// kVariant bit 0: pass-1 twiddles computed (kTw1 = 1); bit 1: pass-2 twiddles computed (kTw2 = 1).
 template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
+  constexpr int kTw1 = kVariant & 1, kTw2 = (kVariant >> 1) & 1;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
   float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
   const StftKernelArgs& a = fa.a;
-  const int tid = threadIdx.x, g = tid >> 8, t = tid & (kT - 1), lane_id = t & 31, warp = t >> 5;
+  const int tid = threadIdx.x, t = tid & (kT - 1), lane_id = t & 31, warp = t >> 5;
+  const int g = __shfl_sync(0xffffffffu, tid >> 8, 0);  // warp-uniform by construction; tells the compiler so
   GroupSmem& gs = sm.g[g];
   const int hop = (int)a.hop, H = 2 * kM, ring_len = (int)fa.ring_len;
   const int off = (H - kM) / 2;
@@ -191,12 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         const int r0 = (int)((f * (uint64_t)hop) % (uint64_t)ring_len);
         float2 v[16];
         // ---- F: z[n] = x[2n] + j x[2n+1], n = t + 256 j
+        // ring spans never straddle the wrap inside a 512-float step; jw = first step past the wrap (warp-uniform)
+        const int jw = (ring_len - r0) >> 9;
+        const float* rf = ring + r0 + 2 * t;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int sj = wrap(r0 + 2 * kT * j, ring_len);  // group-uniform (multiples of 512)
-          v[j] = *reinterpret_cast<const float2*>(ring + sj + 2 * t);
-        }
-        fft_forward<f16::kAll>(v, gs.W, tw1t, tw2o, ad, g);
+        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(rf + 2 * kT * j - (j >= jw ? ring_len : 0));
+        fft_forward<f16::kAll, kTw1, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
 #pragma unroll
         for (int q = 0; q < 16; ++q) gs.W[ad.pC + q] = v[q];
         if (t == 0) {
@@ -236,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           float2* wb = gs.W + ad.pB;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
-          twiddle15<true>(v, tw2o, 16);
+          twiddle15<true, kTw2>(v, tw2o, 16);
           f16::dft16<true>(v);
 #pragma unroll
           for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           const float2* wa = gs.W + ad.pA;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wa[273 * j];
-          twiddle15<true>(v, tw1t, kT);
+          twiddle15<true, kTw1>(v, tw1t, kT);
           f16::dft16p<true, f16::kMid8>(v);
           // q[m], m = t + 256 m2, m2 = 4..11 -> Y as float2[m - 1024]
           float2* y2 = reinterpret_cast<float2*>(gs.Y) + t;
@@ -259,15 +280,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
 #pragma unroll 1
         for (int wsel = 0; wsel < 3; ++wsel) {
           const float* win = (wsel == 1 ? sm.dh : sm.h) + t;
+          const int jg = (ring_len - r0 - off) >> 8;  // first 256-float step past the wrap (may be <= 0 or >= 16)
+          const float* rg = ring + r0 + off + t;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int sj = wrap(r0 + off + kT * j, ring_len);  // group-uniform
             float wv = win[kT * j];
             if (wsel == 2) wv *= ramp0 + (float)(kT * j);       // t*h window, processor.rs:601-608
-            const float cx = fmaf((float)kM, ring[sj + t], bias);
+            const float cx = fmaf((float)kM, rg[kT * j - (j >= jg ? ring_len : 0)], bias);
             v[j] = make_float2(cx * wv, gs.Y[t + kT * j] * wv);
           }
-          fft_forward<f16::kFirst9>(v, gs.W, tw1t, tw2o, ad, g);
+          fft_forward<f16::kFirst9, kTw1, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
           if (wsel == 0) {
 #pragma unroll
             for (int j = 0; j < kBinGroups; ++j) S[j] = v[j];
@@ -340,7 +362,14 @@ bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev) {
 
 int stft_fast2_prepare(StftPlan& plan) {
   auto k0 = k_reassigned_fast2<0>;
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(plan.cfg.hop)));
+  auto k1 = k_reassigned_fast2<1>;
+  auto k2 = k_reassigned_fast2<2>;
+  auto k3 = k_reassigned_fast2<3>;
+  const int smem = (int)smem_bytes(plan.cfg.hop);
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
 }
 
@@ -363,8 +392,18 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  static const int variant = [] { const char* e = getenv("OMB_FAST2_VARIANT"); return e ? atoi(e) & 3 : 0; }();
   auto k0 = k_reassigned_fast2<0>;
-  OMB_LAUNCH(k0, dim3(grid), dim3(kThreads), smem_bytes(a.hop), s, fa);
+  auto k1 = k_reassigned_fast2<1>;
+  auto k2 = k_reassigned_fast2<2>;
+  auto k3 = k_reassigned_fast2<3>;
+  const size_t smem = smem_bytes(a.hop);
+  switch (variant) {
+    case 1: OMB_LAUNCH(k1, dim3(grid), dim3(kThreads), smem, s, fa); break;
+    case 2: OMB_LAUNCH(k2, dim3(grid), dim3(kThreads), smem, s, fa); break;
+    case 3: OMB_LAUNCH(k3, dim3(grid), dim3(kThreads), smem, s, fa); break;
+    default: OMB_LAUNCH(k0, dim3(grid), dim3(kThreads), smem, s, fa); break;
+  }
   OMB_CHECK_LAUNCH();
   return OMB_OK;
 }
