@@ -52,7 +52,7 @@ struct GroupSmem {
 };
 
 struct Smem2 {
-  float2 tw1[15 * kT];
+  float2 tw1[4 * kT];   // rows q = 1, 2, 4, 8 of W_4096^{b q}; the other 11 are products (twiddle15<kTw = 1>)
   float2 tw2[15 * 16];
   float h[kM];
   float dh[kM];
@@ -88,15 +88,13 @@ __device__ __forceinline__ void async_wait_all() {
 }
 
 // Copies lane samples [s0, s1) (multiples of 4) into the ring at (sample index mod ring_len); all CTA threads.
-__device__ __forceinline__ void ring_fetch(float* ring, int ring_len, const float* x, uint64_t s0, uint64_t s1) {
-  for (uint64_t s = s0 + 4ull * threadIdx.x; s < s1; s += 4ull * kThreads) async_copy16(ring + (int)(s % (uint64_t)ring_len), x + s);
+__device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const float* x, uint64_t s0, uint64_t s1) {
+  for (uint64_t s = s0 + 4ull * threadIdx.x; s < s1; s += 4ull * kThreads) async_copy16(ring + ((int)s & ring_mask), x + s);
 }
-
-__device__ __forceinline__ int wrap(int i, int ring_len) { return i >= ring_len ? i - ring_len : i; }
 
 // kTw = 0: 15 table loads (shared memory).  kTw = 1: 4 loads (q = 1, 2, 4, 8) + 11 products — trades 11
 // shared-memory loads for 44 flops (each derived twiddle is at most two multiplications from a table entry).
-template <bool INV, int kTw>
+template <bool INV, int kTw, bool kCompact>
 __device__ __forceinline__ void twiddle15(float2 (&v)[16], const float2* tab, int stride) {
   if (kTw == 0) {
 #pragma unroll
@@ -104,9 +102,9 @@ __device__ __forceinline__ void twiddle15(float2 (&v)[16], const float2* tab, in
   } else {
     float2 w[16];
     w[1] = tab[0 * stride];
-    w[2] = tab[1 * stride];
-    w[4] = tab[3 * stride];
-    w[8] = tab[7 * stride];
+    w[2] = tab[(kCompact ? 1 : 1) * stride];
+    w[4] = tab[(kCompact ? 2 : 3) * stride];
+    w[8] = tab[(kCompact ? 3 : 7) * stride];
     w[3] = cmul(w[1], w[2]);
     w[5] = cmul(w[1], w[4]);
     w[6] = cmul(w[2], w[4]);
@@ -123,10 +121,10 @@ struct Addr {
 };
 
 // DIF forward: v holds elements t + 256 j (access A). On return v[j] = X[t + 256 j] (only the kPrune subset).
-template <int kPrune, int kTw1, int kTw2>
+template <int kPrune, int kTw2>
 __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const float2* tw1t, const float2* tw2o, const Addr& ad, int g) {
   f16::dft16<false>(v);
-  twiddle15<false, kTw1>(v, tw1t, kT);
+  twiddle15<false, 1, true>(v, tw1t, kT);
   float2* wa = W + ad.pA;
 #pragma unroll
   for (int q = 0; q < 16; ++q) wa[273 * q] = v[q];
@@ -135,7 +133,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const fl
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
   f16::dft16<false>(v);
-  twiddle15<false, kTw2>(v, tw2o, 16);
+  twiddle15<false, kTw2, false>(v, tw2o, 16);
 #pragma unroll
   for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
   group_sync(g);
@@ -145,10 +143,12 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const fl
   f16::dft16p<false, kPrune>(v);
 }
 
-// kVariant bit 0: pass-1 twiddles computed (kTw1 = 1); bit 1: pass-2 twiddles computed (kTw2 = 1).
+// kVariant bit 0: pass-2 twiddles computed from 4 loads (kTw2 = 1) instead of 15 table loads.
+// (Pass-1 twiddles are always computed from the 4 rows kept in shared memory: measured fastest, and the 22 KB
+// saved pay for the power-of-two ring.)
 template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
-  constexpr int kTw1 = kVariant & 1, kTw2 = (kVariant >> 1) & 1;
+  constexpr int kTw2 = kVariant & 1;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
   float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
@@ -156,13 +156,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   const int tid = threadIdx.x, t = tid & (kT - 1), lane_id = t & 31, warp = t >> 5;
   const int g = __shfl_sync(0xffffffffu, tid >> 8, 0);  // warp-uniform by construction; tells the compiler so
   GroupSmem& gs = sm.g[g];
-  const int hop = (int)a.hop, H = 2 * kM, ring_len = (int)fa.ring_len;
+  const int hop = (int)a.hop, H = 2 * kM, ring_mask = (int)fa.ring_len - 1;  // ring_len is a power of two
   const int off = (H - kM) / 2;
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   const ReassignConsts rc{a.bin_hz, a.max_hz, a.inv_2pi, a.inv_hop, a.latency_hops};
 
   // ---- one-off: tables into shared memory
-  for (int i = tid; i < 15 * kT; i += kThreads) sm.tw1[i] = __ldg(&fa.tw1[i]);
+  for (int i = tid; i < 4 * kT; i += kThreads) {
+    const int row = (1 << (i >> 8)) - 1;  // q - 1 for q = 1, 2, 4, 8
+    sm.tw1[i] = __ldg(&fa.tw1[row * kT + (i & (kT - 1))]);
+  }
   for (int i = tid; i < 15 * 16; i += kThreads) sm.tw2[i] = __ldg(&fa.tw2[i]);
   for (int i = tid; i < kM; i += kThreads) {
     sm.h[i] = __ldg(&a.win[i]);
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
     {
       const uint64_t s0 = f_begin * (uint64_t)hop;
       const uint64_t s1 = s0 + (uint64_t)H + (uint64_t)hop < s_end ? s0 + (uint64_t)H + (uint64_t)hop : s_end;
-      ring_fetch(ring, ring_len, x, s0, s1);
+      ring_fetch(ring, ring_mask, x, s0, s1);
       async_commit();
     }
     for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kGroupsPerCta) {
@@ -204,20 +207,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
       {                 // prefetch what the next pair adds: two hops
         const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)hop;
         const uint64_t s1 = s0 + 2ull * hop < s_end ? s0 + 2ull * hop : s_end;
-        if (s0 < s1) ring_fetch(ring, ring_len, x, s0, s1);
+        if (s0 < s1) ring_fetch(ring, ring_mask, x, s0, s1);
         async_commit();
       }
       const uint64_t f = fa0 + g;
       if (f < f_end) {
-        const int r0 = (int)((f * (uint64_t)hop) % (uint64_t)ring_len);
+        const int r0 = (int)(f * (uint64_t)hop) & ring_mask;  // multiple of 512
         float2 v[16];
         // ---- F: z[n] = x[2n] + j x[2n+1], n = t + 256 j
-        // ring spans never straddle the wrap inside a 512-float step; jw = first step past the wrap (warp-uniform)
-        const int jw = (ring_len - r0) >> 9;
-        const float* rf = ring + r0 + 2 * t;
+        // ring position of sample s is s & mask; (r0 + 512 j) & mask is warp-uniform, 2t < 512 never carries
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(rf + 2 * kT * j - (j >= jw ? ring_len : 0));
-        fft_forward<f16::kAll, kTw1, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
+        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(ring + ((r0 + 2 * kT * j) & ring_mask) + 2 * t);
+        fft_forward<f16::kAll, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
 #pragma unroll
         for (int q = 0; q < 16; ++q) gs.W[ad.pC + q] = v[q];
         if (t == 0) {
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           float2* wb = gs.W + ad.pB;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
-          twiddle15<true, kTw2>(v, tw2o, 16);
+          twiddle15<true, kTw2, false>(v, tw2o, 16);
           f16::dft16<true>(v);
 #pragma unroll
           for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           const float2* wa = gs.W + ad.pA;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wa[273 * j];
-          twiddle15<true, kTw1>(v, tw1t, kT);
+          twiddle15<true, 1, true>(v, tw1t, kT);
           f16::dft16p<true, f16::kMid8>(v);
           // q[m], m = t + 256 m2, m2 = 4..11 -> Y as float2[m - 1024]
           float2* y2 = reinterpret_cast<float2*>(gs.Y) + t;
@@ -280,16 +281,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
 #pragma unroll 1
         for (int wsel = 0; wsel < 3; ++wsel) {
           const float* win = (wsel == 1 ? sm.dh : sm.h) + t;
-          const int jg = (ring_len - r0 - off) >> 8;  // first 256-float step past the wrap (may be <= 0 or >= 16)
-          const float* rg = ring + r0 + off + t;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float wv = win[kT * j];
             if (wsel == 2) wv *= ramp0 + (float)(kT * j);       // t*h window, processor.rs:601-608
-            const float cx = fmaf((float)kM, rg[kT * j - (j >= jg ? ring_len : 0)], bias);
+            const float cx = fmaf((float)kM, ring[((r0 + off + kT * j) & ring_mask) + t], bias);
             v[j] = make_float2(cx * wv, gs.Y[t + kT * j] * wv);
           }
-          fft_forward<f16::kFirst9, kTw1, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
+          fft_forward<f16::kFirst9, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
           if (wsel == 0) {
 #pragma unroll
             for (int j = 0; j < kBinGroups; ++j) S[j] = v[j];
@@ -337,10 +336,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         group_sync(g);
         {
           const uint64_t slot = lane * a.frames_per_lane + f;
-          omb_spectrogram_point* out = a.out_points + slot * a.point_stride;
+          float* out = reinterpret_cast<float*>(a.out_points + slot * a.point_stride);
 #pragma unroll
           for (int j = 0; j < kBinGroups; ++j)
-            if (keep & (1u << j)) out[gs.offs[j * kWarps + warp] + rank[j]] = pts[j];
+            if (keep & (1u << j)) {
+              float* o = out + 3 * (gs.offs[j * kWarps + warp] + rank[j]);
+              o[0] = pts[j].time_offset;
+              o[1] = pts[j].freq_hz;
+              o[2] = pts[j].power;
+            }
           if (t == 0) a.out_counts[slot] = (uint32_t)gs.offs[kBinGroups * kWarps];
         }
       }
@@ -350,26 +354,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   }
 }
 
-size_t smem_bytes(uint64_t hop) { return sizeof(Smem2) + (size_t)(2 * kM + 3 * hop) * sizeof(float); }
+uint32_t ring_len_for(uint64_t hop) { return (uint32_t)next_pow2(2 * (uint64_t)kM + 3 * hop); }
+size_t smem_bytes(uint64_t hop) { return sizeof(Smem2) + (size_t)ring_len_for(hop) * sizeof(float); }
 
 }  // namespace
 
 bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev) {
   if (!cfg.reassign || cfg.window != (uint64_t)kM || cfg.zero_pad != 1) return false;
-  if (cfg.hop < 512 || (cfg.hop % 512) != 0 || ((2 * (uint64_t)kM + 3 * cfg.hop) % 512) != 0) return false;
+  if (cfg.hop < 512 || (cfg.hop % 512) != 0 || cfg.hop > 2048) return false;
   return dev.max_smem_optin == 0 || smem_bytes(cfg.hop) <= (size_t)dev.max_smem_optin;
 }
 
 int stft_fast2_prepare(StftPlan& plan) {
   auto k0 = k_reassigned_fast2<0>;
   auto k1 = k_reassigned_fast2<1>;
-  auto k2 = k_reassigned_fast2<2>;
-  auto k3 = k_reassigned_fast2<3>;
   const int smem = (int)smem_bytes(plan.cfg.hop);
   OMB_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
 }
 
@@ -382,7 +383,7 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.a = a;
   fa.tw1 = plan.d_fast_tables.ptr;
   fa.tw2 = fa.tw1 + 15 * kT;
-  fa.ring_len = (uint32_t)(2 * kM + 3 * a.hop);
+  fa.ring_len = ring_len_for(a.hop);
   fa.norm_ac = plan.h_norm.size() > 1 ? plan.h_norm[1] : plan.h_norm[0];
   fa.norm_dc = plan.h_norm[0];
   const uint64_t ctas = (uint64_t)std::max(plan.dev.sm_count, 1);
@@ -392,17 +393,14 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
-  static const int variant = [] { const char* e = getenv("OMB_FAST2_VARIANT"); return e ? atoi(e) & 3 : 0; }();
+  static const int variant = [] { const char* e = getenv("OMB_FAST2_VARIANT"); return e ? atoi(e) & 1 : 0; }();
   auto k0 = k_reassigned_fast2<0>;
   auto k1 = k_reassigned_fast2<1>;
-  auto k2 = k_reassigned_fast2<2>;
-  auto k3 = k_reassigned_fast2<3>;
   const size_t smem = smem_bytes(a.hop);
-  switch (variant) {
-    case 1: OMB_LAUNCH(k1, dim3(grid), dim3(kThreads), smem, s, fa); break;
-    case 2: OMB_LAUNCH(k2, dim3(grid), dim3(kThreads), smem, s, fa); break;
-    case 3: OMB_LAUNCH(k3, dim3(grid), dim3(kThreads), smem, s, fa); break;
-    default: OMB_LAUNCH(k0, dim3(grid), dim3(kThreads), smem, s, fa); break;
+  if (variant == 1) {
+    OMB_LAUNCH(k1, dim3(grid), dim3(kThreads), smem, s, fa);
+  } else {
+    OMB_LAUNCH(k0, dim3(grid), dim3(kThreads), smem, s, fa);
   }
   OMB_CHECK_LAUNCH();
   return OMB_OK;
