@@ -31,6 +31,24 @@ __device__ constexpr float kSin32[16] = {0.0f, 0.19509032201612826785f, 0.382683
                                          1.0f, 0.98078528040323044913f, 0.92387953251128673848f, 0.83146961230254523708f,
                                          0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508978178f, 0.19509032201612826785f};
 
+// Complex add / subtract as ONE packed FP32x2 instruction (Blackwell FADD2: both lanes of an aligned register
+// pair in a single issue slot).  The kernels are issue-bound, so halving the issue cost of the ~130 complex
+// additions per radix-16 butterfly matters more than anything else.  OMB_NO_F32X2 restores scalar code.
+__device__ __forceinline__ float2 cadd2(float2 a, float2 b) {
+#if defined(OMB_EMU) || defined(OMB_NO_F32X2)
+  return make_float2(a.x + b.x, a.y + b.y);
+#else
+  return __fadd2_rn(a, b);
+#endif
+}
+__device__ __forceinline__ float2 csub2(float2 a, float2 b) {
+#if defined(OMB_EMU) || defined(OMB_NO_F32X2)
+  return make_float2(a.x - b.x, a.y - b.y);
+#else
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#endif
+}
+
 template <bool INV>
 __device__ __forceinline__ float2 rot_mj(float2 a) {  // a * (-j) forward, a * (+j) inverse
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
@@ -48,14 +66,21 @@ __device__ __forceinline__ float2 mul_tw(float2 a, float2 w) {
 
 template <bool INV>
 __device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float2& a3) {
-  const float2 s0 = make_float2(a0.x + a2.x, a0.y + a2.y);
-  const float2 s1 = make_float2(a0.x - a2.x, a0.y - a2.y);
-  const float2 s2 = make_float2(a1.x + a3.x, a1.y + a3.y);
-  const float2 s3 = rot_mj<INV>(make_float2(a1.x - a3.x, a1.y - a3.y));
-  a0 = make_float2(s0.x + s2.x, s0.y + s2.y);
-  a2 = make_float2(s0.x - s2.x, s0.y - s2.y);
-  a1 = make_float2(s1.x + s3.x, s1.y + s3.y);
-  a3 = make_float2(s1.x - s3.x, s1.y - s3.y);
+  const float2 s0 = cadd2(a0, a2);
+  const float2 s1 = csub2(a0, a2);
+  const float2 s2 = cadd2(a1, a3);
+  const float2 d = csub2(a1, a3);
+  a0 = cadd2(s0, s2);
+  a2 = csub2(s0, s2);
+  // y1 = s1 + rot(d), y3 = s1 - rot(d), rot = multiply by -j (forward) / +j (inverse): component-swapped,
+  // so these four stay scalar
+  if (INV) {
+    a1 = make_float2(s1.x - d.y, s1.y + d.x);
+    a3 = make_float2(s1.x + d.y, s1.y - d.x);
+  } else {
+    a1 = make_float2(s1.x + d.y, s1.y - d.x);
+    a3 = make_float2(s1.x - d.y, s1.y + d.x);
+  }
 }
 
 // v[q] <- sum_j v[j] * W16^{+-jq}; natural order in, natural order out.
@@ -96,18 +121,17 @@ enum Prune { kAll = 0, kFirst9 = 1, kMid8 = 2 };
 
 template <bool INV, int kPrune>
 __device__ __forceinline__ void radix4_part(float2& a0, float2& a1, float2& a2, float2& a3, bool want2) {
-  const float2 s0 = make_float2(a0.x + a2.x, a0.y + a2.y);
-  const float2 s1 = make_float2(a0.x - a2.x, a0.y - a2.y);
-  const float2 s2 = make_float2(a1.x + a3.x, a1.y + a3.y);
-  const float2 s3 = rot_mj<INV>(make_float2(a1.x - a3.x, a1.y - a3.y));
+  const float2 s0 = cadd2(a0, a2);
+  const float2 s1 = csub2(a0, a2);
+  const float2 s2 = cadd2(a1, a3);
+  const float2 d = csub2(a1, a3);
   if (kPrune == kFirst9) {
-    a0 = make_float2(s0.x + s2.x, s0.y + s2.y);
-    a1 = make_float2(s1.x + s3.x, s1.y + s3.y);
-    if (want2) a2 = make_float2(s0.x - s2.x, s0.y - s2.y);
+    a0 = cadd2(s0, s2);
+    if (want2) a2 = csub2(s0, s2);
   } else {  // kMid8
-    a1 = make_float2(s1.x + s3.x, s1.y + s3.y);
-    a2 = make_float2(s0.x - s2.x, s0.y - s2.y);
+    a2 = csub2(s0, s2);
   }
+  a1 = INV ? make_float2(s1.x - d.y, s1.y + d.x) : make_float2(s1.x + d.y, s1.y - d.x);
 }
 
 template <bool INV, int kPrune>
