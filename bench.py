@@ -298,7 +298,7 @@ def run_ours(args):
     if rank != 0:
         return 0
     peak_gbs, peak_src = measured_peaks()
-    kernel_name = "k_reassigned_fast" if plan.is_fast else "k_reassigned_generic"
+    kernel_name = {0: "k_reassigned_generic", 1: "k_reassigned_fast", 2: "k_reassigned_fast2"}[plan.kernel_generation]
     achieved_gbs = frames_per_step * ALGO_BYTES_PER_FRAME / (ms_step / 1000.0) / 1e9
     traffic = recorded_traffic(kernel_name)
     line = {

@@ -233,7 +233,7 @@ int omb_stft_plan_create(const omb_spectrogram_config* cfg, int kernel_choice, o
 }
 void omb_stft_plan_destroy(omb_stft_plan* p) { delete p; }
 uint32_t omb_stft_plan_bins(const omb_stft_plan* p) { return p ? (uint32_t)p->p.cfg.bins() : 0; }
-int omb_stft_plan_is_fast(const omb_stft_plan* p) { return p && p->p.fast ? 1 : 0; }
+int omb_stft_plan_is_fast(const omb_stft_plan* p) { return p ? p->p.fast_kind : 0; }
 float omb_stft_plan_power_scale(const omb_stft_plan* p) { return p ? p->p.power_scale : 0.0f; }
 int omb_stft_execute_device(omb_stft_plan* p, const float* d_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
                             omb_spectrogram_point* d_out_points, uint64_t point_stride, uint32_t* d_out_counts,
