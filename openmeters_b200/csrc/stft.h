@@ -69,6 +69,7 @@ struct StftPlan {
   DeviceBuffer<uint32_t> d_counts;
   DeviceBuffer<uint16_t> d_classic;
   cudaStream_t stream = nullptr;  // owned, for the host path
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // host path: H2D / kernel / D2H overlap across lane chunks
 
   ~StftPlan();
   int init(const omb_spectrogram_config& c, int kernel_choice);

@@ -32,6 +32,8 @@ void StftConfig::to_c(omb_spectrogram_config* out) const {
 
 StftPlan::~StftPlan() {
   if (stream) cudaStreamDestroy(stream);
+  for (auto& ps : pipe)
+    if (ps) cudaStreamDestroy(ps);
 }
 
 int StftPlan::init(const omb_spectrogram_config& c, int choice) {
@@ -141,7 +143,10 @@ int StftPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samp
   if (!h_lanes) return fail(OMB_ERR_INVALID, "null lanes pointer");
   // H2D (one copy per lane when the caller's stride is not dense)
   OMB_TRY(d_in.reserve((size_t)(samples_per_lane * n_lanes)));
-  if (lane_stride == samples_per_lane) {
+  const bool pipelined = cfg.reassign && fast_kind > 0 && n_lanes >= 4;
+  if (pipelined) {
+    // copies are issued chunk by chunk below
+  } else if (lane_stride == samples_per_lane) {
     OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr, h_lanes, sizeof(float) * samples_per_lane * n_lanes, cudaMemcpyHostToDevice, stream));
   } else {
     for (uint32_t l = 0; l < n_lanes; ++l)
@@ -153,6 +158,36 @@ int StftPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samp
     if (!h_points || !h_counts) return fail(OMB_ERR_INVALID, "reassigned plan needs out_points and out_counts");
     OMB_TRY(d_points.reserve((size_t)(slots * point_stride)));
     OMB_TRY(d_counts.reserve((size_t)slots));
+    if (fast_kind > 0 && n_lanes >= 4) {
+      // Specialised kernels need no scratch, so lane chunks can be pipelined over three streams: the H2D of chunk
+      // i+1, the kernel of chunk i and the D2H of chunk i-1 overlap (PCIe is full duplex; D2H of 12-byte points
+      // dominates: ~24.6 KB per frame).
+      OMB_CUDA_TRY(cudaStreamSynchronize(stream));
+      for (auto& ps : pipe)
+        if (!ps) OMB_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+      const uint32_t chunk = std::max<uint32_t>(1, (n_lanes + 11) / 12);
+      int k = 0;
+      for (uint32_t l0 = 0; l0 < n_lanes; l0 += chunk, ++k) {
+        const uint32_t nl = std::min(chunk, n_lanes - l0);
+        cudaStream_t ps = pipe[k % 3];
+        if (lane_stride == samples_per_lane) {
+          OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + (uint64_t)l0 * samples_per_lane, h_lanes + (uint64_t)l0 * lane_stride,
+                                       sizeof(float) * samples_per_lane * nl, cudaMemcpyHostToDevice, ps));
+        } else {
+          for (uint32_t l = l0; l < l0 + nl; ++l)
+            OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + (uint64_t)l * samples_per_lane, h_lanes + (uint64_t)l * lane_stride,
+                                         sizeof(float) * samples_per_lane, cudaMemcpyHostToDevice, ps));
+        }
+        const uint64_t s0 = (uint64_t)l0 * frames;
+        OMB_TRY(execute_device(d_in.ptr + (uint64_t)l0 * samples_per_lane, nl, samples_per_lane, samples_per_lane,
+                               d_points.ptr + s0 * point_stride, point_stride, d_counts.ptr + s0, nullptr, ps));
+        OMB_CUDA_TRY(cudaMemcpyAsync(h_counts + s0, d_counts.ptr + s0, sizeof(uint32_t) * frames * nl, cudaMemcpyDeviceToHost, ps));
+        OMB_CUDA_TRY(cudaMemcpyAsync(h_points + s0 * point_stride, d_points.ptr + s0 * point_stride,
+                                     sizeof(omb_spectrogram_point) * frames * nl * point_stride, cudaMemcpyDeviceToHost, ps));
+      }
+      for (auto& ps : pipe) OMB_CUDA_TRY(cudaStreamSynchronize(ps));
+      return OMB_OK;
+    }
     OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, d_points.ptr, point_stride, d_counts.ptr,
                            nullptr, stream));
     OMB_CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts.ptr, sizeof(uint32_t) * slots, cudaMemcpyDeviceToHost, stream));

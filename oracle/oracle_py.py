@@ -78,7 +78,7 @@ def _cfg_ptr(cfg):
 
 
 def stft_batch(cfg, lanes: np.ndarray, threads: int = 0, point_stride: int | None = None,
-               frame_begin: int = 0, frame_end: int | None = None):
+               frame_begin: int = 0, frame_end: int | None = None, out=None):
     """lanes: (n_lanes, samples) float32. Returns (points[(L,F,stride,3)], counts[(L,F)]) or codes[(L,F,bins)]."""
     a = api()
     lanes = np.ascontiguousarray(lanes, np.float32)
@@ -90,8 +90,12 @@ def stft_batch(cfg, lanes: np.ndarray, threads: int = 0, point_stride: int | Non
     fe = frames if frame_end is None else frame_end
     if cfg.use_reassignment:
         stride = point_stride or bins
-        pts = np.zeros((L, frames, stride, 3), np.float32)
-        cnt = np.zeros((L, frames), np.uint32)
+        if out is not None:  # caller-provided (pts, cnt): timing loops reuse them so page faults are not measured
+            pts, cnt = out
+            assert pts.shape == (L, frames, stride, 3) and cnt.shape == (L, frames)
+        else:
+            pts = np.zeros((L, frames, stride, 3), np.float32)
+            cnt = np.zeros((L, frames), np.uint32)
         rc = a.stft_batch(cp, lanes.ctypes.data, L, S, S, pts.ctypes.data, stride, cnt.ctypes.data, None, threads,
                           frame_begin, fe)
         assert rc == 0

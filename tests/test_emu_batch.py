@@ -62,3 +62,11 @@ def test_specialised_kernel_other_hops_and_windows(emu):
         cfg = SpectrogramConfig(fft_size=4096, hop_size=hop, window=win, use_reassignment=True)
         lanes = synth.cfg2_lanes(1, (8192 + 6 * hop) / 48000.0)
         cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+
+
+def test_host_path_pipelined_lane_chunks(emu):
+    """execute_host pipelines lane chunks over three streams when a specialised kernel is active (>= 4 lanes)."""
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    lanes = synth.cfg2_lanes(5, (8192 + 2 * 1024) / 48000.0)
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 15
