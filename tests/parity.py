@@ -22,6 +22,8 @@ def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_le
     Matched points >= -60 dB re the column peak must agree in frequency and time."""
     stats = dict(n_a=len(a), n_b=len(b), unmatched=0, checked=0)
     peak = float(max(a[:, 2].max() if len(a) else 0.0, b[:, 2].max() if len(b) else 0.0))
+    total = float(b[:, 2].astype(np.float64).sum()) if len(b) else 0.0
+    total = max(total, peak)
     if peak == 0.0:
         assert len(a) == len(b) == 0
         return stats
@@ -35,7 +37,9 @@ def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_le
         # cfg2 signal): max |dt| 1.2e-5 at -40 dB, 5.6e-5 at -50 dB, 9e-4 at -60 dB; max |df| 0.03 / 0.08 / 0.25 Hz.
         # The flat tolerance is therefore applied down to -40 dB and widened linearly in peak/p below
         # (x10 at -50 dB, x100 at -60 dB) — the same shape as the power rule 1e-5*max(p, peak*1e-3).
-        return max(1.0, float(peak * 1e-4 / max(p, 1e-300)))
+        # (rounding noise of an FFT scales with the L2 norm of the whole column, so the reference level is the
+        #  column's total power, which equals ~1-2x the peak for tonal frames and more for broadband ones)
+        return max(1.0, float(total * 1e-4 / max(p, 1e-300)))
 
     tol_f = tol_f0
 
