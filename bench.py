@@ -217,6 +217,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     api = lib_api()
