@@ -8,10 +8,12 @@
 // bins, HBM-bound (4 B in, 8 B out per bin-hop).  Hops are processed in chunks sized so the power
 // scratch written by the first kernel is still L2-resident when the second one reads it.
 #include "device_math.cuh"
+#include "fft_stockham.cuh"
 #include "spectrum.h"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace omb {
 
@@ -65,6 +67,43 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_power_generic(SpectrumPow
     for (int k = tid; k < (int)a.bins; k += nt) {
       const float2 z = work[k];
       out[k] = (z.x * z.x + z.y * z.y) * __ldg(&a.bin_norm[k]);
+    }
+    __syncthreads();
+  }
+}
+
+// Shared-memory variant for N <= 16384: the real N-point transform as one complex N/2-point Stockham FFT of
+// (r[2n], r[2n+1]) + the split X[k] = E[k] + W_N^k O[k] (same scheme as k_classic_smem).
+__global__ void __launch_bounds__(256) k_spectrum_power_smem(SpectrumPowerArgs a) {
+  OMB_DYN_SMEM(float2, smem);
+  __shared__ float red[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int N = (int)a.fft_size, M = N >> 1, logM = (int)a.log2_fft - 1;
+  float2* A = smem;
+  float2* B = smem + M;
+  const uint64_t total = a.hops * a.n_lanes;
+  for (uint64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const uint64_t lane = item / a.hops, h = item % a.hops;
+    const float* x = a.lanes + lane * a.lane_stride + h * a.hop;
+    float part = 0.0f;
+    for (int i = tid; i < N; i += nt) part += __ldg(&x[i]);
+    const float mean = block_sum(part, red) / (float)N;
+    for (int n = tid; n < M; n += nt) {
+      const float r0 = (__ldg(&x[2 * n]) - mean) * __ldg(&a.win[2 * n]);
+      const float r1 = (__ldg(&x[2 * n + 1]) - mean) * __ldg(&a.win[2 * n + 1]);
+      A[n] = make_float2(r0, r1);
+    }
+    __syncthreads();
+    const float2* Z = stockham_fft(A, B, M, logM, a.tw, 2);
+    float* out = a.power + item * a.bins;
+    for (int k = tid; k <= M; k += nt) {
+      const float2 zk = Z[k & (M - 1)];
+      const float2 zm = Z[(M - k) & (M - 1)];
+      const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+      const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+      const float2 w = k < M ? __ldg(&a.tw[k]) : make_float2(-1.0f, 0.0f);
+      const float2 X = cadd(E, cmul(w, O));
+      out[k] = (X.x * X.x + X.y * X.y) * __ldg(&a.bin_norm[k]);
     }
     __syncthreads();
   }
@@ -215,6 +254,17 @@ int SpectrumPlan::power_device(const float* d_lanes, uint32_t n_lanes, uint64_t 
   a.bin_norm = d_norm.ptr;
   a.tw = d_tw.ptr;
   a.power = d_power_out;
+  const uint64_t N = cfg.fft_size;
+  const size_t smem = (size_t)N * sizeof(float2);  // two buffers of N/2 complex
+  if (N >= 16 && N <= 16384 && !getenv("OMB_NO_SMEM_KERNEL") && (dev.max_smem_optin == 0 || smem + 1024 <= (size_t)dev.max_smem_optin)) {
+    OMB_CUDA_TRY(cudaFuncSetAttribute(k_spectrum_power_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)200 * 1024 / smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(dev.sm_count, 1) * per_sm);
+    const unsigned threads = (unsigned)std::min<uint64_t>(256, std::max<uint64_t>(32, N / 8));
+    OMB_LAUNCH(k_spectrum_power_smem, dim3(grid), dim3(threads), smem, s, a);
+    OMB_CHECK_LAUNCH();
+    return OMB_OK;
+  }
   const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(dev.sm_count, 1) * 4);
   a.scratch_stride = cfg.fft_size;
   OMB_TRY(d_scratch.reserve((size_t)(a.scratch_stride * grid)));

@@ -80,6 +80,9 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
       OMB_TRY(stft_fast2_prepare(*this));
       fast_kind = 2;
     }
+  } else if (choice == OMB_KERNEL_AUTO && stft_smem_supported(cfg, dev) && !(getenv("OMB_NO_SMEM_KERNEL"))) {
+    OMB_TRY(stft_smem_prepare(*this));
+    smem_kernel = true;
   } else if (choice == OMB_KERNEL_FAST) {
     return fail(OMB_ERR_UNSUPPORTED, "no specialised kernel for window %llu hop %llu zp %llu reassign %d",
                 (unsigned long long)N, (unsigned long long)cfg.hop, (unsigned long long)cfg.zero_pad, (int)cfg.reassign);
@@ -132,6 +135,7 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   a.out_classic = out_classic;
   if (fast_kind == 2) return launch_stft_fast2(*this, a, s);
   if (fast) return launch_stft_fast(*this, a, s);
+  if (smem_kernel) return launch_stft_smem(*this, a, s, d_scratch);
   return launch_stft_generic(*this, a, s, d_scratch);
 }
 

@@ -1,0 +1,211 @@
+// stft_smem.cu — shared-memory STFT kernels for any power-of-two size that fits on chip.
+//
+// Middle tier between the specialised N = 4096 kernels (stft_fast*.cu) and the any-size global-scratch kernels
+// (stft_generic.cu): one CTA per frame, Stockham radix-4 FFTs ping-ponging between two shared buffers
+// (fft_stockham.cuh), natural-order spectra.
+//   classic    : the real F-point transform runs as ONE complex F/2-point FFT of (r[2n], r[2n+1]) plus the
+//                split X[k] = E[k] + W_F^k O[k]                                       (rows a4, a7)
+//   reassigned : same restructuring as the specialised kernel — packed real forward FFT (N points), fused
+//                Hilbert pair step, one inverse, three windowed F-point FFTs — instead of the literal
+//                2 x 2N + 3 x F                                                        (rows a8-a10)
+// Limits: complex lengths up to 8192 (classic F <= 16384; reassigned N*zp <= 8192); larger goes to the generic kernels.
+#include "fft_stockham.cuh"
+#include "stft.h"
+
+namespace omb {
+
+namespace {
+
+constexpr int kMaxComplex = 8192;
+
+__global__ void __launch_bounds__(256) k_classic_smem(StftKernelArgs a) {
+  OMB_DYN_SMEM(float2, smem);
+  __shared__ float red[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int N = (int)a.window, F = (int)a.fft_len, M = F >> 1, logM = (int)a.log2_fft - 1;
+  float2* A = smem;
+  float2* B = smem + M;
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  const uint64_t total = per_lane * a.n_lanes;
+  for (uint64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const uint64_t lane = item / per_lane, frame = a.first_frame + item % per_lane;
+    const float* x = a.lanes + lane * a.lane_stride + frame * a.hop;
+    float part = 0.0f;
+    for (int i = tid; i < N; i += nt) part += __ldg(&x[i]);
+    const float mean = block_sum(part, red) / (float)N;
+    for (int n = tid; n < M; n += nt) {
+      const int i0 = 2 * n, i1 = 2 * n + 1;
+      const float r0 = i0 < N ? (__ldg(&x[i0]) - mean) * __ldg(&a.win[i0]) : 0.0f;
+      const float r1 = i1 < N ? (__ldg(&x[i1]) - mean) * __ldg(&a.win[i1]) : 0.0f;
+      A[n] = make_float2(r0, r1);
+    }
+    __syncthreads();
+    const float2* Z = stockham_fft(A, B, M, logM, a.tw_fft, 2);  // W_M^i = W_F^{2i}
+    uint16_t* out = a.out_classic + (lane * a.frames_per_lane + frame) * a.bins;
+    for (int k = tid; k <= M; k += nt) {
+      const float2 zk = Z[k & (M - 1)];
+      const float2 zm = Z[(M - k) & (M - 1)];
+      const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+      const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));  // (zk - conj zm) / (2j)
+      const float2 w = k < M ? __ldg(&a.tw_fft[k]) : make_float2(-1.0f, 0.0f);
+      const float2 X = cadd(E, cmul(w, O));
+      const float p = (X.x * X.x + X.y * X.y) * __ldg(&a.bin_norm[k]);
+      out[k] = pack_classic_db_dev(power_to_db_dev(p, kDbFloor));
+    }
+    __syncthreads();
+  }
+}
+
+struct SmemReassignScratch {
+  float2* S;   // [bins]
+  float* nd;   // [bins]
+};
+
+__global__ void __launch_bounds__(256) k_reassigned_smem(StftKernelArgs a, float* gscratch, uint64_t gscratch_stride) {
+  OMB_DYN_SMEM(float2, smem);
+  __shared__ int cnt[33];
+  __shared__ float x0_xm[2];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int N = (int)a.window, F = (int)a.fft_len, H = 2 * N;
+  const int logN = (int)a.log2_hilbert - 1, logF = (int)a.log2_fft;
+  const int off = (H - N) / 2;
+  float2* A = smem;
+  float2* B = smem + F;
+  float* Y = reinterpret_cast<float*>(smem + 2 * F);  // N floats
+  float2* Sg = reinterpret_cast<float2*>(gscratch + (uint64_t)blockIdx.x * gscratch_stride);
+  float* ndg = reinterpret_cast<float*>(Sg + a.bins);
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  const uint64_t total = per_lane * a.n_lanes;
+  const ReassignConsts rc{a.bin_hz, a.max_hz, a.inv_2pi, a.inv_hop, a.latency_hops};
+  for (uint64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const uint64_t lane = item / per_lane, frame = a.first_frame + item % per_lane;
+    const float* x = a.lanes + lane * a.lane_stride + frame * a.hop;
+    // F: packed real transform of the 2N-sample frame
+    for (int n = tid; n < N; n += nt) A[n] = make_float2(__ldg(&x[2 * n]), __ldg(&x[2 * n + 1]));
+    __syncthreads();
+    float2* Z = stockham_fft(A, B, N, logN, a.tw_hil, 2);  // W_N^i = W_H^{2i}
+    float2* other = (Z == A) ? B : A;
+    if (tid == 0) {
+      x0_xm[0] = Z[0].x + Z[0].y;
+      x0_xm[1] = Z[0].x - Z[0].y;
+    }
+    // X: Q[k] = cos(th) conj(Z[N-k]) + j sin(th) Z[k], th = 2 pi k / H; written as conj(Q) for the inverse
+    for (int k = tid; k <= N / 2; k += nt) {
+      if (k == 0) {
+        Z[0] = make_float2(0.0f, 0.0f);
+        continue;
+      }
+      const float2 w = __ldg(&a.tw_hil[k]);  // (cos, -sin)
+      const float c = w.x, s = -w.y;
+      const float2 zk = Z[k], zm = Z[N - k];
+      const float2 qk = make_float2(c * zm.x - s * zk.y, s * zk.x - c * zm.y);
+      const float2 qm = make_float2(-c * zk.x - s * zm.y, s * zm.x + c * zk.y);
+      Z[k] = make_float2(qk.x, -qk.y);
+      if (k != N - k) Z[N - k] = make_float2(qm.x, -qm.y);
+    }
+    __syncthreads();
+    // I: q = conj(FFT(conj Q)); keep y[off + n]: Y[2m'] = Re q[m], Y[2m'+1] = Im q[m], m = off/2 + m'
+    const float2* R = stockham_fft(Z, other, N, logN, a.tw_hil, 2);
+    for (int n = tid; n < N; n += nt) {
+      const float2 q = R[(off + n) >> 1];
+      Y[n] = (n & 1) ? -q.y : q.x;
+    }
+    __syncthreads();
+    const float half_x0 = 0.5f * x0_xm[0], half_xm = 0.5f * x0_xm[1];
+    // G: three windowed F-point transforms
+    const float2* T = nullptr;
+    for (int wsel = 0; wsel < 3; ++wsel) {
+      const float* win = wsel == 1 ? a.dwin : a.win;
+      for (int n = tid; n < F; n += nt) {
+        float2 v = make_float2(0.0f, 0.0f);
+        if (n < N) {
+          float wv = __ldg(&win[n]);
+          if (wsel == 2) wv *= (float)n - (float)(N - 1) * 0.5f;
+          const float bias = ((n & 1) ? -half_xm : half_xm) - half_x0;  // off is even for every N >= 4
+          const float cx = fmaf((float)N, __ldg(&x[off + n]), bias);
+          v = make_float2(cx * wv, Y[n] * wv);
+        }
+        A[n] = v;
+      }
+      __syncthreads();
+      const float2* Rw = stockham_fft(A, B, F, logF, a.tw_fft, 1);
+      if (wsel == 0) {
+        for (int k = tid; k < (int)a.bins; k += nt) Sg[k] = Rw[k];
+      } else if (wsel == 1) {
+        for (int k = tid; k < (int)a.bins; k += nt) {
+          const float2 s = Sg[k], d = Rw[k];
+          ndg[k] = d.y * s.x - d.x * s.y;
+        }
+      } else {
+        T = Rw;
+      }
+      __syncthreads();
+    }
+    // R
+    const uint64_t slot = lane * a.frames_per_lane + frame;
+    omb_spectrogram_point* out = a.out_points + slot * a.point_stride;
+    int base = 0;
+    for (int k0 = 0; k0 < (int)a.bins; k0 += nt) {
+      const int k = k0 + tid;
+      omb_spectrogram_point p;
+      bool keep = false;
+      if (k < (int)a.bins) keep = reassign_bin_nd(Sg[k], ndg[k], T[k], __ldg(&a.bin_norm[k]), k, rc, &p);
+      int tot;
+      const int rank = block_rank(keep, cnt, &tot);
+      if (keep) out[base + rank] = p;
+      base += tot;
+    }
+    if (tid == 0) a.out_counts[slot] = (uint32_t)base;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+bool stft_smem_supported(const StftConfig& cfg, const DeviceInfo& dev) {
+  const uint64_t N = cfg.window, F = cfg.fft_len();
+  if (!is_pow2(N) || !is_pow2(F)) return false;
+  size_t smem;
+  if (cfg.reassign) {
+    if (N < 8 || F > (uint64_t)kMaxComplex) return false;
+    smem = 2 * F * sizeof(float2) + N * sizeof(float);
+  } else {
+    if (F < 16 || F / 2 > (uint64_t)kMaxComplex) return false;
+    smem = F * sizeof(float2);  // two buffers of F/2
+  }
+  return dev.max_smem_optin == 0 || smem + 1024 <= (size_t)dev.max_smem_optin;
+}
+
+static size_t smem_for(const StftConfig& cfg) {
+  const uint64_t N = cfg.window, F = cfg.fft_len();
+  return cfg.reassign ? (size_t)(2 * F * sizeof(float2) + N * sizeof(float)) : (size_t)(F * sizeof(float2));
+}
+
+int stft_smem_prepare(StftPlan& plan) {
+  const int smem = (int)smem_for(plan.cfg);
+  if (plan.cfg.reassign) OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  else OMB_CUDA_TRY(cudaFuncSetAttribute(k_classic_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  return OMB_OK;
+}
+
+int launch_stft_smem(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s, DeviceBuffer<float2>& scratch) {
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  const uint64_t total = per_lane * a.n_lanes;
+  if (total == 0) return OMB_OK;
+  const size_t smem = smem_for(plan.cfg);
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)200 * 1024 / std::max<size_t>(smem, 1)));
+  const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(plan.dev.sm_count, 1) * per_sm);
+  const uint64_t work = plan.cfg.reassign ? a.fft_len : a.fft_len / 2;
+  const unsigned threads = (unsigned)std::min<uint64_t>(256, std::max<uint64_t>(32, work / 4));
+  if (plan.cfg.reassign) {
+    const uint64_t stride = 3ull * a.bins + 1;  // floats: S (2 per bin) + nd (1 per bin)
+    OMB_TRY(scratch.reserve((size_t)((stride * grid + 1) / 2)));
+    OMB_LAUNCH(k_reassigned_smem, dim3(grid), dim3(threads), smem, s, a, reinterpret_cast<float*>(scratch.ptr), stride);
+  } else {
+    OMB_LAUNCH(k_classic_smem, dim3(grid), dim3(threads), smem, s, a);
+  }
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+}  // namespace omb

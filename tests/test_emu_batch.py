@@ -16,6 +16,8 @@ def test_classic_batch(emu, window, n, hop, zp):
     lanes = synth.cfg2_lanes(3, 0.05)
     st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_GENERIC)
     assert st["exact"] >= 0.98
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_AUTO)  # shared-memory Stockham kernel
+    assert st["exact"] >= 0.98
 
 
 @pytest.mark.parametrize("window,n,hop,zp", [(capi.WINDOW_HANN, 64, 16, 1), (capi.WINDOW_BLACKMAN_HARRIS, 256, 64, 1),
@@ -24,6 +26,8 @@ def test_reassigned_batch(emu, window, n, hop, zp):
     cfg = SpectrogramConfig(fft_size=n, hop_size=hop, window=window, use_reassignment=True, zero_padding_factor=zp)
     lanes = synth.cfg2_lanes(2, 0.04)
     st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_GENERIC)
+    assert st["checked"] > 100
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_AUTO)  # shared-memory Stockham kernel
     assert st["checked"] > 100
 
 

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Secondary throughput measurements for the other BASELINE configs (cfg1, cfg3, cfg4, cfg5), device-resident inputs,
+CUDA events on the launching stream.  Prints one JSON object; `bench.py` (cfg2) stays the headline."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openmeters_b200 import _capi as capi  # noqa: E402
+from openmeters_b200 import batch, synth  # noqa: E402
+from openmeters_b200._lib import api as lib_api  # noqa: E402
+from openmeters_b200.processors import LoudnessConfig, SpectrogramConfig, SpectrumConfig  # noqa: E402
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timed(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters / 1000.0
+
+
+def tile_lanes(base: np.ndarray, n: int) -> np.ndarray:
+    reps = (n + base.shape[0] - 1) // base.shape[0]
+    out = np.concatenate([np.roll(base, 977 * r, axis=1) * np.float32(1.0 - 0.01 * r) for r in range(reps)], 0)[:n]
+    return np.ascontiguousarray(out, np.float32)
+
+
+def main():
+    api = lib_api()
+    api.set_device(0)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    res = {}
+
+    # cfg1: classic 1024/512 Hann
+    cfg = SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False)
+    L, S = 256, 1 << 18
+    lanes = torch.from_numpy(tile_lanes(synth.cfg2_lanes(8, S / 48000.0)[:, :S], L)).to(dev)
+    plan = batch.StftPlan(cfg, api=api)
+    F = plan.frames_per_lane(S)
+    out = torch.empty((L * F, plan.bins), dtype=torch.int16, device=dev)
+    t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, classic_ptr=out.data_ptr(), stream=st))
+    b = 512 * 4 + 513 * 2
+    res["cfg1_classic_1024_512"] = dict(frames_per_s=L * F / t, ms=t * 1e3, algorithmic_bytes_per_frame=b, achieved_gbs=L * F * b / t / 1e9,
+                                        hbm_frac=L * F * b / t / 1e9 / PEAK)
+    del plan, out, lanes
+
+    # cfg5: reassigned 8192/2048 BH @96k
+    cfg = SpectrogramConfig(sample_rate=96000.0, fft_size=8192, hop_size=2048, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    L, S = 32, 1 << 20
+    lanes = torch.from_numpy(tile_lanes(synth.cfg5_lanes(8, S), L)).to(dev)
+    plan = batch.StftPlan(cfg, api=api)
+    F = plan.frames_per_lane(S)
+    pts = torch.empty((L * F, plan.bins, 3), dtype=torch.float32, device=dev)
+    cnt = torch.empty((L * F,), dtype=torch.int32, device=dev)
+    t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, pts.data_ptr(), plan.bins, cnt.data_ptr(), stream=st), iters=5)
+    b = 2048 * 4 + 4097 * 12 + 4
+    res["cfg5_reassigned_8192_2048"] = dict(frames_per_s=L * F / t, ms=t * 1e3, algorithmic_bytes_per_frame=b, achieved_gbs=L * F * b / t / 1e9,
+                                            hbm_frac=L * F * b / t / 1e9 / PEAK, kernel_generation=plan.kernel_generation)
+    del plan, pts, cnt, lanes
+
+    # cfg4: spectrum 16384/1024 Hann, PeakHold 12 dB/s, 128 lanes
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0, floor_db=-100.0)
+    L, S = 128, 480000
+    lanes = torch.from_numpy(tile_lanes(synth.cfg4_streams(4, S / 48000.0).reshape(8, -1)[:, :S], L)).to(dev)
+    plan = batch.SpectrumPlan(cfg, api=api)
+    Hh = plan.hops_per_lane(S)
+    w = torch.empty((L * Hh, plan.bins), dtype=torch.float32, device=dev)
+    r = torch.empty_like(w)
+    pk = torch.empty((L * Hh,), dtype=torch.int32, device=dev)
+    t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, w.data_ptr(), r.data_ptr(), pk.data_ptr(), stream=st), iters=5)
+    b = 1024 * 4 + 2 * 8193 * 4
+    res["cfg4_spectrum_16384_1024"] = dict(lane_hops_per_s=L * Hh / t, ms=t * 1e3, algorithmic_bytes_per_lane_hop=b, achieved_gbs=L * Hh * b / t / 1e9,
+                                           hbm_frac=L * Hh * b / t / 1e9 / PEAK)
+    del plan, w, r, pk, lanes
+
+    # cfg3: loudness 8 ch 48 kHz, 16 streams x 30 s, snapshot every 1024 frames
+    x = synth.cfg3_surround(30.0)
+    nS = 16
+    streams = torch.from_numpy(np.stack([x * np.float32(1.0 - 0.02 * i) for i in range(nS)])).to(dev)
+    plan = batch.LoudnessPlan(LoudnessConfig(), 8, capi.SURROUND, api=api)
+    frames = x.size // 8
+    nb = (frames + 1023) // 1024
+    snaps = torch.empty((nS * nb, 112 // 4), dtype=torch.float32, device=dev)
+    assert snaps.element_size() * snaps.shape[1] == 112
+    t = timed(lambda: plan.execute_device(streams.data_ptr(), nS, frames, frames * 8, 1024, snaps.data_ptr(), stream=st), iters=5)
+    res["cfg3_loudness_8ch"] = dict(sample_channels_per_s=nS * frames * 8 / t, ms=t * 1e3, algorithmic_bytes_per_sample_channel=4,
+                                    achieved_gbs=nS * frames * 8 * 4 / t / 1e9, hbm_frac=nS * frames * 8 * 4 / t / 1e9 / PEAK)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
