@@ -93,8 +93,8 @@ def main():
     plan = batch.LoudnessPlan(LoudnessConfig(), 8, capi.SURROUND, api=api)
     frames = x.size // 8
     nb = (frames + 1023) // 1024
-    snaps = torch.empty((nS * nb, 112 // 4), dtype=torch.float32, device=dev)
-    assert snaps.element_size() * snaps.shape[1] == 112
+    snaps = torch.empty((nS * nb, 116 // 4), dtype=torch.float32, device=dev)
+    assert snaps.element_size() * snaps.shape[1] == 116
     t = timed(lambda: plan.execute_device(streams.data_ptr(), nS, frames, frames * 8, 1024, snaps.data_ptr(), stream=st), iters=5)
     res["cfg3_loudness_8ch"] = dict(sample_channels_per_s=nS * frames * 8 / t, ms=t * 1e3, algorithmic_bytes_per_sample_channel=4,
                                     achieved_gbs=nS * frames * 8 * 4 / t / 1e9, hbm_frac=nS * frames * 8 * 4 / t / 1e9 / PEAK)
