@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_power_generic(SpectrumPow
 
 // Shared-memory variant for N <= 16384: the real N-point transform as one complex N/2-point Stockham FFT of
 // (r[2n], r[2n+1]) + the split X[k] = E[k] + W_N^k O[k] (same scheme as k_classic_smem).
-__global__ void __launch_bounds__(256) k_spectrum_power_smem(SpectrumPowerArgs a) {
+__global__ void __launch_bounds__(1024) k_spectrum_power_smem(SpectrumPowerArgs a) {
   OMB_DYN_SMEM(float2, smem);
   __shared__ float red[32];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -260,7 +260,8 @@ int SpectrumPlan::power_device(const float* d_lanes, uint32_t n_lanes, uint64_t 
     OMB_CUDA_TRY(cudaFuncSetAttribute(k_spectrum_power_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)200 * 1024 / smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(dev.sm_count, 1) * per_sm);
-    const unsigned threads = (unsigned)std::min<uint64_t>(256, std::max<uint64_t>(32, N / 8));
+    const uint64_t want = std::max<uint64_t>(256, 2048 / (uint64_t)per_sm);
+    const unsigned threads = (unsigned)std::min<uint64_t>(std::min<uint64_t>(1024, want), std::max<uint64_t>(32, N / 8));
     OMB_LAUNCH(k_spectrum_power_smem, dim3(grid), dim3(threads), smem, s, a);
     OMB_CHECK_LAUNCH();
     return OMB_OK;

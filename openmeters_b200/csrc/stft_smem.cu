@@ -18,7 +18,7 @@ namespace {
 
 constexpr int kMaxComplex = 8192;
 
-__global__ void __launch_bounds__(256) k_classic_smem(StftKernelArgs a) {
+__global__ void __launch_bounds__(1024) k_classic_smem(StftKernelArgs a) {
   OMB_DYN_SMEM(float2, smem);
   __shared__ float red[32];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -61,7 +61,7 @@ struct SmemReassignScratch {
   float* nd;   // [bins]
 };
 
-__global__ void __launch_bounds__(256) k_reassigned_smem(StftKernelArgs a, float* gscratch, uint64_t gscratch_stride) {
+__global__ void __launch_bounds__(1024) k_reassigned_smem(StftKernelArgs a, float* gscratch, uint64_t gscratch_stride) {
   OMB_DYN_SMEM(float2, smem);
   __shared__ int cnt[33];
   __shared__ float x0_xm[2];
@@ -195,8 +195,11 @@ int launch_stft_smem(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s, De
   const size_t smem = smem_for(plan.cfg);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)200 * 1024 / std::max<size_t>(smem, 1)));
   const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(plan.dev.sm_count, 1) * per_sm);
+  // one radix-4 butterfly per thread per stage when possible; when shared memory limits the SM to one or two
+  // CTAs, make them wide (up to 1024 threads) so the SM still has 16-32 warps to hide latency
   const uint64_t work = plan.cfg.reassign ? a.fft_len : a.fft_len / 2;
-  const unsigned threads = (unsigned)std::min<uint64_t>(256, std::max<uint64_t>(32, work / 4));
+  const uint64_t want = std::max<uint64_t>(256, 2048 / (uint64_t)per_sm);
+  const unsigned threads = (unsigned)std::min<uint64_t>(std::min<uint64_t>(1024, want), std::max<uint64_t>(32, work / 4));
   if (plan.cfg.reassign) {
     const uint64_t stride = 3ull * a.bins + 1;  // floats: S (2 per bin) + nd (1 per bin)
     OMB_TRY(scratch.reserve((size_t)((stride * grid + 1) / 2)));
