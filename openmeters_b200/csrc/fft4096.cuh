@@ -1,0 +1,77 @@
+// fft4096.cuh — the 4096-point complex FFT engine shared by the specialised kernels (stft_fast2.cu, spectrum_fast.cu).
+//
+// One 256-thread group transforms 4096 points in place in a padded shared buffer with three radix-16 register passes
+// (fft16.cuh); several groups of one CTA run independent transforms and synchronise with their own named barrier.
+#pragma once
+#include "device_math.cuh"
+#include "fft16.cuh"
+
+namespace omb {
+namespace f4k {
+
+constexpr int kT = 256;  // threads per group
+
+// bar.sync on the group's named barrier (ids 1.. ; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int g) {
+#ifdef OMB_EMU
+  omb_emu::named_sync(1 + g, kT);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kT) : "memory");
+#endif
+}
+
+
+// kTw = 0: 15 table loads (shared memory).  kTw = 1: 4 loads (q = 1, 2, 4, 8) + 11 products — trades 11
+// shared-memory loads for 44 flops (each derived twiddle is at most two multiplications from a table entry).
+template <bool INV, int kTw, bool kCompact>
+__device__ __forceinline__ void twiddle15(float2 (&v)[16], const float2* tab, int stride) {
+  if (kTw == 0) {
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], tab[(q - 1) * stride]);
+  } else {
+    float2 w[16];
+    w[1] = tab[0 * stride];
+    w[2] = tab[(kCompact ? 1 : 1) * stride];
+    w[4] = tab[(kCompact ? 2 : 3) * stride];
+    w[8] = tab[(kCompact ? 3 : 7) * stride];
+    w[3] = cmul(w[1], w[2]);
+    w[5] = cmul(w[1], w[4]);
+    w[6] = cmul(w[2], w[4]);
+    w[7] = cmul(w[3], w[4]);
+#pragma unroll
+    for (int q = 9; q < 16; ++q) w[q] = cmul(w[q - 8], w[8]);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], w[q]);
+  }
+}
+
+struct Addr {
+  int pA, pB, pC;
+};
+
+// DIF forward: v holds elements t + 256 j (access A). On return v[j] = X[t + 256 j] (only the kPrune subset).
+template <int kPrune, int kTw2>
+__device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const float2* tw1t, const float2* tw2o, const Addr& ad, int g) {
+  f16::dft16<false>(v);
+  twiddle15<false, 1, true>(v, tw1t, kT);
+  float2* wa = W + ad.pA;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wa[273 * q] = v[q];
+  group_sync(g);
+  float2* wb = W + ad.pB;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
+  f16::dft16<false>(v);
+  twiddle15<false, kTw2, false>(v, tw2o, 16);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
+  group_sync(g);
+  const float2* wc = W + ad.pC;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = wc[j];
+  f16::dft16p<false, kPrune>(v);
+}
+
+
+}  // namespace f4k
+}  // namespace omb

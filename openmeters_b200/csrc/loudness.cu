@@ -170,7 +170,9 @@ struct LoudBatchArgs {
   uint64_t stream_stride, frames, n_chunks, block_frames, n_blocks;
   uint32_t n_streams, channels, tp_delay_len;
   KWeight kw;
-  double M[16];
+  double M[16];      // A^kKwChunk
+  double Mseg[16];   // A^(kKwChunk*kKwSeg)
+  double* seg_state; // [stream][segment][channel][4]
   double* end_state;     // [stream][chunk][channel][4]  zero-state end states
   double* start_state;   // [stream][chunk][channel][4]  true start states
   float* y;              // [stream][channel][frame]
@@ -184,14 +186,19 @@ struct LoudBatchArgs {
 };
 
 // (1)/(3): one thread per (stream, chunk, channel); channel fastest so a warp reads whole frames.
+// The apply pass (kApply) writes y through a per-warp 32x32 transposed tile so that every global store is a full
+// 128-byte line of one (stream, channel) row instead of 32 scattered 4-byte writes.
 template <bool kApply>
 __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
+  __shared__ float tile[4][32][33];
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t total = (uint64_t)a.n_streams * a.n_chunks * a.channels;
-  if (idx >= total) return;
-  const uint32_t c = (uint32_t)(idx % a.channels);
-  const uint64_t chunk = (idx / a.channels) % a.n_chunks;
-  const uint64_t stream = idx / ((uint64_t)a.channels * a.n_chunks);
+  const bool valid = idx < total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t id = valid ? idx : total - 1;
+  const uint32_t c = (uint32_t)(id % a.channels);
+  const uint64_t chunk = (id / a.channels) % a.n_chunks;
+  const uint64_t stream = id / ((uint64_t)a.channels * a.n_chunks);
   const float* x = a.in + stream * a.stream_stride;
   const uint64_t t0 = chunk * kKwChunk;
   const uint64_t t1 = t0 + kKwChunk < a.frames ? t0 + kKwChunk : a.frames;
@@ -203,52 +210,98 @@ __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
     s[2] = a.start_state[sidx + 2];
     s[3] = a.start_state[sidx + 3];
   }
-  float* y = kApply ? a.y + (stream * a.channels + c) * a.frames : nullptr;
-  double acc = 0.0;
-  for (uint64_t t = t0; t < t1; ++t) {
-    const double yy = kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
-    if (kApply) {
-      const float yf = (float)yy;
-      y[t] = yf;
-      const double v = (double)yf * (double)yf;
-      acc += isfinite(v) ? v : 0.0;
-    }
-  }
-  if (kApply) {
-    a.csum[(stream * a.channels + c) * a.n_chunks + chunk] = acc;
-  } else {
-    // a short final chunk still has to be advanced to a full chunk boundary? No: nothing follows it.
+  if (!kApply) {
+    if (!valid) return;
+    for (uint64_t t = t0; t < t1; ++t) kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
     a.end_state[sidx + 0] = s[0];
     a.end_state[sidx + 1] = s[1];
     a.end_state[sidx + 2] = s[2];
     a.end_state[sidx + 3] = s[3];
+    return;
   }
+  // row base of this lane's (stream, channel, chunk) in y, and how many samples the chunk has
+  const unsigned long long ybase = (unsigned long long)((stream * a.channels + c) * a.frames + t0);
+  const int len = valid ? (int)(t1 - t0) : 0;
+  double acc = 0.0;
+  for (int tt = 0; tt < kKwChunk; tt += 32) {
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      float yf = 0.0f;
+      if (tt + i < len) {
+        yf = (float)kw_step((double)__ldg(&x[(t0 + tt + i) * a.channels + c]), s, a.kw);
+        const double v = (double)yf * (double)yf;
+        acc += isfinite(v) ? v : 0.0;
+      }
+      tile[warp][lane][i] = yf;
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+      const unsigned long long rb = __shfl_sync(0xffffffffu, ybase, r);
+      const int rl = __shfl_sync(0xffffffffu, len, r);
+      if (tt + lane < rl) a.y[rb + tt + lane] = tile[warp][r][lane];
+    }
+    __syncwarp();
+  }
+  if (valid) a.csum[(stream * a.channels + c) * a.n_chunks + chunk] = acc;
 }
 
-// (2): serial scan over chunks, one thread per (stream, channel): start[k+1] = M * start[k] + end0[k].
-__global__ void __launch_bounds__(64) k_kw_scan(LoudBatchArgs a) {
+// (2): scan over chunks of the affine recurrence start[k+1] = M * start[k] + end0[k], three levels so the
+// dependent chain is 64 + n_seg + 64 steps instead of n_chunks (a 30 s stream has 5625 chunks; the first version's
+// single serial walk was 3.7 ms of pure load latency):
+//   kPhase 0: per (stream, channel, segment of kKwSeg chunks) — segment composite from a zero start  -> seg_state
+//   kPhase 1: per (stream, channel) — serial over segments with M^kKwSeg                              -> seg_state (in place: starts)
+//   kPhase 2: per (stream, channel, segment) — re-walk the segment from its true start                -> start_state
+__device__ __forceinline__ void affine_step(double (&s)[4], const double* __restrict__ M, const double* __restrict__ e) {
+  double n[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) n[r] = M[r * 4 + 0] * s[0] + M[r * 4 + 1] * s[1] + M[r * 4 + 2] * s[2] + M[r * 4 + 3] * s[3] + e[r];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) s[r] = n[r];
+}
+
+template <int kPhase>
+__global__ void __launch_bounds__(128) k_kw_scan(LoudBatchArgs a) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (uint64_t)a.n_streams * a.channels) return;
-  const uint32_t c = (uint32_t)(idx % a.channels);
-  const uint64_t stream = idx / a.channels;
-  double s[4] = {0.0, 0.0, 0.0, 0.0};
-  for (uint64_t k = 0; k < a.n_chunks; ++k) {
-    const uint64_t sidx = ((stream * a.n_chunks + k) * a.channels + c) * 4;
-    a.start_state[sidx + 0] = s[0];
-    a.start_state[sidx + 1] = s[1];
-    a.start_state[sidx + 2] = s[2];
-    a.start_state[sidx + 3] = s[3];
-    double n[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-      n[r] = a.M[r * 4 + 0] * s[0] + a.M[r * 4 + 1] * s[1] + a.M[r * 4 + 2] * s[2] + a.M[r * 4 + 3] * s[3] + a.end_state[sidx + r];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) s[r] = n[r];
+  const uint64_t n_seg = (a.n_chunks + kKwSeg - 1) / kKwSeg;
+  if (kPhase == 1) {
+    if (idx >= (uint64_t)a.n_streams * a.channels) return;
+    const uint32_t c = (uint32_t)(idx % a.channels);
+    const uint64_t stream = idx / a.channels;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (uint64_t g = 0; g < n_seg; ++g) {
+      double* p = a.seg_state + ((stream * n_seg + g) * a.channels + c) * 4;
+      const double e[4] = {p[0], p[1], p[2], p[3]};
+      p[0] = s[0]; p[1] = s[1]; p[2] = s[2]; p[3] = s[3];
+      affine_step(s, a.Mseg, e);
+    }
+    return;
   }
+  const uint64_t total = (uint64_t)a.n_streams * n_seg * a.channels;
+  if (idx >= total) return;
+  const uint32_t c = (uint32_t)(idx % a.channels);
+  const uint64_t g = (idx / a.channels) % n_seg;
+  const uint64_t stream = idx / ((uint64_t)a.channels * n_seg);
+  double* sp = a.seg_state + ((stream * n_seg + g) * a.channels + c) * 4;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  if (kPhase == 2) { s[0] = sp[0]; s[1] = sp[1]; s[2] = sp[2]; s[3] = sp[3]; }
+  const uint64_t k0 = g * kKwSeg, k1 = k0 + kKwSeg < a.n_chunks ? k0 + kKwSeg : a.n_chunks;
+  const uint64_t stride = (uint64_t)a.channels * 4;
+  const double* __restrict__ e = a.end_state + ((stream * a.n_chunks + k0) * a.channels + c) * 4;
+  double* __restrict__ st = a.start_state + ((stream * a.n_chunks + k0) * a.channels + c) * 4;
+#pragma unroll 4
+  for (uint64_t k = k0; k < k1; ++k, e += stride, st += stride) {
+    if (kPhase == 2) { st[0] = s[0]; st[1] = s[1]; st[2] = s[2]; st[3] = s[3]; }
+    affine_step(s, a.M, e);
+  }
+  if (kPhase == 0) { sp[0] = s[0]; sp[1] = s[1]; sp[2] = s[2]; sp[3] = s[3]; }
 }
 
-// true peak: one thread per frame of a (stream, block); all channels in the thread; warp max -> atomicMax.
-__global__ void __launch_bounds__(256) k_true_peak(LoudBatchArgs a, TruePeakFir fir) {
+// true peak: a CTA takes 256 frames of one (stream, block): the frames plus a 23-frame halo are loaded coalesced and
+// stored channel-major in shared memory, then every thread runs the polyphase FIR of its frame for each channel from
+// conflict-free rows (taps in the reference's order, separate mul/add roundings: bit-identical to the reference loop).
+constexpr int kTpTile = 256, kTpHalo = 23, kTpRow = kTpTile + kTpHalo + 1;
+__global__ void __launch_bounds__(kTpTile) k_true_peak(LoudBatchArgs a, TruePeakFir fir) {
+  __shared__ float tile[OMB_MAX_CHANNELS][kTpRow];
   const uint64_t sb = blockIdx.x;  // stream * n_blocks + block
   const uint64_t stream = sb / a.n_blocks, blk = sb % a.n_blocks;
   const float* x = a.in + stream * a.stream_stride;
@@ -256,17 +309,27 @@ __global__ void __launch_bounds__(256) k_true_peak(LoudBatchArgs a, TruePeakFir 
   const uint64_t f1 = f0 + a.block_frames < a.frames ? f0 + a.block_frames : a.frames;
   const int lane = threadIdx.x & 31;
   const int C = (int)a.channels;
-  for (uint64_t base = f0 + (uint64_t)blockIdx.y * blockDim.x; base < f1; base += (uint64_t)gridDim.y * blockDim.x) {
+  for (uint64_t base = f0 + (uint64_t)blockIdx.y * kTpTile; base < f1; base += (uint64_t)gridDim.y * kTpTile) {
+    // tile frame index u <-> stream frame base - kTpHalo + u; frames before the stream start are zeros
+    const int n_el = (kTpTile + kTpHalo) * C;
+    for (int e = threadIdx.x; e < n_el; e += kTpTile) {
+      const int u = e / C, c = e - u * C;
+      const int64_t fr = (int64_t)base - kTpHalo + u;
+      tile[c][u] = (fr >= 0 && (uint64_t)fr < a.frames) ? __ldg(&x[(uint64_t)fr * C + c]) : 0.0f;
+    }
+    __syncthreads();
     const uint64_t t = base + threadIdx.x;
+    const int u = kTpHalo + threadIdx.x;
     for (int c = 0; c < C; ++c) {
       float pk = 0.0f;
       if (t < f1) {
-        pk = fabsf(__ldg(&x[t * C + c]));
+        const float* row = &tile[c][u];
+        pk = fabsf(row[0]);
         if (a.tp_delay_len == 12) {
           float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 12; ++i) {  // delay[pos+i] == x[t-i], zeros before the stream start
-            const float d = t >= (uint64_t)i ? __ldg(&x[(t - i) * C + c]) : 0.0f;
+          for (int i = 0; i < 12; ++i) {  // delay[pos+i] == x[t-i]
+            const float d = row[-i];
             o0 = __fadd_rn(o0, __fmul_rn(d, fir.fir4[i][0]));
             o1 = __fadd_rn(o1, __fmul_rn(d, fir.fir4[i][1]));
             o2 = __fadd_rn(o2, __fmul_rn(d, fir.fir4[i][2]));
@@ -275,18 +338,16 @@ __global__ void __launch_bounds__(256) k_true_peak(LoudBatchArgs a, TruePeakFir 
         } else if (a.tp_delay_len == 24) {
           float o = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 24; ++i) {
-            const float d = t >= (uint64_t)i ? __ldg(&x[(t - i) * C + c]) : 0.0f;
-            o = __fadd_rn(o, __fmul_rn(d, fir.fir2[i]));
-          }
+          for (int i = 0; i < 24; ++i) o = __fadd_rn(o, __fmul_rn(row[-i], fir.fir2[i]));
           pk = fmaxf(pk, fabsf(o));
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
       // NaN input: fmaxf drops NaN exactly like Rust's f32::max in TruePeakMeter::process.
-      if (lane == 0) atomicMax(&a.peak[sb * C + c], __float_as_uint(pk));
+      if (lane == 0 && pk > 0.0f) atomicMax(&a.peak[sb * C + c], __float_as_uint(pk));
     }
+    __syncthreads();
   }
 }
 
@@ -406,6 +467,9 @@ int LoudnessPlan::init(const omb_loudness_config& c, uint32_t ch, const uint8_t*
   static_assert(kKwChunk == 256, "chunk matrix uses 8 squarings");
   for (int i = 0; i < 8; ++i) mat4_mul(A, A, A);
   for (int i = 0; i < 16; ++i) chunk_matrix[i] = (double)A[i];
+  static_assert(kKwSeg == 64, "segment matrix uses 6 more squarings");
+  for (int i = 0; i < 6; ++i) mat4_mul(A, A, A);
+  for (int i = 0; i < 16; ++i) seg_matrix[i] = (double)A[i];
   OMB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   return OMB_OK;
 }
@@ -426,6 +490,10 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   a.tp_delay_len = tp_delay_len;
   a.kw = kw;
   std::memcpy(a.M, chunk_matrix, sizeof a.M);
+  std::memcpy(a.Mseg, seg_matrix, sizeof a.Mseg);
+  const uint64_t n_seg = (a.n_chunks + kKwSeg - 1) / kKwSeg;
+  OMB_TRY(d_seg.reserve((size_t)((uint64_t)n_streams * n_seg * channels * 4)));
+  a.seg_state = d_seg.ptr;
   const uint64_t n_state = (uint64_t)n_streams * a.n_chunks * channels * 4;
   OMB_TRY(d_end.reserve((size_t)n_state));
   OMB_TRY(d_start.reserve((size_t)n_state));
@@ -452,12 +520,23 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   auto k_apply = k_kw_chunks<true>;
   OMB_LAUNCH(k_zero, dim3(g1), dim3(128), 0, s, a);
   OMB_CHECK_LAUNCH();
-  OMB_LAUNCH(k_kw_scan, dim3((unsigned)(((uint64_t)n_streams * channels + 63) / 64)), dim3(64), 0, s, a);
-  OMB_CHECK_LAUNCH();
+  {
+    auto k_s0 = k_kw_scan<0>;
+    auto k_s1 = k_kw_scan<1>;
+    auto k_s2 = k_kw_scan<2>;
+    const uint64_t n_segments = (a.n_chunks + kKwSeg - 1) / kKwSeg;
+    const unsigned gs = (unsigned)(((uint64_t)n_streams * n_segments * channels + 127) / 128);
+    OMB_LAUNCH(k_s0, dim3(gs), dim3(128), 0, s, a);
+    OMB_CHECK_LAUNCH();
+    OMB_LAUNCH(k_s1, dim3((unsigned)(((uint64_t)n_streams * channels + 127) / 128)), dim3(128), 0, s, a);
+    OMB_CHECK_LAUNCH();
+    OMB_LAUNCH(k_s2, dim3(gs), dim3(128), 0, s, a);
+    OMB_CHECK_LAUNCH();
+  }
   OMB_LAUNCH(k_apply, dim3(g1), dim3(128), 0, s, a);
   OMB_CHECK_LAUNCH();
-  const unsigned gx = (unsigned)std::min<uint64_t>((block_frames + 255) / 256, 64);
-  OMB_LAUNCH(k_true_peak, dim3((unsigned)((uint64_t)n_streams * a.n_blocks), gx), dim3(256), 0, s, a, fir);
+  const unsigned gx = (unsigned)std::min<uint64_t>((block_frames + kTpTile - 1) / kTpTile, 64);
+  OMB_LAUNCH(k_true_peak, dim3((unsigned)((uint64_t)n_streams * a.n_blocks), gx), dim3(kTpTile), 0, s, a, fir);
   OMB_CHECK_LAUNCH();
   const uint64_t n_snap = (uint64_t)n_streams * a.n_blocks;
   OMB_LAUNCH(k_loud_snapshots, dim3((unsigned)((n_snap * 32 + 127) / 128)), dim3(128), 0, s, a);

@@ -7,6 +7,7 @@ namespace omb {
 
 constexpr int kLoudWindows = 4;        // short-term 3 s, momentary 0.4 s, rms fast 0.3 s, rms slow 1 s
 constexpr int kKwChunk = 256;          // samples per chunk of the chunk-parallel IIR
+constexpr int kKwSeg = 64;             // chunks per segment of the three-level state scan
 
 struct KWeight { double b[5], a[5]; };
 struct TruePeakFir { float fir4[12][3]; float fir2[24]; };
@@ -61,9 +62,10 @@ struct LoudnessPlan {
   KWeight kw;
   TruePeakFir fir;
   double chunk_matrix[16];               // A^kKwChunk, row-major (state transition over one chunk)
+  double seg_matrix[16];                 // A^(kKwChunk*kKwSeg)
   uint64_t caps[kLoudWindows];
   uint32_t tp_delay_len = 0;
-  DeviceBuffer<double> d_end, d_start, d_csum, d_cbase;
+  DeviceBuffer<double> d_end, d_start, d_csum, d_cbase, d_seg;
   DeviceBuffer<float> d_y;
   DeviceBuffer<unsigned> d_peak;
   DeviceBuffer<float> d_in;

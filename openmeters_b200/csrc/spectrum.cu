@@ -233,6 +233,11 @@ int SpectrumPlan::init(const omb_spectrum_config& c) {
   OMB_TRY(d_norm.upload(h_norm, stream));
   OMB_TRY(d_adb.upload(h_adb, stream));
   OMB_TRY(d_tw.upload(make_twiddles((size_t)N, (size_t)std::max<uint64_t>(N / 2, 1)), stream));
+  fast16k = false;
+  if (spectrum_fast_supported(cfg, dev) && !getenv("OMB_NO_FAST_SPECTRUM")) {
+    OMB_TRY(spectrum_fast_prepare(*this));
+    fast16k = true;
+  }
   OMB_CUDA_TRY(cudaStreamSynchronize(stream));
   return OMB_OK;
 }
@@ -254,6 +259,7 @@ int SpectrumPlan::power_device(const float* d_lanes, uint32_t n_lanes, uint64_t 
   a.bin_norm = d_norm.ptr;
   a.tw = d_tw.ptr;
   a.power = d_power_out;
+  if (fast16k && (reinterpret_cast<uintptr_t>(d_lanes) & 7u) == 0 && (lane_stride & 1) == 0) return launch_spectrum_power_fast(*this, a, s);
   const uint64_t N = cfg.fft_size;
   const size_t smem = (size_t)N * sizeof(float2);  // two buffers of N/2 complex
   if (N >= 16 && N <= 16384 && !getenv("OMB_NO_SMEM_KERNEL") && (dev.max_smem_optin == 0 || smem + 1024 <= (size_t)dev.max_smem_optin)) {

@@ -60,6 +60,9 @@ struct SpectrumPlan {
   DeviceBuffer<float2> d_tw, d_scratch;
   DeviceBuffer<float> d_power, d_state;
   DeviceBuffer<unsigned long long> d_keys;
+  bool fast16k = false;                 // spectrum_fast.cu applies (N = 16384)
+  DeviceBuffer<float2> d_fast_tables;
+  DeviceBuffer<double> d_bsum;
   // host-path staging
   DeviceBuffer<float> d_in, d_w, d_r;
   DeviceBuffer<int32_t> d_peak;
@@ -77,5 +80,10 @@ struct SpectrumPlan {
   int execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride, float* h_weighted,
                    float* h_raw, int32_t* h_peak_bin);
 };
+
+// spectrum_fast.cu
+bool spectrum_fast_supported(const SpectrumConfigN& cfg, const DeviceInfo& dev);
+int spectrum_fast_prepare(SpectrumPlan& p);
+int launch_spectrum_power_fast(SpectrumPlan& p, SpectrumPowerArgs& a, cudaStream_t s);
 
 }  // namespace omb

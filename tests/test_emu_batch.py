@@ -74,3 +74,11 @@ def test_host_path_pipelined_lane_chunks(emu):
     lanes = synth.cfg2_lanes(5, (8192 + 2 * 1024) / 48000.0)
     st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
     assert st["cols"] == 15
+
+
+def test_spectrum_fast_16k(emu):
+    """spectrum_fast.cu (N = 16384: two parallel 4096-point FFTs + fused combine / real split) vs the oracle."""
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=capi.AVG_PEAK_HOLD,
+                         averaging_param=12.0, floor_db=-100.0)
+    lanes = synth.cfg4_streams(1, (16384 + 2 * 1024) / 48000.0).reshape(2, -1)
+    cases.spectrum_parity(emu.api, cfg, lanes)
