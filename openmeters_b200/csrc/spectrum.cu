@@ -128,54 +128,61 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_smooth(SpectrumSmoothArgs
   if (live && a.state && a.mode != OMB_AVG_NONE) st = a.state[(uint64_t)lane * a.bins + k];
   const float aw = live ? __ldg(&a.a_db[k]) : 0.0f;
   const float one_minus_alpha = __fsub_rn(1.0f, a.alpha);
-  for (uint64_t h = 0; h < a.hops; ++h) {
-    float raw = a.floor_db, weighted = a.floor_db;
-    if (live) {
-      const float p = __ldg(&a.power[((uint64_t)lane * a.hops + h) * a.bins + k]);
-      float v = p;
-      if (a.mode == OMB_AVG_EXPONENTIAL) {  // spectrum/processor.rs:366-377 (re-seed when the average hit zero)
-        st = st <= 0.0f ? p : __fadd_rn(__fmul_rn(st, a.alpha), __fmul_rn(p, one_minus_alpha));
-        if (st < a.state_floor) st = 0.0f;
-        v = st;
-      } else if (a.mode == OMB_AVG_PEAK_HOLD) {  // :380-388
-        st = fmaxf(__fmul_rn(st, a.decay), p);
-        if (st < a.state_floor) st = 0.0f;
-        v = st;
-      }
-      if (!(v < a.state_floor)) {  // :392-401
-        const float db = __fmul_rn(logf(v), kLnToDb);
-        raw = fmaxf(db, a.floor_db);
-        weighted = fmaxf(__fadd_rn(db, aw), a.floor_db);
-      }
-      const uint64_t o = a.write_all ? (((uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h) * a.bins + k)
-                                     : ((uint64_t)lane * a.bins + k);
-      if (a.write_all || h + 1 == a.hops) {
-        a.out_weighted[o] = weighted;
-        a.out_raw[o] = raw;
-      }
-    }
-    if (a.peak_keys) {  // spectrum/state.rs:321-325: bins 1..len-2, finite, last maximum wins
-      unsigned long long key = 0ull;
-      if (live && k >= 1 && k + 1 < (int)a.bins && isfinite(raw))
-        key = ((unsigned long long)ordered_bits(raw) << 32) | (unsigned)k;
+  for (uint64_t h0 = 0; h0 < a.hops; h0 += 4) {
+    // the recurrence is sequential over hops, the loads are not: fetch four hops of power before using them
+    float pw[4];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-        key = other > key ? other : key;
+    for (int i = 0; i < 4; ++i) pw[i] = (live && h0 + i < a.hops) ? __ldg(&a.power[((uint64_t)lane * a.hops + h0 + i) * a.bins + k]) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint64_t h = h0 + i;
+      if (h >= a.hops) break;
+      float raw = a.floor_db, weighted = a.floor_db;
+      if (live) {
+        const float p = pw[i];
+        float v = p;
+        if (a.mode == OMB_AVG_EXPONENTIAL) {  // spectrum/processor.rs:366-377 (re-seed when the average hit zero)
+          st = st <= 0.0f ? p : __fadd_rn(__fmul_rn(st, a.alpha), __fmul_rn(p, one_minus_alpha));
+          if (st < a.state_floor) st = 0.0f;
+          v = st;
+        } else if (a.mode == OMB_AVG_PEAK_HOLD) {  // :380-388
+          st = fmaxf(__fmul_rn(st, a.decay), p);
+          if (st < a.state_floor) st = 0.0f;
+          v = st;
+        }
+        if (!(v < a.state_floor)) {  // :392-401
+          const float db = __fmul_rn(logf(v), kLnToDb);
+          raw = fmaxf(db, a.floor_db);
+          weighted = fmaxf(__fadd_rn(db, aw), a.floor_db);
+        }
+        const uint64_t o = a.write_all ? (((uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h) * a.bins + k)
+                                       : ((uint64_t)lane * a.bins + k);
+        if (a.write_all || h + 1 == a.hops) {
+          a.out_weighted[o] = weighted;
+          a.out_raw[o] = raw;
+        }
       }
-      if (lane_id == 0 && key) atomicMax(&a.peak_keys[(uint64_t)lane * a.hops + h], key);
+      if (a.peak_keys) {  // spectrum/state.rs:321-325: bins 1..len-2, finite, last maximum wins
+        unsigned long long key = 0ull;
+        if (live && k >= 1 && k + 1 < (int)a.bins && isfinite(raw))
+          key = ((unsigned long long)ordered_bits(raw) << 32) | (unsigned)k;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other > key ? other : key;
+        }
+        if (lane_id == 0 && key) atomicMax(&a.peak_keys[(uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h], key);
+      }
     }
   }
   if (live && a.state && a.mode != OMB_AVG_NONE) a.state[(uint64_t)lane * a.bins + k] = st;
 }
 
-__global__ void k_peak_keys_to_bins(const unsigned long long* keys, uint32_t n_lanes, uint64_t hops, uint64_t hops_total,
-                                    uint64_t hop0, int32_t* out) {
+__global__ void k_peak_keys_to_bins(const unsigned long long* keys, uint64_t n, int32_t* out) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hops * n_lanes) return;
-  const uint64_t lane = i / hops, h = i % hops;
+  if (i >= n) return;
   const unsigned long long key = keys[i];
-  out[lane * hops_total + hop0 + h] = key ? (int32_t)(key & 0xffffffffu) : -1;
+  out[i] = key ? (int32_t)(key & 0xffffffffu) : -1;
 }
 
 }  // namespace
@@ -282,7 +289,7 @@ int SpectrumPlan::power_device(const float* d_lanes, uint32_t n_lanes, uint64_t 
 }
 
 static int smooth_launch(SpectrumPlan& p, const float* d_power_in, uint32_t n_lanes, uint64_t hops, float* d_state, float* d_weighted,
-                         float* d_raw, int32_t* d_peak_bin, bool write_all, uint64_t hops_total, uint64_t hop0, cudaStream_t s) {
+                         float* d_raw, unsigned long long* keys, bool write_all, uint64_t hops_total, uint64_t hop0, cudaStream_t s) {
   if (!hops || !n_lanes) return OMB_OK;
   const SpectrumConfigN& cfg = p.cfg;
   SpectrumSmoothArgs a{};
@@ -301,29 +308,33 @@ static int smooth_launch(SpectrumPlan& p, const float* d_power_in, uint32_t n_la
   a.out_weighted = d_weighted;
   a.out_raw = d_raw;
   a.write_all = write_all ? 1 : 0;
-  a.peak_keys = nullptr;
-  if (d_peak_bin && !write_all) return fail(OMB_ERR_INVALID, "peak bins are only produced together with per-hop outputs");
-  if (d_peak_bin) {
-    OMB_TRY(p.d_keys.reserve((size_t)(hops * n_lanes)));
-    OMB_CUDA_TRY(cudaMemsetAsync(p.d_keys.ptr, 0, sizeof(unsigned long long) * hops * n_lanes, s));
-    a.peak_keys = p.d_keys.ptr;
-  }
+  a.peak_keys = keys;  // caller-owned [n_lanes * hops_total], zeroed
+  if (keys && !write_all) return fail(OMB_ERR_INVALID, "peak bins are only produced together with per-hop outputs");
   SmoothLayout lay{hops_total, hop0};
   const dim3 grid((unsigned)((a.bins + kThreads - 1) / kThreads), n_lanes);
   OMB_LAUNCH(k_spectrum_smooth, grid, dim3(kThreads), 0, s, a, lay);
   OMB_CHECK_LAUNCH();
-  if (d_peak_bin) {
-    const uint64_t n = hops * n_lanes;
-    OMB_LAUNCH(k_peak_keys_to_bins, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p.d_keys.ptr, n_lanes, hops, hops_total, hop0,
-               d_peak_bin);
-    OMB_CHECK_LAUNCH();
-  }
+  return OMB_OK;
+}
+
+static int keys_begin(SpectrumPlan& p, uint64_t n, cudaStream_t s) {
+  OMB_TRY(p.d_keys.reserve((size_t)n));
+  OMB_CUDA_TRY(cudaMemsetAsync(p.d_keys.ptr, 0, sizeof(unsigned long long) * n, s));
+  return OMB_OK;
+}
+static int keys_finish(SpectrumPlan& p, uint64_t n, int32_t* d_peak_bin, cudaStream_t s) {
+  OMB_LAUNCH(k_peak_keys_to_bins, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p.d_keys.ptr, n, d_peak_bin);
+  OMB_CHECK_LAUNCH();
   return OMB_OK;
 }
 
 int SpectrumPlan::smooth_device(const float* d_power_in, uint32_t n_lanes, uint64_t hops, float* d_state_io, float* d_weighted,
                                 float* d_raw, int32_t* d_peak_bin, bool write_all, cudaStream_t s) {
-  return smooth_launch(*this, d_power_in, n_lanes, hops, d_state_io, d_weighted, d_raw, d_peak_bin, write_all, hops, 0, s);
+  const uint64_t n = hops * n_lanes;
+  if (d_peak_bin) OMB_TRY(keys_begin(*this, n, s));
+  OMB_TRY(smooth_launch(*this, d_power_in, n_lanes, hops, d_state_io, d_weighted, d_raw, d_peak_bin ? d_keys.ptr : nullptr, write_all, hops, 0, s));
+  if (d_peak_bin && n) OMB_TRY(keys_finish(*this, n, d_peak_bin, s));
+  return OMB_OK;
 }
 
 int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
@@ -333,7 +344,7 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
   if (!d_lanes || !d_weighted || !d_raw) return fail(OMB_ERR_INVALID, "null argument");
   const uint64_t bins = cfg.bins();
   // chunk of hops whose power scratch (n_lanes*chunk*bins*4 B) stays comfortably inside the 126 MB L2
-  const uint64_t budget_floats = (48ull << 20) / 4;
+  const uint64_t budget_floats = (64ull << 20) / 4;
   uint64_t chunk = std::max<uint64_t>(1, budget_floats / std::max<uint64_t>(1, (uint64_t)n_lanes * bins));
   chunk = std::min(chunk, hops);
   OMB_TRY(d_power.reserve((size_t)((uint64_t)n_lanes * chunk * bins)));
@@ -343,11 +354,22 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
     OMB_CUDA_TRY(cudaMemsetAsync(d_state.ptr, 0, sizeof(float) * n_lanes * bins, s));
     state = d_state.ptr;
   }
-  for (uint64_t h0 = 0; h0 < hops; h0 += chunk) {
-    const uint64_t n = std::min(chunk, hops - h0);
-    OMB_TRY(power_device(d_lanes + h0 * cfg.hop, n_lanes, n, lane_stride, d_power.ptr, s));
-    OMB_TRY(smooth_launch(*this, d_power.ptr, n_lanes, n, state, d_weighted, d_raw, d_peak_bin, true, hops, h0, s));
+  if (d_peak_bin) OMB_TRY(keys_begin(*this, hops * n_lanes, s));
+  if (fast16k) {  // hop-block sums for DC removal: once for the whole batch, chunks index into them
+    OMB_TRY(spectrum_fast_block_sums(*this, d_lanes, lane_stride, n_lanes, hops, s));
+    ext_bsum_blocks = hops - 1 + cfg.fft_size / cfg.hop;
   }
+  int rc = OMB_OK;
+  for (uint64_t h0 = 0; h0 < hops && rc >= 0; h0 += chunk) {
+    const uint64_t n = std::min(chunk, hops - h0);
+    ext_block_off = h0;
+    rc = power_device(d_lanes + h0 * cfg.hop, n_lanes, n, lane_stride, d_power.ptr, s);
+    if (rc >= 0) rc = smooth_launch(*this, d_power.ptr, n_lanes, n, state, d_weighted, d_raw, d_peak_bin ? d_keys.ptr : nullptr, true, hops, h0, s);
+  }
+  ext_bsum_blocks = 0;
+  ext_block_off = 0;
+  OMB_TRY(rc);
+  if (d_peak_bin) OMB_TRY(keys_finish(*this, hops * n_lanes, d_peak_bin, s));
   return OMB_OK;
 }
 

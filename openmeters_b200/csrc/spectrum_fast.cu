@@ -172,6 +172,16 @@ int spectrum_fast_prepare(SpectrumPlan& p) {
   return OMB_OK;
 }
 
+int spectrum_fast_block_sums(SpectrumPlan& p, const float* d_lanes, uint64_t lane_stride, uint32_t n_lanes, uint64_t hops, cudaStream_t s) {
+  const uint64_t n_blocks = hops - 1 + (uint64_t)kN / p.cfg.hop;
+  OMB_TRY(p.d_bsum.reserve((size_t)(n_blocks * n_lanes)));
+  const uint64_t warps = n_blocks * n_lanes;
+  OMB_LAUNCH(k_block_sums, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, s, d_lanes, lane_stride, n_lanes, n_blocks,
+             (uint32_t)p.cfg.hop, p.d_bsum.ptr);
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
 int launch_spectrum_power_fast(SpectrumPlan& p, SpectrumPowerArgs& a, cudaStream_t s) {
   const uint64_t total = a.hops * a.n_lanes;
   if (!total) return OMB_OK;
@@ -183,13 +193,14 @@ int launch_spectrum_power_fast(SpectrumPlan& p, SpectrumPowerArgs& a, cudaStream
   fa.tw2 = fa.tw1 + 15 * kT;
   fa.w16 = fa.tw2 + 15 * 16;
   fa.blocks_per_frame = (uint32_t)(kN / a.hop);
-  fa.n_blocks = a.hops - 1 + fa.blocks_per_frame;
-  OMB_TRY(p.d_bsum.reserve((size_t)(fa.n_blocks * a.n_lanes)));
-  fa.bsum = p.d_bsum.ptr;
-  const uint64_t warps = fa.n_blocks * a.n_lanes;
-  OMB_LAUNCH(k_block_sums, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, s, a.lanes, a.lane_stride, a.n_lanes, fa.n_blocks, a.hop,
-             p.d_bsum.ptr);
-  OMB_CHECK_LAUNCH();
+  if (p.ext_bsum_blocks) {  // batch-wide sums computed by spectrum_fast_block_sums(); this launch starts at ext_block_off
+    fa.n_blocks = p.ext_bsum_blocks;
+    fa.bsum = p.d_bsum.ptr + p.ext_block_off;
+  } else {
+    OMB_TRY(spectrum_fast_block_sums(p, a.lanes, a.lane_stride, a.n_lanes, a.hops, s));
+    fa.n_blocks = a.hops - 1 + fa.blocks_per_frame;
+    fa.bsum = p.d_bsum.ptr;
+  }
   const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(p.dev.sm_count, 1));
   OMB_LAUNCH(k_spectrum_power_16k, dim3(grid), dim3(kThreads), sizeof(SmemS), s, fa);
   OMB_CHECK_LAUNCH();
