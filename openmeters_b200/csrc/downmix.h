@@ -34,6 +34,16 @@ struct DeviceLane {
     begin = 0;
     return OMB_OK;
   }
+  // Moves the pending samples to offset 0 of the other buffer so that data() is 16-byte aligned again.
+  int realign(cudaStream_t s) {
+    if (begin % 4 == 0) return OMB_OK;
+    DeviceBuffer<float>& other = buf[1 - cur];
+    if (other.cap < len) OMB_TRY(other.reserve(std::max<size_t>(len * 2, 8192)));
+    if (len) OMB_CUDA_TRY(cudaMemcpyAsync(other.ptr, data(), len * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    cur = 1 - cur;
+    begin = 0;
+    return OMB_OK;
+  }
   void commit(size_t n) { len += n; }
   void drain(size_t n) {
     n = std::min(n, len);

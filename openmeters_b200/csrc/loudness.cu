@@ -478,6 +478,7 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
                                  uint64_t block_frames, omb_loudness_snapshot* d_out_snap, cudaStream_t s) {
   if (!n_streams || !frames) return OMB_OK;
   if (!d_interleaved || !d_out_snap || block_frames == 0) return fail(OMB_ERR_INVALID, "invalid argument");
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));
   LoudBatchArgs a{};
   a.in = d_interleaved;
   a.stream_stride = stream_stride;

@@ -253,6 +253,7 @@ int SpectrumPlan::power_device(const float* d_lanes, uint32_t n_lanes, uint64_t 
                                cudaStream_t s) {
   const uint64_t total = hops * n_lanes;
   if (!total) return OMB_OK;
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));
   SpectrumPowerArgs a{};
   a.lanes = d_lanes;
   a.lane_stride = lane_stride;

@@ -80,12 +80,16 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
       OMB_TRY(stft_fast2_prepare(*this));
       fast_kind = 2;
     }
-  } else if (choice == OMB_KERNEL_AUTO && stft_smem_supported(cfg, dev) && !(getenv("OMB_NO_SMEM_KERNEL"))) {
-    OMB_TRY(stft_smem_prepare(*this));
-    smem_kernel = true;
   } else if (choice == OMB_KERNEL_FAST) {
     return fail(OMB_ERR_UNSUPPORTED, "no specialised kernel for window %llu hop %llu zp %llu reassign %d",
                 (unsigned long long)N, (unsigned long long)cfg.hop, (unsigned long long)cfg.zero_pad, (int)cfg.reassign);
+  }
+  // The shared-memory tier is prepared whenever it applies: it is the kernel of choice when no specialised kernel
+  // exists, and the fallback of the specialised kernels when a caller's lanes are not 16-byte aligned (e.g. the
+  // streaming FIFO after an odd-sized drain).
+  if (choice != OMB_KERNEL_GENERIC && stft_smem_supported(cfg, dev) && !getenv("OMB_NO_SMEM_KERNEL")) {
+    OMB_TRY(stft_smem_prepare(*this));
+    smem_kernel = true;
   }
   OMB_CUDA_TRY(cudaStreamSynchronize(stream));
   return OMB_OK;
@@ -97,6 +101,7 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   const uint64_t frames = cfg.frames_for(samples_per_lane);
   if (frames == 0 || n_lanes == 0 || first_frame >= frames) return OMB_OK;
   if (!d_lanes) return fail(OMB_ERR_INVALID, "null lanes pointer");
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));  // plans are bound to the device they were created on
   if (cfg.reassign) {
     if (!out_points || !out_counts) return fail(OMB_ERR_INVALID, "reassigned plan needs out_points and out_counts");
     if (point_stride < cfg.bins()) return fail(OMB_ERR_INVALID, "point_stride %llu < bins %llu", (unsigned long long)point_stride, (unsigned long long)cfg.bins());
@@ -133,8 +138,10 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   a.point_stride = point_stride;
   a.out_counts = out_counts;
   a.out_classic = out_classic;
-  if (fast_kind == 2) return launch_stft_fast2(*this, a, s);
-  if (fast) return launch_stft_fast(*this, a, s);
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(d_lanes) & 15u) == 0 && (lane_stride % 4) == 0;
+  if (fast && aligned16) return fast_kind == 2 ? launch_stft_fast2(*this, a, s) : launch_stft_fast(*this, a, s);
+  if (fast && kernel_choice == OMB_KERNEL_FAST)
+    return fail(OMB_ERR_INVALID, "OMB_KERNEL_FAST was forced but the lanes are not 16-byte aligned (pointer and lane_stride % 4 == 0)");
   if (smem_kernel) return launch_stft_smem(*this, a, s, d_scratch);
   return launch_stft_generic(*this, a, s, d_scratch);
 }
@@ -145,24 +152,30 @@ int StftPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samp
   const uint64_t frames = cfg.frames_for(samples_per_lane);
   if (frames == 0 || n_lanes == 0) return OMB_OK;
   if (!h_lanes) return fail(OMB_ERR_INVALID, "null lanes pointer");
-  // H2D (one copy per lane when the caller's stride is not dense)
-  OMB_TRY(d_in.reserve((size_t)(samples_per_lane * n_lanes)));
+  // Device lanes are laid out with a stride rounded up to 4 samples so that every lane is 16-byte aligned for the
+  // specialised kernels; one H2D copy per lane when that differs from the caller's stride.
+  const uint64_t ds = (samples_per_lane + 3) & ~(uint64_t)3;
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));
+  OMB_TRY(d_in.reserve((size_t)(ds * n_lanes)));
+  auto upload = [&](uint32_t l0, uint32_t nl, cudaStream_t st) -> int {
+    if (lane_stride == ds) {
+      OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + (uint64_t)l0 * ds, h_lanes + (uint64_t)l0 * lane_stride,
+                                   sizeof(float) * (ds * (nl - 1) + samples_per_lane), cudaMemcpyHostToDevice, st));
+    } else {
+      for (uint32_t l = l0; l < l0 + nl; ++l)
+        OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + (uint64_t)l * ds, h_lanes + (uint64_t)l * lane_stride, sizeof(float) * samples_per_lane,
+                                     cudaMemcpyHostToDevice, st));
+    }
+    return OMB_OK;
+  };
   const bool pipelined = cfg.reassign && fast_kind > 0 && n_lanes >= 4;
-  if (pipelined) {
-    // copies are issued chunk by chunk below
-  } else if (lane_stride == samples_per_lane) {
-    OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr, h_lanes, sizeof(float) * samples_per_lane * n_lanes, cudaMemcpyHostToDevice, stream));
-  } else {
-    for (uint32_t l = 0; l < n_lanes; ++l)
-      OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + l * samples_per_lane, h_lanes + l * lane_stride, sizeof(float) * samples_per_lane,
-                                   cudaMemcpyHostToDevice, stream));
-  }
+  if (!pipelined) OMB_TRY(upload(0, n_lanes, stream));
   const uint64_t slots = frames * n_lanes;
   if (cfg.reassign) {
     if (!h_points || !h_counts) return fail(OMB_ERR_INVALID, "reassigned plan needs out_points and out_counts");
     OMB_TRY(d_points.reserve((size_t)(slots * point_stride)));
     OMB_TRY(d_counts.reserve((size_t)slots));
-    if (fast_kind > 0 && n_lanes >= 4) {
+    if (pipelined) {
       // Specialised kernels need no scratch, so lane chunks can be pipelined over three streams: the H2D of chunk
       // i+1, the kernel of chunk i and the D2H of chunk i-1 overlap (PCIe is full duplex; D2H of 12-byte points
       // dominates: ~24.6 KB per frame).
@@ -174,16 +187,9 @@ int StftPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samp
       for (uint32_t l0 = 0; l0 < n_lanes; l0 += chunk, ++k) {
         const uint32_t nl = std::min(chunk, n_lanes - l0);
         cudaStream_t ps = pipe[k % 3];
-        if (lane_stride == samples_per_lane) {
-          OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + (uint64_t)l0 * samples_per_lane, h_lanes + (uint64_t)l0 * lane_stride,
-                                       sizeof(float) * samples_per_lane * nl, cudaMemcpyHostToDevice, ps));
-        } else {
-          for (uint32_t l = l0; l < l0 + nl; ++l)
-            OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + (uint64_t)l * samples_per_lane, h_lanes + (uint64_t)l * lane_stride,
-                                         sizeof(float) * samples_per_lane, cudaMemcpyHostToDevice, ps));
-        }
+        OMB_TRY(upload(l0, nl, ps));
         const uint64_t s0 = (uint64_t)l0 * frames;
-        OMB_TRY(execute_device(d_in.ptr + (uint64_t)l0 * samples_per_lane, nl, samples_per_lane, samples_per_lane,
+        OMB_TRY(execute_device(d_in.ptr + (uint64_t)l0 * ds, nl, samples_per_lane, ds,
                                d_points.ptr + s0 * point_stride, point_stride, d_counts.ptr + s0, nullptr, ps));
         OMB_CUDA_TRY(cudaMemcpyAsync(h_counts + s0, d_counts.ptr + s0, sizeof(uint32_t) * frames * nl, cudaMemcpyDeviceToHost, ps));
         OMB_CUDA_TRY(cudaMemcpyAsync(h_points + s0 * point_stride, d_points.ptr + s0 * point_stride,
@@ -192,7 +198,7 @@ int StftPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samp
       for (auto& ps : pipe) OMB_CUDA_TRY(cudaStreamSynchronize(ps));
       return OMB_OK;
     }
-    OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, d_points.ptr, point_stride, d_counts.ptr,
+    OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, ds, d_points.ptr, point_stride, d_counts.ptr,
                            nullptr, stream));
     OMB_CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts.ptr, sizeof(uint32_t) * slots, cudaMemcpyDeviceToHost, stream));
     OMB_CUDA_TRY(cudaMemcpyAsync(h_points, d_points.ptr, sizeof(omb_spectrogram_point) * slots * point_stride,
@@ -200,7 +206,7 @@ int StftPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samp
   } else {
     if (!h_classic) return fail(OMB_ERR_INVALID, "classic plan needs out_classic");
     OMB_TRY(d_classic.reserve((size_t)(slots * cfg.bins())));
-    OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, nullptr, 0, nullptr, d_classic.ptr, stream));
+    OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, ds, nullptr, 0, nullptr, d_classic.ptr, stream));
     OMB_CUDA_TRY(cudaMemcpyAsync(h_classic, d_classic.ptr, sizeof(uint16_t) * slots * cfg.bins(), cudaMemcpyDeviceToHost, stream));
   }
   OMB_CUDA_TRY(cudaStreamSynchronize(stream));

@@ -52,6 +52,7 @@ int SpectrogramStream::rebuild_fft() {  // processor.rs:229-279 (buffer semantic
   const uint64_t active_len = config.reassign ? config.hilbert_len() : config.fft_len();
   const uint64_t buffered = active_len * 2;
   if (pending.len > buffered) pending.drain(pending.len - (size_t)buffered);
+  OMB_TRY(pending.realign(stream));  // keeps the specialised kernels' 16-byte alignment across odd-sized drains
   pending_skip = 0;
   return OMB_OK;
 }
@@ -137,7 +138,7 @@ int SpectrogramStream::process_block(const float* samples, size_t n_samples, uin
   if (config.reassign) {
     OMB_TRY(d_points.reserve((size_t)(n * bins)));
     OMB_TRY(d_counts.reserve((size_t)n));
-    OMB_TRY(plan->execute_device(pending.data(), 1, pending.len, pending.len, d_points.ptr, bins, d_counts.ptr, nullptr, stream));
+    OMB_TRY(plan->execute_device(pending.data(), 1, pending.len, (pending.len + 3) & ~(size_t)3, d_points.ptr, bins, d_counts.ptr, nullptr, stream));
     OMB_TRY(h_counts.reserve((size_t)n));
     OMB_TRY(h_points.reserve((size_t)(n * bins)));
     OMB_CUDA_TRY(cudaMemcpyAsync(h_counts.ptr, d_counts.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -150,7 +151,7 @@ int SpectrogramStream::process_block(const float* samples, size_t n_samples, uin
     }
   } else {
     OMB_TRY(d_classic.reserve((size_t)(n * bins)));
-    OMB_TRY(plan->execute_device(pending.data(), 1, pending.len, pending.len, nullptr, 0, nullptr, d_classic.ptr, stream));
+    OMB_TRY(plan->execute_device(pending.data(), 1, pending.len, (pending.len + 3) & ~(size_t)3, nullptr, 0, nullptr, d_classic.ptr, stream));
     classic.resize((size_t)(n * bins));
     OMB_CUDA_TRY(cudaMemcpyAsync(classic.data(), d_classic.ptr, n * bins * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream));
     OMB_CUDA_TRY(cudaStreamSynchronize(stream));

@@ -6,7 +6,7 @@ import pytest
 from openmeters_b200 import _capi as capi
 from openmeters_b200 import synth
 from openmeters_b200.processors import LoudnessConfig, SpectrogramConfig, SpectrumConfig
-from tests import cases
+from tests import cases, parity
 
 
 @pytest.mark.parametrize("window,n,hop,zp", [(capi.WINDOW_HANN, 64, 16, 1), (capi.WINDOW_BLACKMAN_HARRIS, 256, 64, 2),
@@ -82,3 +82,42 @@ def test_spectrum_fast_16k(emu):
                          averaging_param=12.0, floor_db=-100.0)
     lanes = synth.cfg4_streams(1, (16384 + 2 * 1024) / 48000.0).reshape(2, -1)
     cases.spectrum_parity(emu.api, cfg, lanes)
+
+
+def test_streaming_survives_misaligned_fifo(emu):
+    """After an odd-sized drain (config change) the device FIFO is no longer 16-byte aligned: the specialised
+    N=4096 kernel must hand over to the shared-memory tier instead of failing, with identical columns."""
+    from openmeters_b200.processors import AudioBlock, SpectrogramProcessor
+    from oracle import oracle_py
+
+    lane = synth.cfg2_lanes(1, 1.0)[0]
+    outs = {}
+    for name, api in (("emu", emu.api), ("oracle", oracle_py.api())):
+        p = SpectrogramProcessor(SpectrogramConfig(fft_size=256, hop_size=65, window=capi.WINDOW_BLACKMAN_HARRIS,
+                                                   use_reassignment=True, history_length=64), api=api)
+        p.process_block(AudioBlock(lane[:1001], 1, 48000.0))          # 12 frames * 65 = 780... +65 -> odd FIFO offset below
+        p.process_block(AudioBlock(lane[1001:1101], 1, 48000.0))      # 13th frame: FIFO begins at sample 845 (odd)
+        c = p.config()
+        c.fft_size, c.hop_size = 4096, 1024                            # rebuild: keeps the newest 2*H samples (odd offset)
+        p.update_config(c)
+        cols = []
+        for s in range(1101, 1101 + 12 * 1024 + 9000, 1024):
+            up = p.process_block(AudioBlock(lane[s:s + 1024], 1, 48000.0))
+            if up is not None:
+                cols.extend(up.new_columns)
+        outs[name] = cols
+    assert len(outs["emu"]) == len(outs["oracle"]) > 3
+    for a, b in zip(outs["emu"], outs["oracle"]):
+        parity.compare_reassigned_column(a, b, sr=48000.0, fft_len=4096, window=4096, hop=1024)
+
+
+def test_host_path_ragged_lane_length(emu):
+    """Lane lengths that are not a multiple of 4 samples: the host path pads the device stride so every lane stays
+    16-byte aligned for the specialised kernel (KERNEL_FAST would fail loudly otherwise)."""
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    lanes = np.ascontiguousarray(synth.cfg2_lanes(5, (8192 + 2 * 1024 + 4) / 48000.0)[:, : 8192 + 2 * 1024 + 3])
+    assert lanes.shape[1] % 4 == 3
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 15
+    st = cases.stft_parity(emu.api, cfg, lanes[:2], kernel=capi.KERNEL_FAST, expect_fast=True)  # non-pipelined branch
+    assert st["cols"] == 6
