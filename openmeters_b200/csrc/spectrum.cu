@@ -128,15 +128,19 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_smooth(SpectrumSmoothArgs
   if (live && a.state && a.mode != OMB_AVG_NONE) st = a.state[(uint64_t)lane * a.bins + k];
   const float aw = live ? __ldg(&a.a_db[k]) : 0.0f;
   const float one_minus_alpha = __fsub_rn(1.0f, a.alpha);
-  for (uint64_t h0 = 0; h0 < a.hops; h0 += 4) {
-    // the recurrence is sequential over hops, the loads are not: fetch four hops of power before using them
-    float pw[4];
+  const bool interior = live && k >= 1 && k + 1 < (int)a.bins;
+  constexpr int kAhead = 8;
+  for (uint64_t h0 = 0; h0 < a.hops; h0 += kAhead) {
+    // the recurrence is sequential over hops, the loads are not: fetch kAhead hops of power before using them
+    float pw[kAhead];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pw[i] = (live && h0 + i < a.hops) ? __ldg(&a.power[((uint64_t)lane * a.hops + h0 + i) * a.bins + k]) : 0.0f;
+    for (int i = 0; i < kAhead; ++i)
+      pw[i] = (live && h0 + i < a.hops) ? __ldg(&a.power[((uint64_t)lane * a.hops + h0 + i) * a.bins + k]) : 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kAhead; ++i) {
       const uint64_t h = h0 + i;
       if (h >= a.hops) break;
+      const bool emit = a.write_all || h + 1 == a.hops;  // dB values are only needed where something is stored
       float raw = a.floor_db, weighted = a.floor_db;
       if (live) {
         const float p = pw[i];
@@ -150,28 +154,25 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_smooth(SpectrumSmoothArgs
           if (st < a.state_floor) st = 0.0f;
           v = st;
         }
-        if (!(v < a.state_floor)) {  // :392-401
-          const float db = __fmul_rn(logf(v), kLnToDb);
-          raw = fmaxf(db, a.floor_db);
-          weighted = fmaxf(__fadd_rn(db, aw), a.floor_db);
-        }
-        const uint64_t o = a.write_all ? (((uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h) * a.bins + k)
-                                       : ((uint64_t)lane * a.bins + k);
-        if (a.write_all || h + 1 == a.hops) {
+        if (emit) {
+          if (!(v < a.state_floor)) {  // :392-401
+            const float db = __fmul_rn(logf(v), kLnToDb);
+            raw = fmaxf(db, a.floor_db);
+            weighted = fmaxf(__fadd_rn(db, aw), a.floor_db);
+          }
+          const uint64_t o = a.write_all ? (((uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h) * a.bins + k)
+                                         : ((uint64_t)lane * a.bins + k);
           a.out_weighted[o] = weighted;
           a.out_raw[o] = raw;
         }
       }
-      if (a.peak_keys) {  // spectrum/state.rs:321-325: bins 1..len-2, finite, last maximum wins
-        unsigned long long key = 0ull;
-        if (live && k >= 1 && k + 1 < (int)a.bins && isfinite(raw))
-          key = ((unsigned long long)ordered_bits(raw) << 32) | (unsigned)k;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-          key = other > key ? other : key;
-        }
-        if (lane_id == 0 && key) atomicMax(&a.peak_keys[(uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h], key);
+      if (a.peak_keys && emit) {  // spectrum/state.rs:321-325: bins 1..len-2, finite, last maximum wins
+        // two warp-wide integer max reductions (REDUX): the largest ordered dB value, then the largest bin holding it
+        const unsigned ob = (interior && isfinite(raw)) ? ordered_bits(raw) : 0u;
+        const unsigned best = __reduce_max_sync(0xffffffffu, ob);
+        const unsigned bin = __reduce_max_sync(0xffffffffu, (ob == best) ? (unsigned)k : 0u);
+        if (lane_id == 0 && best)
+          atomicMax(&a.peak_keys[(uint64_t)lane * lay.out_hops_total + lay.out_hop0 + h], ((unsigned long long)best << 32) | bin);
       }
     }
   }

@@ -1,0 +1,149 @@
+// stft_classic_fast.cu — warp-per-frame classic spectrogram column for N = 1024, zero padding 1
+// (BASELINE configs[0]; spectrogram/processor.rs:349-381, :103-108; util/audio/window.rs:66-88).
+//
+// One warp owns one frame from the first load to the last u16 store; nothing but __syncwarp separates its
+// phases, so 32 frames per SM are in flight independently and the memory phases of some overlap the arithmetic
+// of others.  The real 1024-point transform is the complex 512-point transform of z[n] = r[2n] + j r[2n+1]:
+//
+//   load     : half-warp s (16 lanes, r = lane & 15) reads z[n], z[n+256] for n = r + 16 j and forms the first
+//              radix-2 DIF stage on the fly: s = 0 keeps z[n] + z[n+256] (even bins), s = 1 keeps
+//              (z[n] - z[n+256]) * W_512^n (odd bins).  DC removal and the window are applied while loading.
+//   256-point: each half-warp runs its own 256-point FFT as two in-register radix-16 butterflies (fft16.cuh) with a
+//              16 x 16 transpose through a warp-private shared-memory tile in between.
+//   split    : bins k and 1024/2 - k share the pair (Z[k], Z[512-k]): X[k] = E + W_1024^k O and
+//              |X[512-k]| = |E - W_1024^k O|, so every lane converts 16 bins to dB / u16 from 8 pair loads.
+//
+// Algorithmic bytes per frame: hop * 4 read + 513 * 2 written (3074 B at hop 512).
+#include "device_math.cuh"
+#include "fft16.cuh"
+#include "stft.h"
+
+#include <cstdlib>
+
+namespace omb {
+
+namespace {
+
+using namespace f16;
+
+constexpr int kN = 1024, kM = 512, kWarps = 8, kTile = 16 * 17 * 2;  // two padded 16 x 16 tiles >= 512 bins
+
+struct SmemC {
+  float2 w1024[512];      // W_1024^k
+  float2 w512[256];       // W_512^n
+  float2 tw2[15 * 16];    // W_256^{r q}, [(q - 1) * 16 + r]
+  float2 win2[512];       // (h[2n], h[2n+1])
+  float2 work[kWarps][kTile];
+};
+
+__device__ __forceinline__ unsigned short to_code(float power) { return pack_classic_db_dev(power_to_db_dev(power, kDbFloor)); }
+
+__global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs a) {
+  OMB_DYN_SMEM(unsigned char, raw);
+  SmemC& sm = *reinterpret_cast<SmemC*>(raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 512; i += kWarps * 32) {
+    sm.w1024[i] = __ldg(&a.tw_fft[i]);
+    sm.win2[i] = make_float2(__ldg(&a.win[2 * i]), __ldg(&a.win[2 * i + 1]));
+  }
+  for (int i = tid; i < 256; i += kWarps * 32) sm.w512[i] = __ldg(&a.tw_fft[2 * i]);
+  for (int i = tid; i < 240; i += kWarps * 32) {
+    const int idx = 4 * (i / 16 + 1) * (i % 16);  // W_256^{rq} = W_1024^{4rq}; the table holds the upper half circle only
+    float2 w = __ldg(&a.tw_fft[idx & 511]);
+    if (idx >= 512) w = make_float2(-w.x, -w.y);
+    sm.tw2[i] = w;
+  }
+  __syncthreads();
+
+  const int s = lane >> 4, r = lane & 15;
+  float2* work = sm.work[warp];
+  float2* tile = work + s * (16 * 17);
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  const uint64_t total = per_lane * a.n_lanes;
+  const uint64_t stride_items = (uint64_t)gridDim.x * kWarps;
+  const float norm_edge = __ldg(&a.bin_norm[0]), norm_mid = __ldg(&a.bin_norm[1]);
+
+  for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < total; item += stride_items) {
+    const uint64_t lane_idx = item / per_lane, frame = a.first_frame + item % per_lane;
+    const float2* x2 = reinterpret_cast<const float2*>(a.lanes + lane_idx * a.lane_stride + frame * a.hop);
+
+    // mean of the frame (window.rs:76-79)
+    float part = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 v = __ldg(&x2[lane + 32 * i]);
+      part += v.x + v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float mean = part / (float)kN;
+
+    float2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = r + 16 * j;
+      const float2 xa = __ldg(&x2[n]), xb = __ldg(&x2[n + 256]);
+      const float2 wa = sm.win2[n], wb = sm.win2[n + 256];
+      const float2 va = make_float2((xa.x - mean) * wa.x, (xa.y - mean) * wa.y);
+      const float2 vb = make_float2((xb.x - mean) * wb.x, (xb.y - mean) * wb.y);
+      const float2 d = s ? csub2(va, vb) : cadd2(va, vb);
+      const float2 w = s ? sm.w512[n] : make_float2(1.0f, 0.0f);
+      v[j] = mul_tw<false>(d, w);
+    }
+    dft16<false>(v);  // over j: A[r][q]
+    tile[r] = v[0];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) tile[q * 17 + r] = mul_tw<false>(v[q], sm.tw2[(q - 1) * 16 + r]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tile[r * 17 + i];  // lane q = r collects A'[0..15][q]
+    dft16<false>(v);                                         // over r: Z_s[q + 16 p]
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 16; ++p) work[2 * (r + 16 * p) + s] = v[p];  // Z[2 k' + s]
+    __syncwarp();
+
+    uint16_t* out = a.out_classic + (lane_idx * a.frames_per_lane + frame) * (uint64_t)(kM + 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = lane + 32 * i;  // 0..255, partner bin 512 - k
+      const float2 zk = work[k], zm = work[(kM - k) & (kM - 1)];
+      const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+      const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));  // (zk - conj zm) / (2j)
+      const float2 T = cmul(sm.w1024[k], O);
+      const float2 Xk = cadd(E, T), Xm = csub(E, T);  // |X[512-k]| = |conj(E - T)|
+      const float nk = k == 0 ? norm_edge : norm_mid;
+      out[k] = to_code((Xk.x * Xk.x + Xk.y * Xk.y) * nk);
+      out[kM - k] = to_code((Xm.x * Xm.x + Xm.y * Xm.y) * nk);
+    }
+    if (lane == 0) {  // bin 256 pairs with itself: X = conj(Z[256])
+      const float2 z = work[256];
+      out[256] = to_code((z.x * z.x + z.y * z.y) * norm_mid);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+bool stft_classic_fast_supported(const StftConfig& cfg, const DeviceInfo& dev) {
+  if (cfg.reassign || cfg.window != (uint64_t)kN || cfg.zero_pad != 1 || (cfg.hop & 1)) return false;
+  if (getenv("OMB_NO_CLASSIC_FAST")) return false;
+  return dev.max_smem_optin == 0 || sizeof(SmemC) <= (size_t)dev.max_smem_optin;
+}
+
+int stft_classic_fast_prepare(StftPlan&) {
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_classic_1024, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemC)));
+  return OMB_OK;
+}
+
+int launch_stft_classic_fast(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
+  const uint64_t total = (a.frames_per_lane - a.first_frame) * a.n_lanes;
+  if (!total) return OMB_OK;
+  const uint64_t want = (total + kWarps - 1) / kWarps;
+  const int grid = (int)std::min<uint64_t>(want, (uint64_t)std::max(plan.dev.sm_count, 1) * 4);
+  OMB_LAUNCH(k_classic_1024, dim3(grid), dim3(kWarps * 32), sizeof(SmemC), s, a);
+  return OMB_OK;
+}
+
+}  // namespace omb

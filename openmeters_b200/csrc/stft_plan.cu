@@ -80,6 +80,10 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
       OMB_TRY(stft_fast2_prepare(*this));
       fast_kind = 2;
     }
+  } else if (choice != OMB_KERNEL_GENERIC && stft_classic_fast_supported(cfg, dev)) {
+    OMB_TRY(stft_classic_fast_prepare(*this));
+    fast = true;
+    fast_kind = 3;
   } else if (choice == OMB_KERNEL_FAST) {
     return fail(OMB_ERR_UNSUPPORTED, "no specialised kernel for window %llu hop %llu zp %llu reassign %d",
                 (unsigned long long)N, (unsigned long long)cfg.hop, (unsigned long long)cfg.zero_pad, (int)cfg.reassign);
@@ -139,9 +143,11 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   a.out_counts = out_counts;
   a.out_classic = out_classic;
   const bool aligned16 = (reinterpret_cast<uintptr_t>(d_lanes) & 15u) == 0 && (lane_stride % 4) == 0;
-  if (fast && aligned16) return fast_kind == 2 ? launch_stft_fast2(*this, a, s) : launch_stft_fast(*this, a, s);
+  const bool aligned8 = (reinterpret_cast<uintptr_t>(d_lanes) & 7u) == 0 && (lane_stride % 2) == 0;
+  if (fast_kind == 3 && aligned8) return launch_stft_classic_fast(*this, a, s);
+  if (fast && fast_kind != 3 && aligned16) return fast_kind == 2 ? launch_stft_fast2(*this, a, s) : launch_stft_fast(*this, a, s);
   if (fast && kernel_choice == OMB_KERNEL_FAST)
-    return fail(OMB_ERR_INVALID, "OMB_KERNEL_FAST was forced but the lanes are not 16-byte aligned (pointer and lane_stride % 4 == 0)");
+    return fail(OMB_ERR_INVALID, "OMB_KERNEL_FAST was forced but the lanes are not aligned (reassigned: 16 bytes and lane_stride % 4 == 0; classic: 8 bytes and lane_stride % 2 == 0)");
   if (smem_kernel) return launch_stft_smem(*this, a, s, d_scratch);
   return launch_stft_generic(*this, a, s, d_scratch);
 }

@@ -309,6 +309,14 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int
   return omb_emu_shfl(v, (src >= 0 && src / width == lane / width) ? src : lane);
 }
 
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {  // REDUX.MAX.U32
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned other = __shfl_xor_sync(mask, v, o);
+    v = other > v ? other : v;
+  }
+  return v;
+}
+
 using std::isfinite;
 using std::isinf;
 using std::isnan;

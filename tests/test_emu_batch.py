@@ -121,3 +121,13 @@ def test_host_path_ragged_lane_length(emu):
     assert st["cols"] == 15
     st = cases.stft_parity(emu.api, cfg, lanes[:2], kernel=capi.KERNEL_FAST, expect_fast=True)  # non-pipelined branch
     assert st["cols"] == 6
+
+
+def test_classic_warp_kernel_1024(emu):
+    """stft_classic_fast.cu (cfg1: N = 1024 classic, one warp per frame) vs the oracle; several hops, a DC offset
+    (exercises the mean removal) and more frames than one pass of the persistent grid covers per warp."""
+    for hop, win in ((512, capi.WINDOW_HANN), (256, capi.WINDOW_BLACKMAN_HARRIS), (1536, capi.WINDOW_HAMMING)):
+        cfg = SpectrogramConfig(fft_size=1024, hop_size=hop, window=win, use_reassignment=False)
+        lanes = synth.cfg1_stereo(0.4).reshape(-1, 2).T if hop == 512 else synth.cfg2_lanes(3, 0.25) + np.float32(0.125)
+        st = cases.stft_parity(emu.api, cfg, np.ascontiguousarray(lanes, np.float32), kernel=capi.KERNEL_FAST, expect_fast=True)
+        assert st["exact"] >= 0.98, st
