@@ -50,7 +50,9 @@ struct Addr {
 };
 
 // DIF forward: v holds elements t + 256 j (access A). On return v[j] = X[t + 256 j] (only the kPrune subset).
-template <int kPrune, int kTw2>
+// kLocal3: pass 3 stays inside the half-warp that ran pass 2 (ad.pC = 273 (t >> 4) + 17 (t & 15)): only a warp-level
+// sync separates the two passes, and thread t ends up with bins tf + 256 j, tf = (t >> 4) + 16 (t & 15).
+template <int kPrune, int kTw2, bool kLocal3 = false>
 __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const float2* tw1t, const float2* tw2o, const Addr& ad, int g) {
   f16::dft16<false>(v);
   twiddle15<false, 1, true>(v, tw1t, kT);

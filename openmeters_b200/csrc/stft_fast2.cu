@@ -87,11 +87,14 @@ __device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const flo
 }
 
 // kVariant bit 0: pass-2 twiddles computed from 4 loads (kTw2 = 1) instead of 15 table loads.
+// kVariant bit 1: the F and I transforms keep their 256-point sub-transforms inside one half-warp (no group barrier
+// between passes 2 and 3 / 1 and 2): frequency-domain ownership becomes tf + 256 j, tf = (t >> 4) + 16 (t & 15).
 // (Pass-1 twiddles are always computed from the 4 rows kept in shared memory: measured fastest, and the 22 KB
 // saved pay for the power-of-two ring.)
 template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
   constexpr int kTw2 = kVariant & 1;
+  constexpr bool kLocal = (kVariant & 2) != 0;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
   float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
@@ -121,13 +124,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   ad.pC = 273 * (t & 15) + 17 * (t >> 4);
   const float2* tw1t = sm.tw1 + t;
   const float2* tw2o = sm.tw2 + (t & 15);
-  float cos_t, sin_t;  // th_t = 2 pi t / H
+  const int tf = kLocal ? (t >> 4) + 16 * (t & 15) : t;  // this thread's bins between F and I: tf + 256 j
+  Addr adf = ad;
+  adf.pC = 273 * (tf & 15) + 17 * (tf >> 4);
+  float cos_t, sin_t;  // th_tf = 2 pi tf / H
   {
-    sincospif((float)t / (float)kM, &sin_t, &cos_t);  // th_t = 2 pi t / 8192 = pi * (t / 4096); one-off per thread
+    sincospif((float)tf / (float)kM, &sin_t, &cos_t);  // 2 pi tf / 8192 = pi * (tf / 4096); one-off per thread
   }
   const float sign = (t & 1) ? -1.0f : 1.0f;
   const float ramp0 = (float)t - (float)(kM - 1) * 0.5f;  // n - (N-1)/2 at j = 0
-  const int pt = (kT - t) & (kT - 1);
+  const int pt = (kT - tf) & (kT - 1);
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
   __syncthreads();
 
@@ -161,9 +167,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         // ring position of sample s is s & mask; (r0 + 512 j) & mask is warp-uniform, 2t < 512 never carries
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(ring + ((r0 + 2 * kT * j) & ring_mask) + 2 * t);
-        fft_forward<f16::kAll, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
+        fft_forward<f16::kAll, kTw2, kLocal>(v, gs.W, tw1t, tw2o, adf, g);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) gs.W[ad.pC + q] = v[q];
+        for (int q = 0; q < 16; ++q) gs.W[adf.pC + q] = v[q];
         if (t == 0) {
           gs.x0_xm[0] = v[0].x + v[0].y;
           gs.x0_xm[1] = v[0].x - v[0].y;
@@ -194,10 +200,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         // ---- I: inverse, DIT, thread t holds Q[t + 256 j]; result y -> gs.Y
         {
           f16::dft16<true>(v);
-          float2* wc = gs.W + ad.pC;
+          float2* wc = gs.W + adf.pC;
 #pragma unroll
           for (int q = 0; q < 16; ++q) wc[q] = v[q];
-          group_sync(g);
+          if (kLocal) __syncwarp(); else group_sync(g);
           float2* wb = gs.W + ad.pB;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
@@ -309,11 +315,10 @@ bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev) {
 }
 
 int stft_fast2_prepare(StftPlan& plan) {
-  auto k0 = k_reassigned_fast2<0>;
-  auto k1 = k_reassigned_fast2<1>;
   const int smem = (int)smem_bytes(plan.cfg.hop);
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
 }
 
@@ -336,14 +341,14 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
-  static const int variant = [] { const char* e = getenv("OMB_FAST2_VARIANT"); return e ? atoi(e) & 1 : 0; }();
-  auto k0 = k_reassigned_fast2<0>;
-  auto k1 = k_reassigned_fast2<1>;
+  static const int variant = [] { const char* e = getenv("OMB_FAST2_VARIANT"); return e ? atoi(e) & 3 : 2; }();
   const size_t smem = smem_bytes(a.hop);
   if (variant == 1) {
-    OMB_LAUNCH(k1, dim3(grid), dim3(kThreads), smem, s, fa);
+    OMB_LAUNCH(k_reassigned_fast2<1>, dim3(grid), dim3(kThreads), smem, s, fa);
+  } else if (variant >= 2) {
+    OMB_LAUNCH(k_reassigned_fast2<2>, dim3(grid), dim3(kThreads), smem, s, fa);
   } else {
-    OMB_LAUNCH(k0, dim3(grid), dim3(kThreads), smem, s, fa);
+    OMB_LAUNCH(k_reassigned_fast2<0>, dim3(grid), dim3(kThreads), smem, s, fa);
   }
   OMB_CHECK_LAUNCH();
   return OMB_OK;

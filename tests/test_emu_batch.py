@@ -131,3 +131,13 @@ def test_classic_warp_kernel_1024(emu):
         lanes = synth.cfg1_stereo(0.4).reshape(-1, 2).T if hop == 512 else synth.cfg2_lanes(3, 0.25) + np.float32(0.125)
         st = cases.stft_parity(emu.api, cfg, np.ascontiguousarray(lanes, np.float32), kernel=capi.KERNEL_FAST, expect_fast=True)
         assert st["exact"] >= 0.98, st
+
+
+def test_specialised_reassigned_kernel_8192(emu):
+    """stft_fast8k.cu (cfg5: N = 8192, two 4096-point sub-transforms per CTA) vs the oracle: several hops, a run
+    split across CTAs, ring wrap-around (more frames than the ring holds hops)."""
+    for hop, win, frames, nl in ((2048, capi.WINDOW_BLACKMAN_HARRIS, 21, 2), (512, capi.WINDOW_HANN, 5, 1), (1536, capi.WINDOW_BLACKMAN, 13, 1)):
+        cfg = SpectrogramConfig(sample_rate=96000.0, fft_size=8192, hop_size=hop, window=win, use_reassignment=True)
+        lanes = synth.cfg5_lanes(nl, 16384 + (frames - 1) * hop)
+        st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+        assert st["cols"] == nl * frames and st["unmatched"] <= 4, st

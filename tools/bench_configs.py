@@ -38,66 +38,74 @@ def tile_lanes(base: np.ndarray, n: int) -> np.ndarray:
 
 
 def main():
+    only = None
+    if "--only" in sys.argv:  # e.g. --only cfg5 (one config: short enough to run under ncu)
+        only = sys.argv[sys.argv.index("--only") + 1].split(",")
+    want = lambda name: only is None or name in only
     api = lib_api()
     api.set_device(0)
     dev = torch.device("cuda", 0)
     st = torch.cuda.current_stream(dev).cuda_stream
     res = {}
 
-    # cfg1: classic 1024/512 Hann
-    cfg = SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False)
-    L, S = 256, 1 << 18
-    lanes = torch.from_numpy(tile_lanes(synth.cfg2_lanes(8, S / 48000.0)[:, :S], L)).to(dev)
-    plan = batch.StftPlan(cfg, api=api)
-    F = plan.frames_per_lane(S)
-    out = torch.empty((L * F, plan.bins), dtype=torch.int16, device=dev)
-    t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, classic_ptr=out.data_ptr(), stream=st))
-    b = 512 * 4 + 513 * 2
-    res["cfg1_classic_1024_512"] = dict(frames_per_s=L * F / t, ms=t * 1e3, algorithmic_bytes_per_frame=b, achieved_gbs=L * F * b / t / 1e9,
-                                        hbm_frac=L * F * b / t / 1e9 / PEAK)
-    del plan, out, lanes
+    if want("cfg1"):
+        # cfg1: classic 1024/512 Hann
+        cfg = SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False)
+        L, S = 256, 1 << 18
+        lanes = torch.from_numpy(tile_lanes(synth.cfg2_lanes(8, S / 48000.0)[:, :S], L)).to(dev)
+        plan = batch.StftPlan(cfg, api=api)
+        F = plan.frames_per_lane(S)
+        out = torch.empty((L * F, plan.bins), dtype=torch.int16, device=dev)
+        t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, classic_ptr=out.data_ptr(), stream=st))
+        b = 512 * 4 + 513 * 2
+        res["cfg1_classic_1024_512"] = dict(frames_per_s=L * F / t, ms=t * 1e3, algorithmic_bytes_per_frame=b, achieved_gbs=L * F * b / t / 1e9,
+                                            hbm_frac=L * F * b / t / 1e9 / PEAK)
+        del plan, out, lanes
 
-    # cfg5: reassigned 8192/2048 BH @96k
-    cfg = SpectrogramConfig(sample_rate=96000.0, fft_size=8192, hop_size=2048, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
-    L, S = 32, 1 << 20
-    lanes = torch.from_numpy(tile_lanes(synth.cfg5_lanes(8, S), L)).to(dev)
-    plan = batch.StftPlan(cfg, api=api)
-    F = plan.frames_per_lane(S)
-    pts = torch.empty((L * F, plan.bins, 3), dtype=torch.float32, device=dev)
-    cnt = torch.empty((L * F,), dtype=torch.int32, device=dev)
-    t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, pts.data_ptr(), plan.bins, cnt.data_ptr(), stream=st), iters=5)
-    b = 2048 * 4 + 4097 * 12 + 4
-    res["cfg5_reassigned_8192_2048"] = dict(frames_per_s=L * F / t, ms=t * 1e3, algorithmic_bytes_per_frame=b, achieved_gbs=L * F * b / t / 1e9,
-                                            hbm_frac=L * F * b / t / 1e9 / PEAK, kernel_generation=plan.kernel_generation)
-    del plan, pts, cnt, lanes
+    if want("cfg5"):
+        # cfg5: reassigned 8192/2048 BH @96k
+        cfg = SpectrogramConfig(sample_rate=96000.0, fft_size=8192, hop_size=2048, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+        L, S = 32, 1 << 20
+        lanes = torch.from_numpy(tile_lanes(synth.cfg5_lanes(8, S), L)).to(dev)
+        plan = batch.StftPlan(cfg, api=api)
+        F = plan.frames_per_lane(S)
+        pts = torch.empty((L * F, plan.bins, 3), dtype=torch.float32, device=dev)
+        cnt = torch.empty((L * F,), dtype=torch.int32, device=dev)
+        t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, pts.data_ptr(), plan.bins, cnt.data_ptr(), stream=st), iters=5)
+        b = 2048 * 4 + 4097 * 12 + 4
+        res["cfg5_reassigned_8192_2048"] = dict(frames_per_s=L * F / t, ms=t * 1e3, algorithmic_bytes_per_frame=b, achieved_gbs=L * F * b / t / 1e9,
+                                                hbm_frac=L * F * b / t / 1e9 / PEAK, kernel_generation=plan.kernel_generation)
+        del plan, pts, cnt, lanes
 
-    # cfg4: spectrum 16384/1024 Hann, PeakHold 12 dB/s, 128 lanes
-    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0, floor_db=-100.0)
-    L, S = 128, 480000
-    lanes = torch.from_numpy(tile_lanes(synth.cfg4_streams(4, S / 48000.0).reshape(8, -1)[:, :S], L)).to(dev)
-    plan = batch.SpectrumPlan(cfg, api=api)
-    Hh = plan.hops_per_lane(S)
-    w = torch.empty((L * Hh, plan.bins), dtype=torch.float32, device=dev)
-    r = torch.empty_like(w)
-    pk = torch.empty((L * Hh,), dtype=torch.int32, device=dev)
-    t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, w.data_ptr(), r.data_ptr(), pk.data_ptr(), stream=st), iters=5)
-    b = 1024 * 4 + 2 * 8193 * 4
-    res["cfg4_spectrum_16384_1024"] = dict(lane_hops_per_s=L * Hh / t, ms=t * 1e3, algorithmic_bytes_per_lane_hop=b, achieved_gbs=L * Hh * b / t / 1e9,
-                                           hbm_frac=L * Hh * b / t / 1e9 / PEAK)
-    del plan, w, r, pk, lanes
+    if want("cfg4"):
+        # cfg4: spectrum 16384/1024 Hann, PeakHold 12 dB/s, 128 lanes
+        cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0, floor_db=-100.0)
+        L, S = 128, 480000
+        lanes = torch.from_numpy(tile_lanes(synth.cfg4_streams(4, S / 48000.0).reshape(8, -1)[:, :S], L)).to(dev)
+        plan = batch.SpectrumPlan(cfg, api=api)
+        Hh = plan.hops_per_lane(S)
+        w = torch.empty((L * Hh, plan.bins), dtype=torch.float32, device=dev)
+        r = torch.empty_like(w)
+        pk = torch.empty((L * Hh,), dtype=torch.int32, device=dev)
+        t = timed(lambda: plan.execute_device(lanes.data_ptr(), L, S, S, w.data_ptr(), r.data_ptr(), pk.data_ptr(), stream=st), iters=5)
+        b = 1024 * 4 + 2 * 8193 * 4
+        res["cfg4_spectrum_16384_1024"] = dict(lane_hops_per_s=L * Hh / t, ms=t * 1e3, algorithmic_bytes_per_lane_hop=b, achieved_gbs=L * Hh * b / t / 1e9,
+                                               hbm_frac=L * Hh * b / t / 1e9 / PEAK)
+        del plan, w, r, pk, lanes
 
-    # cfg3: loudness 8 ch 48 kHz, 16 streams x 30 s, snapshot every 1024 frames
-    x = synth.cfg3_surround(30.0)
-    nS = 16
-    streams = torch.from_numpy(np.stack([x * np.float32(1.0 - 0.02 * i) for i in range(nS)])).to(dev)
-    plan = batch.LoudnessPlan(LoudnessConfig(), 8, capi.SURROUND, api=api)
-    frames = x.size // 8
-    nb = (frames + 1023) // 1024
-    snaps = torch.empty((nS * nb, 116 // 4), dtype=torch.float32, device=dev)
-    assert snaps.element_size() * snaps.shape[1] == 116
-    t = timed(lambda: plan.execute_device(streams.data_ptr(), nS, frames, frames * 8, 1024, snaps.data_ptr(), stream=st), iters=5)
-    res["cfg3_loudness_8ch"] = dict(sample_channels_per_s=nS * frames * 8 / t, ms=t * 1e3, algorithmic_bytes_per_sample_channel=4,
-                                    achieved_gbs=nS * frames * 8 * 4 / t / 1e9, hbm_frac=nS * frames * 8 * 4 / t / 1e9 / PEAK)
+    if want("cfg3"):
+        # cfg3: loudness 8 ch 48 kHz, 16 streams x 30 s, snapshot every 1024 frames
+        x = synth.cfg3_surround(30.0)
+        nS = 16
+        streams = torch.from_numpy(np.stack([x * np.float32(1.0 - 0.02 * i) for i in range(nS)])).to(dev)
+        plan = batch.LoudnessPlan(LoudnessConfig(), 8, capi.SURROUND, api=api)
+        frames = x.size // 8
+        nb = (frames + 1023) // 1024
+        snaps = torch.empty((nS * nb, 116 // 4), dtype=torch.float32, device=dev)
+        assert snaps.element_size() * snaps.shape[1] == 116
+        t = timed(lambda: plan.execute_device(streams.data_ptr(), nS, frames, frames * 8, 1024, snaps.data_ptr(), stream=st), iters=5)
+        res["cfg3_loudness_8ch"] = dict(sample_channels_per_s=nS * frames * 8 / t, ms=t * 1e3, algorithmic_bytes_per_sample_channel=4,
+                                        achieved_gbs=nS * frames * 8 * 4 / t / 1e9, hbm_frac=nS * frames * 8 * 4 / t / 1e9 / PEAK)
     print(json.dumps(res))
 
 
