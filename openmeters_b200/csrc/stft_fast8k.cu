@@ -41,6 +41,7 @@ constexpr int kWarps = kT / 32;          // warps per group
 constexpr int kWSize = f16::phys_size(kSub);
 constexpr int kBinGroups = 9;            // a = t + 256 j, j < 8, and a = 2048 (group 0, t = 0, j = 8)
 constexpr int kCntN = kBinGroups * kWarps;
+constexpr int kDhSmem = 2816;            // dh[0 .. kDhSmem) lives in the shared memory left over; the rest stays L1-resident
 
 struct Fast8kArgs {
   StftKernelArgs a;
@@ -60,6 +61,7 @@ struct Smem8k {
   int offs[kCntN + 1];
   float x0_xm[2];
   int pad_[1];
+  float dh_lo[kDhSmem];
   // float ring[ring_len] follows
 };
 static_assert(sizeof(Smem8k) % 16 == 0, "ring must stay 16-byte aligned");
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
   }
   for (int i = tid; i < 15 * 16; i += kThreads) sm.tw2[i] = __ldg(&fa.tw2[i]);
   for (int i = tid; i < kN8; i += kThreads) sm.h[i] = __ldg(&a.win[i]);
+  for (int i = tid; i < kDhSmem; i += kThreads) sm.dh_lo[i] = __ldg(&a.dwin[i]);
   Addr ad;
   ad.pA = t + (t >> 4);
   ad.pB = 273 * (t >> 4) + (t & 15);
@@ -148,12 +151,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
       if (f + 1 < f_end) ring_fetch(ring, L, wrap(r0 + H, L), x + f * (uint64_t)hop + (uint64_t)H, hop);  // the one free slot
       async_commit();
 
+      // The frame occupies ring positions [r0, r0 + H) mod L: offsets below `split` are reached from lo, the rest
+      // from hi = lo - L (split is a multiple of 512, so a 512-sample block never straddles the wrap).
+      const float* lo = ring + r0;
+      const float* hi = lo - L;
+      const int split = L - r0;
       float2 v[16];
       // ---- F: z[n] = x[2n] + j x[2n+1]; group 0: z[n] + z[n+4096], group 1: (z[n] - z[n+4096]) W_8192^n, n = t + 256 j
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float2 za = *reinterpret_cast<const float2*>(ring + wrap(r0 + 512 * j, L) + 2 * t);
-        const float2 zb = *reinterpret_cast<const float2*>(ring + wrap(r0 + 512 * j + kN8, L) + 2 * t);
+        const float2 za = *reinterpret_cast<const float2*>((512 * j < split ? lo : hi) + 512 * j + 2 * t);
+        const float2 zb = *reinterpret_cast<const float2*>((512 * j + kN8 < split ? lo : hi) + 512 * j + kN8 + 2 * t);
         if (g == 0) {
           v[j] = f16::cadd2(za, zb);
         } else {
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
           const int n = kT * j;  // + t
           float wa_, wb_;
           if (wsel == 1) {
-            wa_ = __ldg(dwin + n);
+            wa_ = (n + kT <= kDhSmem) ? sm.dh_lo[t + n] : __ldg(dwin + n);
             wb_ = __ldg(dwin + n + kSub);
           } else {
             wa_ = sm.h[t + n];
@@ -258,8 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
             wa_ *= ramp0 + (float)n;
             wb_ *= ramp0 + (float)(n + kSub);
           }
-          const float xa = fmaf((float)kN8, ring[wrap(r0 + off + n, L) + t], bias);
-          const float xb = fmaf((float)kN8, ring[wrap(r0 + off + n + kSub, L) + t], bias);
+          const float xa = fmaf((float)kN8, ((off + n < split ? lo : hi) + off + n)[t], bias);
+          const float xb = fmaf((float)kN8, ((off + n + kSub < split ? lo : hi) + off + n + kSub)[t], bias);
           const float2 ca = make_float2(xa * wa_, sm.Y[t + n] * wa_);
           const float2 cb = make_float2(xb * wb_, sm.Y[t + n + kSub] * wb_);
           if (g == 0) {
