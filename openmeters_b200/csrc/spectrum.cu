@@ -345,6 +345,16 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
   if (!hops || !n_lanes) return OMB_OK;
   if (!d_lanes || !d_weighted || !d_raw) return fail(OMB_ERR_INVALID, "null argument");
   const uint64_t bins = cfg.bins();
+  // Enough lanes to fill the GPU with one CTA per lane: the fused kernel (power spectrum never leaves the SM).
+  // OMB_SPECTRUM_FUSED=0/1 pins the choice (measurement / cross-checks).
+  {
+    const char* e = getenv("OMB_SPECTRUM_FUSED");
+    const int pin = e ? atoi(e) : -1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_lanes) & 15u) == 0 && (lane_stride % 4) == 0;
+    const bool enough = (uint64_t)n_lanes * 2 >= (uint64_t)std::max(dev.sm_count, 1);
+    if (fast16k && fused16k && aligned && pin != 0 && (enough || pin == 1))
+      return launch_spectrum_fused(*this, d_lanes, n_lanes, hops, lane_stride, d_weighted, d_raw, d_peak_bin, s);
+  }
   // chunk of hops whose power scratch (n_lanes*chunk*bins*4 B) stays comfortably inside the 126 MB L2
   const uint64_t budget_floats = (64ull << 20) / 4;
   uint64_t chunk = std::max<uint64_t>(1, budget_floats / std::max<uint64_t>(1, (uint64_t)n_lanes * bins));

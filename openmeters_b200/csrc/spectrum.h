@@ -63,6 +63,8 @@ struct SpectrumPlan {
   bool fast16k = false;                 // spectrum_fast.cu applies (N = 16384)
   DeviceBuffer<float2> d_fast_tables;
   DeviceBuffer<double> d_bsum;
+  bool fused16k = false;                // whole-batch fused kernel available (spectrum_fast.cu, k_spectrum_fused_16k)
+  DeviceBuffer<float> d_means;
   uint64_t ext_bsum_blocks = 0;         // > 0: d_bsum already holds [lane][ext_bsum_blocks] sums for the whole batch
   uint64_t ext_block_off = 0;           //      and this launch starts at that block
   // host-path staging
@@ -87,6 +89,8 @@ struct SpectrumPlan {
 bool spectrum_fast_supported(const SpectrumConfigN& cfg, const DeviceInfo& dev);
 int spectrum_fast_prepare(SpectrumPlan& p);
 int launch_spectrum_power_fast(SpectrumPlan& p, SpectrumPowerArgs& a, cudaStream_t s);
+int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lanes, uint64_t hops, uint64_t lane_stride, float* d_weighted,
+                          float* d_raw, int32_t* d_peak_bin, cudaStream_t s);
 int spectrum_fast_block_sums(SpectrumPlan& p, const float* d_lanes, uint64_t lane_stride, uint32_t n_lanes, uint64_t hops, cudaStream_t s);
 
 }  // namespace omb

@@ -9,6 +9,9 @@
 //     X[k] = A + W_16384^k B,  X[8192-k] = conj(A - W_16384^k B),  A = (P + conj Q)/2, B = (P - conj Q)/(2j)
 // DC removal uses per-hop f64 block sums from a small pre-kernel (mean = sum of N/hop block sums / N), so the PCM is
 // read once by the FFT kernel.  Rows a4, a12 of SURVEY.md §8; spectrum/processor.rs:215-244.
+#include <algorithm>
+#include <cmath>
+
 #include "fft4096.cuh"
 #include "spectrum.h"
 
@@ -142,6 +145,272 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_power_16k(SpecFastArgs
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused batch kernel: one CTA walks ALL hops of one lane.  The N samples of a frame live in a shared-memory ring
+// of N + hop floats (the next hop arrives by 16-byte async copies while the current one is transformed), the window
+// is shared-memory resident, and the smoothing recurrence (spectrum/processor.rs:349-402) runs in the FFT epilogue
+// with its state in registers: every thread owns the same <= 18 bins for the whole lane, so the power spectrum
+// never leaves the SM and the per-hop outputs [weighted, raw] are written exactly once (69 640 algorithmic bytes
+// per lane-hop, no scratch round trip, no second kernel).  The arg-max (state.rs:321-325, last maximum wins) is a
+// CTA reduction instead of global atomics.  Parallelism is one CTA per lane, so the plan uses this kernel only when
+// there are enough lanes to fill the GPU; the two-kernel path above remains for few lanes and for streaming.
+constexpr int kSlots = 4;                      // aa = tid + 512 i, i < 4 -> bins aa, 8192 - aa, 4096 - aa, 4096 + aa
+
+struct SpecFusedArgs {
+  SpectrumPowerArgs a;                         // lanes / lane_stride / n_lanes / hops / hop / win
+  const float2* tw1;
+  const float2* tw2;
+  const float* means;                          // [lane][hops] frame means (f64 block sums -> f32), see k_frame_means
+  const float* a_db;                           // [8193]
+  float* out_weighted;                         // [(lane * hops + h) * 8193 + k]
+  float* out_raw;
+  int32_t* peak_bin;                           // [lane * hops + h] or null
+  int mode;
+  float alpha, decay, state_floor, floor_db;
+  float norm_ac, norm_dc;
+  uint32_t ring_len;
+};
+
+struct SmemF {
+  float2 W[2][kWSize];
+  float2 tw1[4 * kT];
+  float2 tw2[15 * 16];
+  float win[kN];
+  float adb_lo[kM + 4];                        // A-weights of bins 0..4096 (the upper half sits in registers)
+  unsigned long long wkey[2][kThreads / 32];   // per-warp arg-max keys, double-buffered by hop parity
+  // float ring[ring_len] follows
+};
+static_assert(sizeof(SmemF) % 16 == 0, "ring must stay 16-byte aligned");
+
+__global__ void k_frame_means(const double* bsum, uint64_t n_blocks, uint64_t hops, uint32_t n_lanes, uint32_t blocks_per_frame,
+                              float* means) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hops * n_lanes) return;
+  const uint64_t lane = i / hops, h = i % hops;
+  const double* bs = bsum + lane * n_blocks + h;
+  double s = 0.0;
+  for (uint32_t b = 0; b < blocks_per_frame; ++b) s += bs[b];
+  means[i] = (float)(s / (double)kN);
+}
+
+__device__ __forceinline__ void f_async_copy16(float* dst_smem, const float* src_gmem) {
+#ifdef OMB_EMU
+  for (int i = 0; i < 4; ++i) dst_smem[i] = src_gmem[i];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem));
+#endif
+}
+__device__ __forceinline__ void f_async_commit_wait(bool wait) {
+#ifndef OMB_EMU
+  if (wait) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  else asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+__device__ __forceinline__ void f_ring_fetch(float* ring, int L, int p0, const float* x, int count) {
+  for (int i = 4 * (int)threadIdx.x; i < count; i += 4 * kThreads) {
+    int p = p0 + i;
+    p -= (p >= L) ? L : 0;
+    f_async_copy16(ring + p, x + i);
+  }
+}
+
+__device__ __forceinline__ unsigned f_ordered_bits(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ln(v) from the special-function unit (MUFU.LG2 + one multiply; <= 3 ulp, CUDA __logf) — the epilogue is
+// issue-bound and the ~25-instruction accurate logf was its largest single item.  3 ulp of a dB value is <= 6e-6
+// relative in linear power (the parity budget is 1e-5); never used for the integer-coded classic columns.
+__device__ __forceinline__ float fast_ln(float v) {
+#ifdef OMB_EMU
+  return logf(v);
+#else
+  return __logf(v);
+#endif
+}
+
+// One smoothed bin: state update, dB, stores; folds the bin into the running arg-max (best ordered dB bits, its bin;
+// a later bin in ascending order wins ties, state.rs:321-325).  Branch-free apart from the uniform mode switch.
+template <int kMode>
+__device__ __forceinline__ void fused_bin(const SpecFusedArgs& fa, float p, float& st, int bin, float aw, float* ow, float* orw,
+                                          unsigned& best, unsigned& best_bin) {
+  float v = p;
+  if (kMode == OMB_AVG_EXPONENTIAL) {
+    st = st <= 0.0f ? p : __fadd_rn(__fmul_rn(st, fa.alpha), __fmul_rn(p, __fsub_rn(1.0f, fa.alpha)));
+    st = st < fa.state_floor ? 0.0f : st;
+    v = st;
+  } else if (kMode == OMB_AVG_PEAK_HOLD) {
+    st = fmaxf(__fmul_rn(st, fa.decay), p);
+    st = st < fa.state_floor ? 0.0f : st;
+    v = st;
+  }
+  const bool below = v < fa.state_floor;  // :392-401 (NaN powers take the dB path, as in the reference)
+  const float db = __fmul_rn(fast_ln(below ? 1.0f : v), kLnToDb);
+  const float raw = below ? fa.floor_db : fmaxf(db, fa.floor_db);
+  const float weighted = below ? fa.floor_db : fmaxf(__fadd_rn(db, aw), fa.floor_db);
+  ow[bin] = weighted;
+  orw[bin] = raw;
+  const bool interior = bin >= 1 && bin + 1 < kN / 2 + 1;
+  const unsigned ob = (interior && isfinite(raw)) ? f_ordered_bits(raw) : 0u;
+  const bool take = ob > best || (ob == best && (unsigned)bin > best_bin);
+  best = take ? ob : best;
+  best_bin = take ? (unsigned)bin : best_bin;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArgs fa) {
+  OMB_DYN_SMEM(unsigned char, smem_raw);
+  SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
+  float* ring = reinterpret_cast<float*>(smem_raw + sizeof(SmemF));
+  const SpectrumPowerArgs& a = fa.a;
+  const int tid = threadIdx.x, t = tid & (kT - 1), lane_id = tid & 31;
+  const int g = __shfl_sync(0xffffffffu, tid >> 8, 0);
+  const int hop = (int)a.hop, L = (int)fa.ring_len;
+  for (int i = tid; i < 4 * kT; i += kThreads) {
+    const int row = (1 << (i >> 8)) - 1;
+    sm.tw1[i] = __ldg(&fa.tw1[row * kT + (i & (kT - 1))]);
+  }
+  for (int i = tid; i < 15 * 16; i += kThreads) sm.tw2[i] = __ldg(&fa.tw2[i]);
+  for (int i = tid; i < kN; i += kThreads) sm.win[i] = __ldg(&a.win[i]);
+  for (int i = tid; i <= kM; i += kThreads) sm.adb_lo[i] = __ldg(&fa.a_db[i]);
+  float aw_hi[kSlots][2];  // A-weights of this thread's bins 8192 - aa and 4096 + aa
+#pragma unroll
+  for (int i = 0; i < kSlots; ++i) {
+    aw_hi[i][0] = __ldg(&fa.a_db[2 * kM - (tid + kThreads * i)]);
+    aw_hi[i][1] = __ldg(&fa.a_db[kM + tid + kThreads * i]);
+  }
+  const float aw_mid = __ldg(&fa.a_db[kM + kM / 2]);  // bin 6144 (thread 0's extra pair)
+  Addr ad;
+  ad.pA = t + (t >> 4);
+  ad.pB = 273 * (t >> 4) + (t & 15);
+  ad.pC = 273 * (t & 15) + 17 * (t >> 4);
+  const float2* tw1t = sm.tw1 + t;
+  const float2* tw2o = sm.tw2 + (t & 15);
+  float cw, sw;  // W_16384^tid = cw - j sw
+  sincospif((float)tid / (float)(kN / 2), &sw, &cw);
+  __syncthreads();
+
+  for (uint32_t lane = blockIdx.x; lane < a.n_lanes; lane += gridDim.x) {
+    const float* x = a.lanes + (uint64_t)lane * a.lane_stride;
+    const float* means = fa.means + (uint64_t)lane * a.hops;
+    float st[kSlots][4];
+    float st_mid[2] = {0.0f, 0.0f};  // bins 2048 and 6144 (aa = 2048), thread 0 only
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) st[i][b] = 0.0f;
+    int r0 = 0;
+    f_ring_fetch(ring, L, 0, x, kN);
+    f_async_commit_wait(false);
+    float mean_next = __ldg(&means[0]);
+    for (uint64_t h = 0; h < a.hops; ++h) {
+      f_async_commit_wait(true);
+      __syncthreads();  // ring holds frame h; everybody is done with frame h - 1 (ring, W, wkey[(h - 1) & 1] complete)
+      if (h + 1 < a.hops) {
+        int p0 = r0 + kN;
+        p0 -= (p0 >= L) ? L : 0;
+        f_ring_fetch(ring, L, p0, x + h * (uint64_t)hop + kN, hop);
+      }
+      f_async_commit_wait(false);
+      if (fa.peak_bin && h > 0 && tid == 0) {  // finish the previous hop's arg-max
+        unsigned long long best = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) best = sm.wkey[(h - 1) & 1][w] > best ? sm.wkey[(h - 1) & 1][w] : best;
+        fa.peak_bin[(uint64_t)lane * a.hops + h - 1] = best ? (int32_t)(best & 0xffffffffu) : -1;
+      }
+      const float mean = mean_next;
+      if (h + 1 < a.hops) mean_next = __ldg(&means[h + 1]);
+      const float* lo = ring + r0;
+      const float* hi = lo - L;
+      const int split = L - r0;  // multiple of 4 (hop % 4 == 0): a float2 at an even offset never straddles the wrap
+      // group g transforms z[2m + g], z[n] = (r[2n], r[2n+1]); thread t owns m = t + 256 j -> samples 4m + 2g, +1
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i0 = 4 * (t + kT * j) + 2 * g;
+        const float2 xv = *reinterpret_cast<const float2*>((i0 < split ? lo : hi) + i0);
+        const float2 wv = *reinterpret_cast<const float2*>(sm.win + i0);
+        v[j] = make_float2((xv.x - mean) * wv.x, (xv.y - mean) * wv.y);
+      }
+      fft_forward<f16::kAll, 0>(v, sm.W[g], tw1t, tw2o, ad, g);
+      float2* wc = sm.W[g] + ad.pC;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) wc[q] = v[q];
+      __syncthreads();
+      // epilogue: combine + real split + |X|^2 norm + smoothing + dB, four bins per (thread, slot)
+      float* ow = fa.out_weighted + ((uint64_t)lane * a.hops + h) * (uint64_t)(kN / 2 + 1);
+      float* orw = fa.out_raw + ((uint64_t)lane * a.hops + h) * (uint64_t)(kN / 2 + 1);
+      unsigned best = 0, best_bin = 0;
+#pragma unroll
+      for (int i = 0; i <= kSlots; ++i) {
+        const int aa = (i < kSlots) ? tid + kThreads * i : kM / 2;
+        if (i == kSlots && tid != 0) break;
+        const int bb = kM - aa;
+        const float2 Ea = sm.W[0][posC(aa)], Oa = sm.W[1][posC(aa)];
+        const float2 Eb = sm.W[0][posC(bb & (kM - 1))], Ob = sm.W[1][posC(bb & (kM - 1))];
+        // W_16384^aa = W_16384^tid * W_32^i (aa = 2048: W_8)
+        const float ci = (i < kSlots) ? f16::kCos32[i] : f16::kH, si = (i < kSlots) ? f16::kSin32[i] : f16::kH;
+        const float2 w = (i < kSlots) ? make_float2(cw * ci - sw * si, -(sw * ci + cw * si)) : make_float2(ci, -si);
+        const float2 w8 = cmul(w, w);
+        const float2 ta = cmul(w8, Oa);
+        const float2 tb = cmul(make_float2(-w8.x, w8.y), Ob);
+        const float2 Za = cadd(Ea, ta), Za2 = csub(Ea, ta);
+        const float2 Zb = cadd(Eb, tb), Zb2 = csub(Eb, tb);
+        float p0, p1, p2, p3;
+        {
+          const float2 A = make_float2(0.5f * (Za.x + Zb2.x), 0.5f * (Za.y - Zb2.y));
+          const float2 d = make_float2(Za.x - Zb2.x, Za.y + Zb2.y);
+          const float2 B = make_float2(0.5f * d.y, -0.5f * d.x);
+          const float2 T = cmul(w, B);
+          const float2 X0 = cadd(A, T), X1 = csub(A, T);
+          p0 = (X0.x * X0.x + X0.y * X0.y) * (aa == 0 ? fa.norm_dc : fa.norm_ac);   // bin aa
+          p1 = (X1.x * X1.x + X1.y * X1.y) * (aa == 0 ? fa.norm_dc : fa.norm_ac);   // bin 8192 - aa
+        }
+        {
+          const float2 A = make_float2(0.5f * (Zb.x + Za2.x), 0.5f * (Zb.y - Za2.y));
+          const float2 d = make_float2(Zb.x - Za2.x, Zb.y + Za2.y);
+          const float2 B = make_float2(0.5f * d.y, -0.5f * d.x);
+          const float2 wk = make_float2(-w.y, -w.x);
+          const float2 T = cmul(wk, B);
+          const float2 X0 = cadd(A, T), X1 = csub(A, T);
+          p2 = (X0.x * X0.x + X0.y * X0.y) * fa.norm_ac;                           // bin 4096 - aa
+          p3 = (X1.x * X1.x + X1.y * X1.y) * fa.norm_ac;                           // bin 4096 + aa
+        }
+        if (i < kSlots) {
+          fused_bin<kMode>(fa, p0, st[i][0], aa, sm.adb_lo[aa], ow, orw, best, best_bin);
+          fused_bin<kMode>(fa, p1, st[i][1], 2 * kM - aa, aw_hi[i][0], ow, orw, best, best_bin);
+          fused_bin<kMode>(fa, p2, st[i][2], bb, sm.adb_lo[bb], ow, orw, best, best_bin);
+          // aa = 0: bin 4096 a second time (the same bin from the mirrored pair, as in k_spectrum_power_16k where the
+          // later store wins too) — cheaper than a divergent branch for one thread
+          fused_bin<kMode>(fa, p3, st[i][3], kM + aa, aw_hi[i][1], ow, orw, best, best_bin);
+        } else {  // aa = 2048: the two pairs coincide (bins 2048 and 6144)
+          fused_bin<kMode>(fa, p0, st_mid[0], aa, sm.adb_lo[aa], ow, orw, best, best_bin);
+          fused_bin<kMode>(fa, p1, st_mid[1], 2 * kM - aa, aw_mid, ow, orw, best, best_bin);
+        }
+      }
+      if (fa.peak_bin) {
+        const unsigned hi32 = __reduce_max_sync(0xffffffffu, best);
+        const unsigned lo32 = __reduce_max_sync(0xffffffffu, (best == hi32) ? best_bin : 0u);
+        if (lane_id == 0) sm.wkey[h & 1][tid >> 5] = hi32 ? (((unsigned long long)hi32 << 32) | lo32) : 0ull;
+      }
+      r0 += hop;
+      r0 -= (r0 >= L) ? L : 0;
+    }
+    __syncthreads();
+    if (fa.peak_bin && a.hops > 0 && tid == 0) {
+      unsigned long long best = 0;
+      for (int w = 0; w < kThreads / 32; ++w) best = sm.wkey[(a.hops - 1) & 1][w] > best ? sm.wkey[(a.hops - 1) & 1][w] : best;
+      fa.peak_bin[(uint64_t)lane * a.hops + a.hops - 1] = best ? (int32_t)(best & 0xffffffffu) : -1;
+    }
+    __syncthreads();
+  }
+}
+
+size_t fused_smem_bytes(uint64_t hop) { return sizeof(SmemF) + (size_t)(kN + hop) * sizeof(float); }
+
 }  // namespace
 
 bool spectrum_fast_supported(const SpectrumConfigN& cfg, const DeviceInfo& dev) {
@@ -169,6 +438,60 @@ int spectrum_fast_prepare(SpectrumPlan& p) {
   }
   OMB_TRY(p.d_fast_tables.upload(tab, p.stream));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_spectrum_power_16k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
+  p.fused16k = false;
+  if ((p.cfg.hop % 4) == 0 && (p.dev.max_smem_optin == 0 || fused_smem_bytes(p.cfg.hop) <= (size_t)p.dev.max_smem_optin)) {
+    const int fs = (int)fused_smem_bytes(p.cfg.hop);
+    OMB_CUDA_TRY(cudaFuncSetAttribute(k_spectrum_fused_16k<OMB_AVG_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+    OMB_CUDA_TRY(cudaFuncSetAttribute(k_spectrum_fused_16k<OMB_AVG_EXPONENTIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+    OMB_CUDA_TRY(cudaFuncSetAttribute(k_spectrum_fused_16k<OMB_AVG_PEAK_HOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+    p.fused16k = true;
+  }
+  return OMB_OK;
+}
+
+// Whole-batch fused path (FFT + smoothing + dB + arg-max in one kernel, one CTA per lane). Zero initial state.
+int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lanes, uint64_t hops, uint64_t lane_stride, float* d_weighted,
+                          float* d_raw, int32_t* d_peak_bin, cudaStream_t s) {
+  if (!hops || !n_lanes) return OMB_OK;
+  const SpectrumConfigN& cfg = p.cfg;
+  OMB_TRY(spectrum_fast_block_sums(p, d_lanes, lane_stride, n_lanes, hops, s));
+  const uint64_t n_blocks = hops - 1 + (uint64_t)kN / cfg.hop;
+  OMB_TRY(p.d_means.reserve((size_t)(hops * n_lanes)));
+  OMB_LAUNCH(k_frame_means, dim3((unsigned)((hops * n_lanes + 255) / 256)), dim3(256), 0, s, p.d_bsum.ptr, n_blocks, hops, n_lanes,
+             (uint32_t)(kN / cfg.hop), p.d_means.ptr);
+  OMB_CHECK_LAUNCH();
+  SpecFusedArgs fa{};
+  fa.a.lanes = d_lanes;
+  fa.a.lane_stride = lane_stride;
+  fa.a.n_lanes = n_lanes;
+  fa.a.hops = hops;
+  fa.a.hop = (uint32_t)cfg.hop;
+  fa.a.win = p.d_win.ptr;
+  fa.tw1 = p.d_fast_tables.ptr;
+  fa.tw2 = fa.tw1 + 15 * kT;
+  fa.means = p.d_means.ptr;
+  fa.a_db = p.d_adb.ptr;
+  fa.out_weighted = d_weighted;
+  fa.out_raw = d_raw;
+  fa.peak_bin = d_peak_bin;
+  fa.mode = (int)cfg.averaging;
+  fa.alpha = std::min(std::max(cfg.averaging_param, 0.0f), 0.9999f);
+  fa.decay = db_to_power_host(-std::fmax(cfg.averaging_param, 0.0f) * ((float)cfg.hop / cfg.sample_rate));
+  fa.state_floor = p.state_floor;
+  fa.floor_db = cfg.floor_db;
+  fa.norm_ac = p.h_norm.size() > 1 ? p.h_norm[1] : p.h_norm[0];
+  fa.norm_dc = p.h_norm[0];
+  fa.ring_len = (uint32_t)(kN + cfg.hop);
+  const unsigned grid = (unsigned)std::min<uint64_t>(n_lanes, (uint64_t)std::max(p.dev.sm_count, 1));
+  const size_t fs = fused_smem_bytes(cfg.hop);
+  if (fa.mode == OMB_AVG_PEAK_HOLD) {
+    OMB_LAUNCH(k_spectrum_fused_16k<OMB_AVG_PEAK_HOLD>, dim3(grid), dim3(kThreads), fs, s, fa);
+  } else if (fa.mode == OMB_AVG_EXPONENTIAL) {
+    OMB_LAUNCH(k_spectrum_fused_16k<OMB_AVG_EXPONENTIAL>, dim3(grid), dim3(kThreads), fs, s, fa);
+  } else {
+    OMB_LAUNCH(k_spectrum_fused_16k<OMB_AVG_NONE>, dim3(grid), dim3(kThreads), fs, s, fa);
+  }
+  OMB_CHECK_LAUNCH();
   return OMB_OK;
 }
 

@@ -141,3 +141,14 @@ def test_specialised_reassigned_kernel_8192(emu):
         lanes = synth.cfg5_lanes(nl, 16384 + (frames - 1) * hop)
         st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
         assert st["cols"] == nl * frames and st["unmatched"] <= 4, st
+
+
+@pytest.mark.parametrize("mode,param", [(capi.AVG_PEAK_HOLD, 12.0), (capi.AVG_EXPONENTIAL, 0.6), (capi.AVG_NONE, 0.0)])
+def test_spectrum_fused_16k(emu, mode, param, monkeypatch):
+    """k_spectrum_fused_16k (FFT + smoothing + dB + arg-max in one kernel, one CTA per lane; pinned on with
+    OMB_SPECTRUM_FUSED=1 because two lanes would not select it) vs the oracle: ring wrap-around across 20 hops."""
+    monkeypatch.setenv("OMB_SPECTRUM_FUSED", "1")
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=mode, averaging_param=param, floor_db=-100.0)
+    lanes = synth.cfg4_streams(1, (16384 + 19 * 1024) / 48000.0).reshape(2, -1)
+    st = cases.spectrum_parity(emu.api, cfg, lanes)
+    assert st is not None

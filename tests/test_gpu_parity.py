@@ -157,6 +157,28 @@ def test_cfg4_spectrum_batch(product):
     cases.spectrum_parity(product.api, cfg, lanes)
 
 
+@pytest.mark.parametrize("mode,param", [(capi.AVG_PEAK_HOLD, 12.0), (capi.AVG_EXPONENTIAL, 0.7), (capi.AVG_NONE, 0.0)])
+def test_cfg4_spectrum_fused_kernel(product, mode, param, monkeypatch):
+    """The whole-batch fused kernel (one CTA per lane: FFT + smoothing + dB + arg-max), pinned on for a small lane
+    count, against the oracle; and the auto-selected path with enough lanes to fill the GPU against the two-kernel
+    path on the same data (same power values up to the epilogue twiddle rounding)."""
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=mode, averaging_param=param, floor_db=-100.0)
+    monkeypatch.setenv("OMB_SPECTRUM_FUSED", "1")
+    lanes = synth.cfg4_streams(3, 3.0).reshape(6, -1)
+    cases.spectrum_parity(product.api, cfg, lanes)
+    if mode != capi.AVG_PEAK_HOLD:
+        return
+    many = np.ascontiguousarray(np.concatenate([np.roll(lanes, 331 * r, axis=1) * np.float32(1 - 0.03 * r) for r in range(16)], 0)[:, :16384 + 40 * 1024])
+    monkeypatch.delenv("OMB_SPECTRUM_FUSED")
+    plan = batch.SpectrumPlan(cfg, api=product.api)
+    wf, rf, pf = plan.execute_host(many)            # 96 lanes: fused kernel
+    monkeypatch.setenv("OMB_SPECTRUM_FUSED", "0")
+    w2, r2, p2 = plan.execute_host(many)            # two-kernel path
+    parity.compare_db(rf, r2, cfg.floor_db)
+    parity.compare_db(wf, w2, cfg.floor_db)
+    assert np.mean(pf == p2) > 0.999
+
+
 @pytest.mark.parametrize("mode,param", [(capi.AVG_NONE, 0.0), (capi.AVG_EXPONENTIAL, 0.5)])
 def test_spectrum_modes(product, mode, param):
     lanes = synth.cfg4_streams(2, 1.5).reshape(4, -1)
