@@ -346,6 +346,72 @@ int omb_loudness_execute_host(omb_loudness_plan* p, const float* h_interleaved, 
                               uint64_t frames, uint64_t stream_stride, uint64_t block_frames,
                               omb_loudness_snapshot* h_out);
 
+
+/* ------------------------------------------------------------------------ */
+/* Rows f1 / f4 of SURVEY.md §8: the ordered audio timeline either side of   */
+/* the processors.  Host-side state machines (no device work of their own);  */
+/* the processors they feed keep their device-resident FIFOs.                */
+/* ------------------------------------------------------------------------ */
+
+/* dsp.rs:79-85 AudioFormat. Two formats are equal when every field is (PartialEq derive). */
+typedef struct omb_audio_format {
+  uint32_t channels;
+  float sample_rate;
+  uint64_t generation;
+  uint8_t positions[OMB_MAX_CHANNELS];
+} omb_audio_format;
+
+/* infra/pipewire/transport.rs:39-54 CapturedSpan */
+enum { OMB_SPAN_PCM = 0, OMB_SPAN_SILENCE = 1, OMB_SPAN_RESET = 2 };
+/* kind PCM: samples/n_samples valid until the callback returns; SILENCE: frames; RESET: nothing else. */
+typedef void (*omb_span_fn)(void* user, int kind, const float* samples, size_t n_samples, uint64_t frames,
+                            const omb_audio_format* format);
+
+/* Row f4 — AudioReader's packet timeline (transport.rs:573-657): packets carry [start_ns, end_ns) on the capture
+ * clock; a gap before a packet becomes a Silence span, an overlap with what was already delivered is skipped,
+ * PCM is coalesced in a scratch vector until flushed.  The lock-free queue, epochs and fault watchdog around it
+ * are PipeWire plumbing and stay out of scope. */
+typedef struct omb_timeline omb_timeline;
+int omb_timeline_create(const omb_audio_format* initial_format, omb_timeline** out);
+void omb_timeline_destroy(omb_timeline* t);
+/* ::accept (transport.rs:573-625). samples == NULL is a silence packet of `frames` frames. */
+int omb_timeline_accept(omb_timeline* t, const float* samples, uint64_t frames, const omb_audio_format* format,
+                        uint64_t start_ns, uint64_t end_ns, omb_span_fn consume, void* user);
+/* ::flush (transport.rs:634-643) */
+int omb_timeline_flush(omb_timeline* t, omb_span_fn consume, void* user);
+/* ::reset_timeline (transport.rs:645-656): drops the scratch, moves the cursor, aligns to the next packet. */
+int omb_timeline_reset(omb_timeline* t, uint64_t cursor_ns);
+uint64_t omb_timeline_cursor(const omb_timeline* t);
+size_t omb_timeline_pending_samples(const omb_timeline* t);
+
+/* Row f1 — DspBatcher (meter.rs:27-84) + ingest_silence (meter.rs:143-165) + VisualManager::ingest_samples
+ * (visuals/registry.rs:396-418) for the three hot-path processors.  After every ingest the callback receives the
+ * chunk that was ingested and the three processors' outputs (NULL where a processor is not attached or returned
+ * None); the pointers are library-owned and valid until the callback returns. */
+typedef struct omb_meter omb_meter;
+typedef void (*omb_ingest_fn)(void* user, const float* samples, size_t n_samples, const omb_audio_format* format,
+                              const omb_spectrogram_update* spectrogram, const omb_spectrum_snapshot* spectrum,
+                              const omb_loudness_snapshot* loudness);
+int omb_meter_create(omb_meter** out);
+void omb_meter_destroy(omb_meter* m);
+/* Borrowed handles (any may be NULL = module disabled); they must outlive the meter. */
+int omb_meter_attach(omb_meter* m, omb_spectrogram* spectrogram, omb_spectrum* spectrum, omb_loudness* loudness);
+int omb_meter_set_callback(omb_meter* m, omb_ingest_fn fn, void* user);
+/* DspBatcher::push (meter.rs:40-73); *n_ingests (may be NULL) = its return value. */
+int omb_meter_push(omb_meter* m, const float* samples, size_t n_samples, const omb_audio_format* format, uint32_t* n_ingests);
+/* ingest_silence (meter.rs:143-165): more than 2 s of silence resets instead of replaying zeros. */
+int omb_meter_push_silence(omb_meter* m, uint64_t frames, const omb_audio_format* format, uint32_t* n_ingests);
+/* DspBatcher::reset (meter.rs:75-78): clear + reset_audio on every attached processor. */
+int omb_meter_reset(omb_meter* m);
+/* DspBatcher::clear (meter.rs:80-83) */
+int omb_meter_clear(omb_meter* m);
+/* MeterEngine::advance's span dispatch (meter.rs:115-124): feed one CapturedSpan. */
+int omb_meter_consume_span(omb_meter* m, int kind, const float* samples, size_t n_samples, uint64_t frames,
+                           const omb_audio_format* format, uint32_t* n_ingests);
+size_t omb_meter_pending_samples(const omb_meter* m);
+/* 1 when the batcher currently holds a format (DspBatcher.format.is_some()). */
+int omb_meter_has_format(const omb_meter* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,20 @@ class LoudnessSnapshot(C.Structure):
     ]
 
 
+class AudioFormat(C.Structure):
+    _fields_ = [
+        ("channels", C.c_uint32),
+        ("sample_rate", C.c_float),
+        ("generation", C.c_uint64),
+        ("positions", C.c_uint8 * MAX_CHANNELS),
+    ]
+
+
+SPAN_PCM, SPAN_SILENCE, SPAN_RESET = 0, 1, 2
+SPAN_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_uint64, C.POINTER(AudioFormat))
+INGEST_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.POINTER(AudioFormat),
+                        C.POINTER(SpectrogramUpdate), C.POINTER(SpectrumSnapshot), C.POINTER(LoudnessSnapshot))
+
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
@@ -171,6 +185,25 @@ HEADER_SYMBOLS = {
     "loudness_plan_destroy": (None, [_vp]),
     "loudness_execute_device": (C.c_int, [_vp, _vp, _u32, _u64, _u64, _u64, _vp, _vp]),
     "loudness_execute_host": (C.c_int, [_vp, _vp, _u32, _u64, _u64, _u64, _vp]),
+    # rows f1 / f4: the ordered audio timeline (host-side state machines)
+    "timeline_create": (C.c_int, [C.POINTER(AudioFormat), C.POINTER(_vp)]),
+    "timeline_destroy": (None, [_vp]),
+    "timeline_accept": (C.c_int, [_vp, _f32p, _u64, C.POINTER(AudioFormat), _u64, _u64, SPAN_FN, _vp]),
+    "timeline_flush": (C.c_int, [_vp, SPAN_FN, _vp]),
+    "timeline_reset": (C.c_int, [_vp, _u64]),
+    "timeline_cursor": (_u64, [_vp]),
+    "timeline_pending_samples": (_sz, [_vp]),
+    "meter_create": (C.c_int, [C.POINTER(_vp)]),
+    "meter_destroy": (None, [_vp]),
+    "meter_attach": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "meter_set_callback": (C.c_int, [_vp, INGEST_FN, _vp]),
+    "meter_push": (C.c_int, [_vp, _f32p, _sz, C.POINTER(AudioFormat), _u32p]),
+    "meter_push_silence": (C.c_int, [_vp, _u64, C.POINTER(AudioFormat), _u32p]),
+    "meter_reset": (C.c_int, [_vp]),
+    "meter_clear": (C.c_int, [_vp]),
+    "meter_consume_span": (C.c_int, [_vp, C.c_int, _f32p, _sz, _u64, C.POINTER(AudioFormat), _u32p]),
+    "meter_pending_samples": (_sz, [_vp]),
+    "meter_has_format": (C.c_int, [_vp]),
 }
 
 

@@ -146,6 +146,11 @@ class SpectrogramProcessor:
             capi.positions_array(block.positions), C.byref(up)), "spectrogram_process_block")
         if rc == capi.NO_DATA:
             return None
+        return self._update(up)
+
+    @staticmethod
+    def _update(up: capi.SpectrogramUpdate) -> SpectrogramUpdate:
+        """Copies a library-owned omb_spectrogram_update into numpy-backed columns."""
         n = up.n_columns
         offs = np.ctypeslib.as_array(up.column_offsets, shape=(n + 1,)).astype(np.int64)
         cols = []

@@ -47,7 +47,9 @@ EXTRA = {
 _SHARED = [k for k in capi.HEADER_SYMBOLS if not (
     k in ("last_error", "device_count", "set_device", "kernel_launch_count") or k.startswith("stft_plan")
     or k.startswith("stft_execute") or k.startswith("spectrum_plan") or k.startswith("spectrum_execute")
-    or k.startswith("loudness_plan") or k.startswith("loudness_execute"))]
+    or k.startswith("loudness_plan") or k.startswith("loudness_execute")
+    # host-side timeline logic: restated in Python (oracle/meter_py.py), not in the C++ oracle
+    or k.startswith("timeline_") or k.startswith("meter_"))]
 
 
 def build(force: bool = False) -> str:
