@@ -412,6 +412,46 @@ size_t omb_meter_pending_samples(const omb_meter* m);
 /* 1 when the batcher currently holds a format (DspBatcher.format.is_some()). */
 int omb_meter_has_format(const omb_meter* m);
 
+
+/* ------------------------------------------------------------------------ */
+/* Row f2 of SURVEY.md §8: what consumes the reassigned points — the splat   */
+/* accumulation of the spectrogram view, as a CUDA scatter-add.              */
+/* ------------------------------------------------------------------------ */
+
+enum { OMB_FREQ_LINEAR = 0, OMB_FREQ_LOG = 1, OMB_FREQ_ERB = 2 }; /* util/audio/frequency.rs:25-31 */
+
+/* The subset of spectrogram/render.rs:187-252 `Uniforms` the accumulation and resolve passes read. The palette /
+ * rotation / clip transform of the final composite stay with the GUI: images here are in accumulation space. */
+typedef struct omb_splat_params {
+  uint32_t freq_scale;          /* OMB_FREQ_* */
+  float freq_min, freq_max;     /* display axis in Hz (spectrogram/state.rs:49-52) */
+  float uv_y_range[2];          /* zoom / pan window into the [0,1] frequency axis */
+  float ext_w, ext_h;           /* spectrogram.wgsl extents(): widget size in physical pixels (swapped when rotated) */
+  float scale_factor;           /* >= 1; one column = scale_factor pixels, splats are scale_factor^2 */
+  float tilt_db;                /* dB / octave re 1 kHz; 0 = off */
+  uint32_t ring_capacity;       /* history_length: slots in the point ring */
+  uint32_t newest_col;          /* (write_slot + ring_capacity - 1) % ring_capacity */
+  uint32_t col_count;           /* columns received so far; min(col_count, ring_capacity) slots are drawn */
+  float reassigned_power_scale; /* omb_spectrogram_update.reassigned_power_scale */
+} omb_splat_params;
+
+/* Accumulation-texture size (render.rs:511-531 resize_accum with rotation folded into ext): ceil(max(ext, 1)). */
+void omb_splat_image_size(const omb_splat_params* p, uint32_t* width, uint32_t* height);
+
+/* vs_accum_splat + fs_accum with additive blending (spectrogram.wgsl:126-147,215-225): every point of every drawn
+ * slot adds its (tilted) power to the pixels its scale_factor-sized quad covers.  d_rings: n_rings point rings laid
+ * out [ring][slot][point_stride]; d_slot_counts[ring][slot] = points in the slot (clamped to point_stride);
+ * d_accum: n_rings images [height][width] f32, cleared by this call (LoadOp::Clear).  The Rg16Float dual-scale
+ * trick (wgsl:4-7) exists only because of the f16 attachment and is not reproduced: accumulation is f32. */
+int omb_splat_accumulate_device(const omb_spectrogram_point* d_rings, uint64_t point_stride, const uint32_t* d_slot_counts,
+                                uint32_t n_rings, const omb_splat_params* p, float* d_accum, void* cuda_stream);
+/* fs_resolve (wgsl:227-237) up to the palette: dB = max(ln(max(power*scale, 1e-20)) * LN_TO_DB, -140), and -inf
+ * where nothing was accumulated (the transparent pixels). */
+int omb_splat_resolve_device(const float* d_accum, uint32_t n_rings, const omb_splat_params* p, float* d_db, void* cuda_stream);
+/* Host-pointer convenience (H2D of the ring, both passes, D2H of the images). h_accum may be NULL. */
+int omb_splat_render_host(const omb_spectrogram_point* h_rings, uint64_t point_stride, const uint32_t* h_slot_counts,
+                          uint32_t n_rings, const omb_splat_params* p, float* h_accum, float* h_db);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,24 @@ class AudioFormat(C.Structure):
     ]
 
 
+class SplatParams(C.Structure):
+    _fields_ = [
+        ("freq_scale", C.c_uint32),
+        ("freq_min", C.c_float),
+        ("freq_max", C.c_float),
+        ("uv_y_range", C.c_float * 2),
+        ("ext_w", C.c_float),
+        ("ext_h", C.c_float),
+        ("scale_factor", C.c_float),
+        ("tilt_db", C.c_float),
+        ("ring_capacity", C.c_uint32),
+        ("newest_col", C.c_uint32),
+        ("col_count", C.c_uint32),
+        ("reassigned_power_scale", C.c_float),
+    ]
+
+
+FREQ_LINEAR, FREQ_LOG, FREQ_ERB = 0, 1, 2
 SPAN_PCM, SPAN_SILENCE, SPAN_RESET = 0, 1, 2
 SPAN_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_uint64, C.POINTER(AudioFormat))
 INGEST_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.POINTER(AudioFormat),
@@ -204,6 +222,11 @@ HEADER_SYMBOLS = {
     "meter_consume_span": (C.c_int, [_vp, C.c_int, _f32p, _sz, _u64, C.POINTER(AudioFormat), _u32p]),
     "meter_pending_samples": (_sz, [_vp]),
     "meter_has_format": (C.c_int, [_vp]),
+    # row f2: splat accumulation + resolve
+    "splat_image_size": (None, [C.POINTER(SplatParams), _u32p, _u32p]),
+    "splat_accumulate_device": (C.c_int, [_vp, _u64, _vp, _u32, C.POINTER(SplatParams), _vp, _vp]),
+    "splat_resolve_device": (C.c_int, [_vp, _u32, C.POINTER(SplatParams), _vp, _vp]),
+    "splat_render_host": (C.c_int, [_vp, _u64, _vp, _u32, C.POINTER(SplatParams), _vp, _vp]),
 }
 
 

@@ -49,7 +49,9 @@ _SHARED = [k for k in capi.HEADER_SYMBOLS if not (
     or k.startswith("stft_execute") or k.startswith("spectrum_plan") or k.startswith("spectrum_execute")
     or k.startswith("loudness_plan") or k.startswith("loudness_execute")
     # host-side timeline logic: restated in Python (oracle/meter_py.py), not in the C++ oracle
-    or k.startswith("timeline_") or k.startswith("meter_"))]
+    or k.startswith("timeline_") or k.startswith("meter_")
+    # splat accumulation: restated in numpy (oracle/splat_py.py)
+    or k.startswith("splat_"))]
 
 
 def build(force: bool = False) -> str:

@@ -355,6 +355,18 @@ template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline float fminf_(float a, float b) { return std::fmin(a, b); }
 
 template <class T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline float atomicAdd(float* p, float v) {  // blocks run on worker threads: CAS loop on the bit pattern
+  unsigned* u = reinterpret_cast<unsigned*>(p);
+  unsigned old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+  float f;
+  do {
+    std::memcpy(&f, &old, 4);
+    f += v;
+    std::memcpy(&want, &f, 4);
+  } while (!__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  std::memcpy(&f, &old, 4);
+  return f;
+}
 static inline unsigned atomicMax(unsigned* p, unsigned v) {
   unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (o < v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

@@ -106,6 +106,32 @@ def main():
         t = timed(lambda: plan.execute_device(streams.data_ptr(), nS, frames, frames * 8, 1024, snaps.data_ptr(), stream=st), iters=5)
         res["cfg3_loudness_8ch"] = dict(sample_channels_per_s=nS * frames * 8 / t, ms=t * 1e3, algorithmic_bytes_per_sample_channel=4,
                                         achieved_gbs=nS * frames * 8 * 4 / t / 1e9, hbm_frac=nS * frames * 8 * 4 / t / 1e9 / PEAK)
+    if want("splat"):
+        # row f2: splat accumulation of cfg2 columns (64 rings x 1024 columns x 2049 points) into 64 images of 1024 x 512
+        import ctypes as C
+        from openmeters_b200 import splat
+        R, hl, stride = 64, 1000, 2049
+        rng = np.random.default_rng(1)
+        pts = torch.empty((R, hl, stride, 3), dtype=torch.float32, device=dev)
+        pts[..., 0].uniform_(-2.5, 0.5)
+        pts[..., 1] = torch.exp(torch.empty((R, hl, stride), device=dev).uniform_(float(np.log(1.0)), float(np.log(24000.0))))
+        pts[..., 2] = 10.0 ** torch.empty((R, hl, stride), device=dev).uniform_(-14.0, 0.0)
+        cnt = torch.full((R, hl), stride, dtype=torch.int32, device=dev)
+        fmin, fmax = splat.display_axis(48000.0)
+        p = splat.SplatParams(freq_min=fmin, freq_max=fmax, ring_capacity=hl, newest_col=hl - 1, col_count=hl, ext_w=1024.0, ext_h=512.0)
+        c = p.to_c()
+        acc = torch.empty((R, 512, 1024), dtype=torch.float32, device=dev)
+        db = torch.empty_like(acc)
+
+        def run():
+            assert api.splat_accumulate_device(pts.data_ptr(), stride, cnt.data_ptr(), R, C.byref(c), acc.data_ptr(), st) == 0
+            assert api.splat_resolve_device(acc.data_ptr(), R, C.byref(c), db.data_ptr(), st) == 0
+        t = timed(run, iters=5)
+        npts = R * hl * stride
+        b = 12 * npts + 2 * 4 * acc.numel() + 4 * acc.numel()   # points in; image cleared + accumulated + resolved
+        res["splat_accumulate_resolve"] = dict(points_per_s=npts / t, ms=t * 1e3, algorithmic_bytes=b, achieved_gbs=b / t / 1e9, hbm_frac=b / t / 1e9 / PEAK,
+                                               columns_per_s=R * hl / t)
+        del pts, cnt, acc, db
     print(json.dumps(res))
 
 
