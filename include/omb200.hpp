@@ -79,6 +79,8 @@ class SpectrogramProcessor {
     return u;
   }
 
+  omb_spectrogram* handle() const { return h_; }
+
  private:
   omb_spectrogram* h_ = nullptr;
 };
@@ -111,6 +113,8 @@ class SpectrumProcessor {
     return &snap_;
   }
 
+  omb_spectrum* handle() const { return h_; }
+
  private:
   omb_spectrum* h_ = nullptr;
   SpectrumSnapshot snap_;
@@ -135,9 +139,94 @@ class LoudnessProcessor {
     return s;
   }
 
+  omb_loudness* handle() const { return h_; }
+
  private:
   omb_loudness* h_ = nullptr;
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rows f1 / f4: the ordered audio timeline (meter.rs, infra/pipewire/transport.rs)
+using AudioFormat = omb_audio_format;  // dsp.rs:79-85
+
+// transport.rs:39-54 CapturedSpan
+struct CapturedSpan {
+  int kind = OMB_SPAN_RESET;          // OMB_SPAN_*
+  std::vector<float> samples;         // Pcm
+  uint64_t frames = 0;                // Silence
+  AudioFormat format{};
+};
+
+// AudioReader's packet timeline (transport.rs:573-657): accept / flush / reset_timeline.
+class PacketTimeline {
+ public:
+  explicit PacketTimeline(const AudioFormat& initial) { check(omb_timeline_create(&initial, &h_), "omb_timeline_create"); }
+  ~PacketTimeline() { omb_timeline_destroy(h_); }
+  PacketTimeline(const PacketTimeline&) = delete;
+  PacketTimeline& operator=(const PacketTimeline&) = delete;
+  // samples == nullptr: a silence packet. Spans are appended to `out` in emission order.
+  void accept(const float* samples, uint64_t frames, const AudioFormat& f, uint64_t start_ns, uint64_t end_ns, std::vector<CapturedSpan>& out) {
+    check(omb_timeline_accept(h_, samples, frames, &f, start_ns, end_ns, &PacketTimeline::collect, &out), "omb_timeline_accept");
+  }
+  void flush(std::vector<CapturedSpan>& out) { check(omb_timeline_flush(h_, &PacketTimeline::collect, &out), "omb_timeline_flush"); }
+  void reset_timeline(uint64_t cursor_ns) { check(omb_timeline_reset(h_, cursor_ns), "omb_timeline_reset"); }
+  uint64_t cursor() const { return omb_timeline_cursor(h_); }
+
+ private:
+  static void collect(void* user, int kind, const float* samples, size_t n, uint64_t frames, const omb_audio_format* f) {
+    CapturedSpan s;
+    s.kind = kind;
+    if (samples) s.samples.assign(samples, samples + n);
+    s.frames = frames;
+    if (f) s.format = *f;
+    static_cast<std::vector<CapturedSpan>*>(user)->push_back(std::move(s));
+  }
+  omb_timeline* h_ = nullptr;
+};
+
+// DspBatcher (meter.rs:27-84) + ingest_silence (:143-165) + VisualManager::ingest_samples (registry.rs:396-418) over
+// borrowed processors.  `on_ingest` (optional) sees every ingested chunk with the processors' outputs.
+class DspBatcher {
+ public:
+  DspBatcher(SpectrogramProcessor* sg, SpectrumProcessor* sp, LoudnessProcessor* ld, omb_ingest_fn on_ingest = nullptr, void* user = nullptr) {
+    check(omb_meter_create(&h_), "omb_meter_create");
+    check(omb_meter_attach(h_, sg ? sg->handle() : nullptr, sp ? sp->handle() : nullptr, ld ? ld->handle() : nullptr), "omb_meter_attach");
+    if (on_ingest) check(omb_meter_set_callback(h_, on_ingest, user), "omb_meter_set_callback");
+  }
+  ~DspBatcher() { omb_meter_destroy(h_); }
+  DspBatcher(const DspBatcher&) = delete;
+  DspBatcher& operator=(const DspBatcher&) = delete;
+  uint32_t push(const float* samples, size_t n, const AudioFormat& f) { uint32_t c = 0; check(omb_meter_push(h_, samples, n, &f, &c), "omb_meter_push"); return c; }
+  uint32_t ingest_silence(uint64_t frames, const AudioFormat& f) { uint32_t c = 0; check(omb_meter_push_silence(h_, frames, &f, &c), "omb_meter_push_silence"); return c; }
+  // MeterEngine::advance's dispatch (meter.rs:115-124)
+  uint32_t consume(const CapturedSpan& s) {
+    uint32_t c = 0;
+    check(omb_meter_consume_span(h_, s.kind, s.samples.data(), s.samples.size(), s.frames, &s.format, &c), "omb_meter_consume_span");
+    return c;
+  }
+  void reset() { check(omb_meter_reset(h_), "omb_meter_reset"); }
+  void clear() { check(omb_meter_clear(h_), "omb_meter_clear"); }
+  size_t pending_samples() const { return omb_meter_pending_samples(h_); }
+
+ private:
+  omb_meter* h_ = nullptr;
+};
+
+// Row f2: accumulation + resolve passes of the spectrogram view (render.rs:104-165, spectrogram.wgsl) on host buffers.
+using SplatParams = omb_splat_params;
+struct SplatImages {
+  uint32_t width = 0, height = 0;
+  std::vector<float> accum, db;  // [ring][height][width]
+};
+inline SplatImages splat_render(const SpectrogramPoint* rings, uint64_t point_stride, const uint32_t* slot_counts, uint32_t n_rings,
+                                const SplatParams& p) {
+  SplatImages im;
+  omb_splat_image_size(&p, &im.width, &im.height);
+  im.accum.resize((size_t)im.width * im.height * n_rings);
+  im.db.resize(im.accum.size());
+  check(omb_splat_render_host(rings, point_stride, slot_counts, n_rings, &p, im.accum.data(), im.db.data()), "omb_splat_render_host");
+  return im;
+}
 
 // registry.rs:247-256 VisualModule — the trait the reference drives its visuals through.
 struct VisualModule {

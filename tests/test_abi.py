@@ -89,3 +89,17 @@ def test_host_side_tables_match_oracle(lib, oracle):
         assert np.array_equal(p.stereo_matrix(ch, p.fallback_positions(ch)), o.stereo_matrix(ch, o.fallback_positions(ch)))
     odd = [capi.POS_LOW_FREQUENCY, capi.POS_AUX0, capi.POS_FRONT_RIGHT, capi.POS_UNKNOWN]
     assert np.array_equal(p.stereo_matrix(4, odd), o.stereo_matrix(4, odd))
+
+
+def test_cpp_mirror_compiles_and_runs(lib, tmp_path):
+    """include/omb200.hpp (C++ host mirror) builds against the library and its host-side classes behave."""
+    import subprocess
+
+    from openmeters_b200 import _lib
+
+    exe = tmp_path / "mirror_smoke"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["g++", "-std=c++20", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "mirror_smoke.cpp"),
+                    "-L", libdir, "-lomb200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
