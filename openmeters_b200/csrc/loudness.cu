@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace omb {
 
@@ -175,8 +176,9 @@ struct LoudBatchArgs {
   double* seg_state; // [stream][segment][channel][4]
   double* end_state;     // [stream][chunk][channel][4]  zero-state end states
   double* start_state;   // [stream][chunk][channel][4]  true start states
-  float* y;              // [stream][channel][frame]
+  float* y;              // [stream][frame][channel] (K-weighted samples, the input's layout)
   double* csum;          // [stream][channel][chunk]
+  const double* cbase;   // [stream][channel][chunk + 1] exclusive prefix sums of csum (null: sum the chunks directly)
   unsigned* peak;        // [stream][block][channel]  float bits (non-negative)
   uint64_t caps[kLoudWindows];
   double weights[OMB_MAX_CHANNELS];
@@ -186,32 +188,23 @@ struct LoudBatchArgs {
 };
 
 // (1)/(3): one thread per (stream, chunk, channel); channel fastest so a warp reads whole frames.
-// The apply pass (kApply) writes y through a per-warp 32x32 transposed tile so that every global store is a full
-// 128-byte line of one (stream, channel) row instead of 32 scattered 4-byte writes.
+// The apply pass (kApply) writes y in the input's own interleaved layout [stream][frame][channel]: a warp's store of one
+// time step is then whole 32-byte sectors (8 channels x 4 B), exactly like its load — no transposition needed — and the
+// snapshot kernel's edge sums read one sector per frame for all channels of a window.
 template <bool kApply>
 __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
-  __shared__ float tile[4][32][33];
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t total = (uint64_t)a.n_streams * a.n_chunks * a.channels;
-  const bool valid = idx < total;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t id = valid ? idx : total - 1;
-  const uint32_t c = (uint32_t)(id % a.channels);
-  const uint64_t chunk = (id / a.channels) % a.n_chunks;
-  const uint64_t stream = id / ((uint64_t)a.channels * a.n_chunks);
+  if (idx >= total) return;
+  const uint32_t c = (uint32_t)(idx % a.channels);
+  const uint64_t chunk = (idx / a.channels) % a.n_chunks;
+  const uint64_t stream = idx / ((uint64_t)a.channels * a.n_chunks);
   const float* x = a.in + stream * a.stream_stride;
   const uint64_t t0 = chunk * kKwChunk;
   const uint64_t t1 = t0 + kKwChunk < a.frames ? t0 + kKwChunk : a.frames;
   double s[4] = {0.0, 0.0, 0.0, 0.0};
   const uint64_t sidx = ((stream * a.n_chunks + chunk) * a.channels + c) * 4;
-  if (kApply) {
-    s[0] = a.start_state[sidx + 0];
-    s[1] = a.start_state[sidx + 1];
-    s[2] = a.start_state[sidx + 2];
-    s[3] = a.start_state[sidx + 3];
-  }
   if (!kApply) {
-    if (!valid) return;
     for (uint64_t t = t0; t < t1; ++t) kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
     a.end_state[sidx + 0] = s[0];
     a.end_state[sidx + 1] = s[1];
@@ -219,30 +212,20 @@ __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
     a.end_state[sidx + 3] = s[3];
     return;
   }
-  // row base of this lane's (stream, channel, chunk) in y, and how many samples the chunk has
-  const unsigned long long ybase = (unsigned long long)((stream * a.channels + c) * a.frames + t0);
-  const int len = valid ? (int)(t1 - t0) : 0;
+  s[0] = a.start_state[sidx + 0];
+  s[1] = a.start_state[sidx + 1];
+  s[2] = a.start_state[sidx + 2];
+  s[3] = a.start_state[sidx + 3];
+  float* y = a.y + stream * a.frames * a.channels;
   double acc = 0.0;
-  for (int tt = 0; tt < kKwChunk; tt += 32) {
 #pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-      float yf = 0.0f;
-      if (tt + i < len) {
-        yf = (float)kw_step((double)__ldg(&x[(t0 + tt + i) * a.channels + c]), s, a.kw);
-        const double v = (double)yf * (double)yf;
-        acc += isfinite(v) ? v : 0.0;
-      }
-      tile[warp][lane][i] = yf;
-    }
-    __syncwarp();
-    for (int r = 0; r < 32; ++r) {
-      const unsigned long long rb = __shfl_sync(0xffffffffu, ybase, r);
-      const int rl = __shfl_sync(0xffffffffu, len, r);
-      if (tt + lane < rl) a.y[rb + tt + lane] = tile[warp][r][lane];
-    }
-    __syncwarp();
+  for (uint64_t t = t0; t < t1; ++t) {
+    const float yf = (float)kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
+    const double v = (double)yf * (double)yf;
+    acc += isfinite(v) ? v : 0.0;
+    y[t * a.channels + c] = yf;
   }
-  if (valid) a.csum[(stream * a.channels + c) * a.n_chunks + chunk] = acc;
+  a.csum[(stream * a.channels + c) * a.n_chunks + chunk] = acc;
 }
 
 // (2): scan over chunks of the affine recurrence start[k+1] = M * start[k] + end0[k], three levels so the
@@ -351,28 +334,139 @@ __global__ void __launch_bounds__(kTpTile) k_true_peak(LoudBatchArgs a, TruePeak
   }
 }
 
+// 4x true peak, register-blocked (sample rates below 96 kHz — the common case): the tile is staged like above, then
+// every thread owns kTpRun consecutive frames of ONE channel, keeps their 11-sample history in registers and runs the
+// three 12-tap phases with scalar multiplies and adds in the reference's order (separate roundings, bit-identical sums).
+// (Packed FP32x2 would halve the issue slots, but ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 — one rounding
+// instead of two, even with -fmad=false — so the packed form cannot keep the reference's bits.)
+// A warp covers 32 runs of one channel: the smem row is padded 9-for-8 so the stride-8 reads are conflict-free, and
+// the max is reduced once per kTpRun frames instead of once per frame.  ~60 instructions per sample-channel instead
+// of ~190 (profiles/r01b_notes.md).
+constexpr int kTpRun = 8, kTp4Halo = 11;
+constexpr int kTp4Row = (kTpTile + kTp4Halo) + (kTpTile + kTp4Halo) / 8 + 2;
+
+template <int kC>  // channel count known at compile time (index arithmetic of the staging loop), 0 = any
+__global__ void __launch_bounds__(kTpTile) k_true_peak4(LoudBatchArgs a, TruePeakFir fir) {
+  __shared__ float tile[OMB_MAX_CHANNELS][kTp4Row];
+  const uint64_t sb = blockIdx.x;  // stream * n_blocks + block
+  const uint64_t stream = sb / a.n_blocks, blk = sb % a.n_blocks;
+  const float* x = a.in + stream * a.stream_stride;
+  const uint64_t f0 = blk * a.block_frames;
+  const uint64_t f1 = f0 + a.block_frames < a.frames ? f0 + a.block_frames : a.frames;
+  const int C = kC ? kC : (int)a.channels;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // warp = channel (C <= 8 warps take part in the FIR)
+  float best = 0.0f;
+  for (uint64_t base = f0 + (uint64_t)blockIdx.y * kTpTile; base < f1; base += (uint64_t)gridDim.y * kTpTile) {
+    // tile frame index u <-> stream frame base - kTp4Halo + u; frames before the stream start are zeros
+    const int n_el = (kTpTile + kTp4Halo) * C;
+    for (int e = threadIdx.x; e < n_el; e += kTpTile) {
+      const int u = e / C, c = e - u * C;
+      const int64_t fr = (int64_t)base - kTp4Halo + u;
+      tile[c][u + (u >> 3)] = (fr >= 0 && (uint64_t)fr < a.frames) ? __ldg(&x[(uint64_t)fr * C + c]) : 0.0f;
+    }
+    __syncthreads();
+    if (warp < C) {
+      // this thread's frames: base + 8 lane + r, r < 8; window w[k] = tile frame 8 lane + k, k < 19 (w[11 + r] is frame r)
+      float w[kTpRun + kTp4Halo];
+      const float* row = tile[warp];
+#pragma unroll
+      for (int k = 0; k < kTpRun + kTp4Halo; ++k) {
+        const int u = kTpRun * lane + k;
+        w[k] = row[u + (u >> 3)];
+      }
+#pragma unroll
+      for (int r = 0; r < kTpRun; ++r) {
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {  // delay[pos + i] == x[t - i]
+          const float d = w[kTp4Halo + r - i];
+          o0 = __fadd_rn(o0, __fmul_rn(d, fir.fir4[i][0]));
+          o1 = __fadd_rn(o1, __fmul_rn(d, fir.fir4[i][1]));
+          o2 = __fadd_rn(o2, __fmul_rn(d, fir.fir4[i][2]));
+        }
+        // NaN input: fmaxf drops NaN exactly like Rust's f32::max in TruePeakMeter::process.
+        const float pk = fmaxf(fmaxf(fmaxf(fabsf(w[kTp4Halo + r]), fabsf(o0)), fabsf(o1)), fabsf(o2));
+        if (base + (uint64_t)(kTpRun * lane + r) < f1) best = fmaxf(best, pk);
+      }
+    }
+    __syncthreads();
+  }
+  if (warp < C) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0 && best > 0.0f) atomicMax(&a.peak[sb * C + warp], __float_as_uint(best));
+  }
+}
+
+// Exclusive prefix sums of the chunk sums, one CTA per (stream, channel) row: cbase[row][k] = sum of csum[row][0..k).
+// Every thread owns a contiguous slice (local sum -> block scan of the 256 slice sums -> prefix inside the slice).
+// f64: a 0.3 s window out of an hour of audio loses < 1e-12 relative to the subtraction.
+__global__ void __launch_bounds__(256) k_csum_prefix(LoudBatchArgs a, double* cbase) {
+  __shared__ double part[256];
+  const uint64_t row = blockIdx.x;
+  const int t = threadIdx.x;
+  const double* cs = a.csum + row * a.n_chunks;
+  double* out = cbase + row * (a.n_chunks + 1);
+  const uint64_t per = (a.n_chunks + 255) / 256;
+  const uint64_t k0 = (uint64_t)t * per, k1 = k0 + per < a.n_chunks ? k0 + per : a.n_chunks;
+  double local = 0.0;
+  for (uint64_t k = k0; k < k1; ++k) local += cs[k];
+  part[t] = local;
+  __syncthreads();
+  if (t < 32) {  // exclusive scan of 256 partial sums by one warp, 8 per lane
+    double v[8], run = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = run;
+      run += part[t * 8 + i];
+    }
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (t >= o) incl += n;
+    }
+    const double base = incl - run;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[t * 8 + i] = base + v[i];
+  }
+  __syncthreads();
+  double acc = part[t];
+  for (uint64_t k = k0; k < k1; ++k) {
+    out[k] = acc;
+    acc += cs[k];
+  }
+  if (t == 255) out[a.n_chunks] = part[255] + local;  // exclusive prefix of the last slice + the slice itself = total
+}
+
 // Sum of y^2 over frames [t0, t1) of one (stream, channel): whole chunk sums + two partial edges.
 __device__ double window_sum(const LoudBatchArgs& a, uint64_t stream, uint32_t c, uint64_t t0, uint64_t t1) {
   if (t1 <= t0) return 0.0;
-  const float* y = a.y + (stream * a.channels + c) * a.frames;
+  const float* y = a.y + stream * a.frames * a.channels + c;  // interleaved [frame][channel]
+  const uint64_t C = a.channels;
   const double* cs = a.csum + (stream * a.channels + c) * a.n_chunks;
   const uint64_t k0 = (t0 + kKwChunk - 1) / kKwChunk;  // first chunk fully inside
   const uint64_t k1 = t1 / kKwChunk;                   // one past the last chunk fully inside
   double acc = 0.0;
   if (k0 >= k1) {  // no whole chunk inside
     for (uint64_t t = t0; t < t1; ++t) {
-      const double v = (double)y[t] * (double)y[t];
+      const double v = (double)y[t * C] * (double)y[t * C];
       acc += isfinite(v) ? v : 0.0;
     }
     return acc;
   }
   for (uint64_t t = t0; t < k0 * kKwChunk; ++t) {
-    const double v = (double)y[t] * (double)y[t];
+    const double v = (double)y[t * C] * (double)y[t * C];
     acc += isfinite(v) ? v : 0.0;
   }
-  for (uint64_t k = k0; k < k1; ++k) acc += cs[k];
+  if (a.cbase) {
+    const double* cb = a.cbase + (stream * a.channels + c) * (a.n_chunks + 1);
+    acc += cb[k1] - cb[k0];
+  } else {
+    for (uint64_t k = k0; k < k1; ++k) acc += cs[k];
+  }
   for (uint64_t t = k1 * kKwChunk; t < t1; ++t) {
-    const double v = (double)y[t] * (double)y[t];
+    const double v = (double)y[t * C] * (double)y[t * C];
     acc += isfinite(v) ? v : 0.0;
   }
   return acc;
@@ -501,6 +595,7 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   OMB_TRY(d_y.reserve((size_t)((uint64_t)n_streams * channels * frames)));
   OMB_TRY(d_csum.reserve((size_t)((uint64_t)n_streams * channels * a.n_chunks)));
   OMB_TRY(d_peak.reserve((size_t)((uint64_t)n_streams * a.n_blocks * channels)));
+  OMB_TRY(d_cbase.reserve((size_t)((uint64_t)n_streams * channels * (a.n_chunks + 1))));
   a.end_state = d_end.ptr;
   a.start_state = d_start.ptr;
   a.y = d_y.ptr;
@@ -537,8 +632,25 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   OMB_LAUNCH(k_apply, dim3(g1), dim3(128), 0, s, a);
   OMB_CHECK_LAUNCH();
   const unsigned gx = (unsigned)std::min<uint64_t>((block_frames + kTpTile - 1) / kTpTile, 64);
-  OMB_LAUNCH(k_true_peak, dim3((unsigned)((uint64_t)n_streams * a.n_blocks), gx), dim3(kTpTile), 0, s, a, fir);
+  if (tp_delay_len == 12 && !getenv("OMB_NO_TRUE_PEAK4")) {
+    // enough (stream, block) pairs to fill the GPU: one CTA walks all tiles of its block (set-up and the final reduction
+    // are paid once per block instead of once per 256 frames)
+    const unsigned gy = (uint64_t)n_streams * a.n_blocks >= (uint64_t)std::max(dev.sm_count, 1) * 16 ? 1u : gx;
+    const dim3 grid((unsigned)((uint64_t)n_streams * a.n_blocks), gy);
+    if (channels == 8) {
+      OMB_LAUNCH(k_true_peak4<8>, grid, dim3(kTpTile), 0, s, a, fir);
+    } else if (channels == 2) {
+      OMB_LAUNCH(k_true_peak4<2>, grid, dim3(kTpTile), 0, s, a, fir);
+    } else {
+      OMB_LAUNCH(k_true_peak4<0>, grid, dim3(kTpTile), 0, s, a, fir);
+    }
+  } else {
+    OMB_LAUNCH(k_true_peak, dim3((unsigned)((uint64_t)n_streams * a.n_blocks), gx), dim3(kTpTile), 0, s, a, fir);
+  }
   OMB_CHECK_LAUNCH();
+  OMB_LAUNCH(k_csum_prefix, dim3((unsigned)((uint64_t)n_streams * channels)), dim3(256), 0, s, a, d_cbase.ptr);
+  OMB_CHECK_LAUNCH();
+  a.cbase = d_cbase.ptr;
   const uint64_t n_snap = (uint64_t)n_streams * a.n_blocks;
   OMB_LAUNCH(k_loud_snapshots, dim3((unsigned)((n_snap * 32 + 127) / 128)), dim3(128), 0, s, a);
   OMB_CHECK_LAUNCH();
