@@ -34,8 +34,11 @@ def scatter_lanes(all_lanes, n_lanes: int, samples: int, src: int = 0, device=No
     rank, world = dist.get_rank(), dist.get_world_size()
     mine = lanes_for_rank(n_lanes, rank, world)
     out = torch.empty((len(mine), samples), dtype=torch.float32, device=device)
+    # NCCL: one batched group of sends, so the transfers to all peers run concurrently over NVLink / NVSwitch instead of
+    # being serialised as independent collectives (what unbatched P2P ops are in eager-init mode).
+    batched = dist.get_backend() == "nccl"
     if rank == src:
-        reqs = []
+        reqs, ops, keep = [], [], []
         for r in range(world):
             idx = lanes_for_rank(n_lanes, r, world)
             if not idx:
@@ -43,12 +46,21 @@ def scatter_lanes(all_lanes, n_lanes: int, samples: int, src: int = 0, device=No
             part = all_lanes[idx].contiguous()
             if r == src:
                 out.copy_(part)
+            elif batched:
+                keep.append(part)
+                ops.append(dist.P2POp(dist.isend, part, r))
             else:
                 reqs.append(dist.isend(part, dst=r))
+        if ops:
+            reqs = dist.batch_isend_irecv(ops)
         for q in reqs:
             q.wait()
     elif mine:
-        dist.recv(out, src=src)
+        if batched:
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, out, src)]):
+                q.wait()
+        else:
+            dist.recv(out, src=src)
     return out, mine
 
 
