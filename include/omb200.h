@@ -452,6 +452,42 @@ int omb_splat_resolve_device(const float* d_accum, uint32_t n_rings, const omb_s
 int omb_splat_render_host(const omb_spectrogram_point* h_rings, uint64_t point_stride, const uint32_t* h_slot_counts,
                           uint32_t n_rings, const omb_splat_params* p, float* h_accum, float* h_db);
 
+
+/* ------------------------------------------------------------------------ */
+/* Row f1, device side: the multi-stream ring.  S independent streams that    */
+/* share one spectrogram config and advance in lock-step (one capture clock,  */
+/* e.g. the DspBatcher cadence): every push appends one block to EVERY stream */
+/* in a device-resident ring [stream][pending] and all newly ready columns of */
+/* all streams come out of ONE launch of the batched kernel.  Column for      */
+/* column identical to S separate omb_spectrogram handles fed the same blocks.*/
+/* ------------------------------------------------------------------------ */
+typedef struct omb_spectrogram_bank omb_spectrogram_bank;
+
+/* Dense form of S SpectrogramUpdates (processor.rs:160-168): every stream has n_columns new columns. */
+typedef struct omb_spectrogram_bank_update {
+  uint64_t fft_size, hop_size, history_length;
+  float sample_rate, reassigned_power_scale;
+  int32_t reset;
+  int32_t kind;                         /* OMB_COLUMN_* */
+  uint32_t n_streams, n_columns, bins, _pad;
+  const uint32_t* counts;               /* reassigned: [stream][column] points in the column */
+  const omb_spectrogram_point* points;  /* reassigned: [stream][column][bins] slots, the first counts[..] are valid (ascending bin) */
+  const uint16_t* classic_db;           /* classic:    [stream][column][bins] */
+} omb_spectrogram_bank_update;
+
+int omb_spectrogram_bank_create(const omb_spectrogram_config* cfg, uint32_t n_streams, omb_spectrogram_bank** out);
+void omb_spectrogram_bank_destroy(omb_spectrogram_bank* b);
+/* ::reset_audio of every stream (processor.rs:212-217) */
+int omb_spectrogram_bank_reset_audio(omb_spectrogram_bank* b);
+/* ::process_block of every stream (processor.rs:490-516) with one block each: stream s reads `frames` interleaved frames
+ * of `channels` channels at samples + s * stream_stride (floats).  OMB_NO_DATA when no stream has a new column.
+ * Output pointers are library-owned pinned host memory, valid until the next call. */
+int omb_spectrogram_bank_push(omb_spectrogram_bank* b, const float* samples, uint64_t stream_stride, size_t frames,
+                              uint32_t channels, float sample_rate, const uint8_t positions[OMB_MAX_CHANNELS],
+                              omb_spectrogram_bank_update* out);
+/* Samples pending per stream (the VecDeque length of processor.rs:412-437). */
+size_t omb_spectrogram_bank_pending(const omb_spectrogram_bank* b);
+
 #ifdef __cplusplus
 }
 #endif

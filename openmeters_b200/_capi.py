@@ -129,6 +129,25 @@ class SplatParams(C.Structure):
     ]
 
 
+class SpectrogramBankUpdate(C.Structure):
+    _fields_ = [
+        ("fft_size", C.c_uint64),
+        ("hop_size", C.c_uint64),
+        ("history_length", C.c_uint64),
+        ("sample_rate", C.c_float),
+        ("reassigned_power_scale", C.c_float),
+        ("reset", C.c_int32),
+        ("kind", C.c_int32),
+        ("n_streams", C.c_uint32),
+        ("n_columns", C.c_uint32),
+        ("bins", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("counts", C.POINTER(C.c_uint32)),
+        ("points", C.POINTER(SpectrogramPoint)),
+        ("classic_db", C.POINTER(C.c_uint16)),
+    ]
+
+
 FREQ_LINEAR, FREQ_LOG, FREQ_ERB = 0, 1, 2
 SPAN_PCM, SPAN_SILENCE, SPAN_RESET = 0, 1, 2
 SPAN_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_uint64, C.POINTER(AudioFormat))
@@ -222,6 +241,12 @@ HEADER_SYMBOLS = {
     "meter_consume_span": (C.c_int, [_vp, C.c_int, _f32p, _sz, _u64, C.POINTER(AudioFormat), _u32p]),
     "meter_pending_samples": (_sz, [_vp]),
     "meter_has_format": (C.c_int, [_vp]),
+    # row f1, device side: multi-stream ring
+    "spectrogram_bank_create": (C.c_int, [C.POINTER(SpectrogramConfig), _u32, C.POINTER(_vp)]),
+    "spectrogram_bank_destroy": (None, [_vp]),
+    "spectrogram_bank_reset_audio": (C.c_int, [_vp]),
+    "spectrogram_bank_push": (C.c_int, [_vp, _f32p, _u64, _sz, _u32, C.c_float, _u8p, C.POINTER(SpectrogramBankUpdate)]),
+    "spectrogram_bank_pending": (_sz, [_vp]),
     # row f2: splat accumulation + resolve
     "splat_image_size": (None, [C.POINTER(SplatParams), _u32p, _u32p]),
     "splat_accumulate_device": (C.c_int, [_vp, _u64, _vp, _u32, C.POINTER(SplatParams), _vp, _vp]),

@@ -192,3 +192,65 @@ class Meter:
     @property
     def has_format(self) -> bool:
         return bool(self._api.meter_has_format(self._h))
+
+
+@dataclass
+class BankUpdate:
+    """S SpectrogramUpdates in dense form: columns[s] is the list of stream s's new columns ((n,3) float32 point arrays or
+    (bins,) uint16 code arrays), exactly what S separate SpectrogramProcessors would have returned."""
+
+    fft_size: int
+    hop_size: int
+    sample_rate: float
+    history_length: int
+    reset: bool
+    reassigned_power_scale: float
+    kind: int
+    columns: list
+
+
+class SpectrogramBank:
+    """Device-side multi-stream ring (row f1): S lock-step spectrogram streams, one kernel launch per push."""
+
+    def __init__(self, config, n_streams: int, api=None):
+        self._api = api or _default_api()
+        self._h = C.c_void_p()
+        self.n_streams = int(n_streams)
+        c = config.to_c()
+        _check(self._api, self._api.spectrogram_bank_create(C.byref(c), self.n_streams, C.byref(self._h)), "spectrogram_bank_create")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._api.spectrogram_bank_destroy(h)
+
+    def reset_audio(self) -> None:
+        _check(self._api, self._api.spectrogram_bank_reset_audio(self._h), "spectrogram_bank_reset_audio")
+
+    @property
+    def pending(self) -> int:
+        return int(self._api.spectrogram_bank_pending(self._h))
+
+    def push(self, blocks, channels: int = 1, sample_rate: float = 48000.0, positions=None, copy: bool = True) -> Optional[BankUpdate]:
+        """blocks: (S, frames * channels) float32, one interleaved block per stream."""
+        x = np.ascontiguousarray(blocks, np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.n_streams
+        frames = x.shape[1] // max(channels, 1)
+        up = capi.SpectrogramBankUpdate()
+        rc = _check(self._api, self._api.spectrogram_bank_push(self._h, _ptr(x), x.shape[1], frames, channels, sample_rate,
+                                                               capi.positions_array(positions), C.byref(up)), "spectrogram_bank_push")
+        if rc == capi.NO_DATA:
+            return None
+        S, n, bins = up.n_streams, up.n_columns, up.bins
+        cols = []
+        if up.kind == capi.COLUMN_REASSIGNED:
+            cnt = np.ctypeslib.as_array(up.counts, shape=(S, n))
+            pts = np.ctypeslib.as_array(C.cast(up.points, C.POINTER(C.c_float)), shape=(S, n, bins, 3))
+            if copy:
+                cols = [[pts[s, c, :cnt[s, c]].copy() for c in range(n)] for s in range(S)]
+            else:
+                cols = (cnt, pts)
+        else:
+            codes = np.ctypeslib.as_array(up.classic_db, shape=(S, n, bins))
+            cols = [[codes[s, c].copy() for c in range(n)] for s in range(S)] if copy else codes
+        return BankUpdate(up.fft_size, up.hop_size, up.sample_rate, up.history_length, bool(up.reset), up.reassigned_power_scale, up.kind, cols)

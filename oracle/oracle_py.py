@@ -51,7 +51,9 @@ _SHARED = [k for k in capi.HEADER_SYMBOLS if not (
     # host-side timeline logic: restated in Python (oracle/meter_py.py), not in the C++ oracle
     or k.startswith("timeline_") or k.startswith("meter_")
     # splat accumulation: restated in numpy (oracle/splat_py.py)
-    or k.startswith("splat_"))]
+    or k.startswith("splat_")
+    # the multi-stream bank is checked against S independent oracle processors
+    or k.startswith("spectrogram_bank_"))]
 
 
 def build(force: bool = False) -> str:

@@ -132,6 +132,42 @@ def main():
         res["splat_accumulate_resolve"] = dict(points_per_s=npts / t, ms=t * 1e3, algorithmic_bytes=b, achieved_gbs=b / t / 1e9, hbm_frac=b / t / 1e9 / PEAK,
                                                columns_per_s=R * hl / t)
         del pts, cnt, acc, db
+    if want("bank"):
+        # row f1: live ring-buffer input at many streams.  512 lock-step streams, DspBatcher-sized blocks (1024 stereo frames at
+        # 48 kHz), cfg2 analysis: one omb_spectrogram_bank_push per tick vs one omb_spectrogram_process_block per stream per tick.
+        import time
+        from openmeters_b200.meter import SpectrogramBank
+        from openmeters_b200.processors import AudioBlock, SpectrogramProcessor
+        cfgb = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True, history_length=64)
+        S, nf, ticks = 512, 1024, 24
+        rng = np.random.default_rng(0)
+        blocks = rng.uniform(-0.5, 0.5, (S, nf * 2)).astype(np.float32)
+        bank = SpectrogramBank(cfgb, S, api=api)
+        for _ in range(10):
+            bank.push(blocks, 2, 48000.0, copy=False)       # fills the first window (8 ticks) and warms up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cols = 0
+        for _ in range(ticks):
+            up = bank.push(blocks, 2, 48000.0, copy=False)
+            cols += S * up.columns[0].shape[1]
+        tb = time.perf_counter() - t0
+        S1 = 32
+        procs = [SpectrogramProcessor(cfgb, api=api) for _ in range(S1)]
+        blks = [AudioBlock(blocks[s], 2, 48000.0) for s in range(S1)]
+        for _ in range(10):
+            for p_, b_ in zip(procs, blks):
+                p_.process_block(b_)
+        t0 = time.perf_counter()
+        cols1 = 0
+        for _ in range(ticks):
+            for p_, b_ in zip(procs, blks):
+                cols1 += len(p_.process_block(b_).new_columns)
+        t1 = time.perf_counter() - t0
+        res["bank_cfg2_live_streams"] = dict(streams=S, block_frames=nf, columns_per_s=cols / tb, ms_per_tick=tb / ticks * 1e3,
+                                             realtime_streams=(cols / tb) / (48000.0 / 1024.0),
+                                             per_stream_handles=dict(streams=S1, columns_per_s=cols1 / t1, ms_per_tick=t1 / ticks * 1e3,
+                                                                     note="includes the Python mirror's per-column copies"))
     print(json.dumps(res))
 
 
