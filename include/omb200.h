@@ -321,7 +321,8 @@ int omb_spectrum_plan_create(const omb_spectrum_config* cfg, omb_spectrum_plan**
 void omb_spectrum_plan_destroy(omb_spectrum_plan* p);
 /* Every lane is one trace with its own smoothing state (zero-initialised).
  * out_weighted/out_raw: [(l*hops + h)*bins + k] f32; out_peak_bin (may be NULL):
- * [(l*hops+h)] argmax of raw over bins 1..bins-2, last max wins (state.rs:321-325), -1 if none. */
+ * [(l*hops+h)] peak_bin of the plan's peak spec (below; default: A-weighted trace, 20 Hz..Nyquist), last max wins
+ * (state.rs:321-325), -1 if none. */
 int omb_spectrum_execute_device(omb_spectrum_plan* p, const float* d_lanes, uint32_t n_lanes,
                                 uint64_t samples_per_lane, uint64_t lane_stride,
                                 float* d_out_weighted, float* d_out_raw, int32_t* d_out_peak_bin,
@@ -329,6 +330,37 @@ int omb_spectrum_execute_device(omb_spectrum_plan* p, const float* d_lanes, uint
 int omb_spectrum_execute_host(omb_spectrum_plan* p, const float* h_lanes, uint32_t n_lanes,
                               uint64_t samples_per_lane, uint64_t lane_stride,
                               float* h_out_weighted, float* h_out_raw, int32_t* h_out_peak_bin);
+
+/* Row f3 — the peak label of the spectrum view (spectrum/state.rs:98-140, 180-205, 321-356).
+ *
+ * peak_bin(bins, db, min_f, max_f) (state.rs:321-325): arg-max of the selected trace over bins 1..bins-2 whose
+ * frequency lies in [min_hz, max_hz] and whose dB value is finite; the LAST maximum wins (Iterator::max_by with
+ * total_cmp). apply_snapshot (state.rs:106-107,134-136) calls it with min_f = MIN_FREQUENCY = 20 Hz,
+ * max_f = frequency_bins[last].max(min_f * 1.02) on trace_db(traces[primary], weighting_mode), whose default is
+ * A-weighted (visuals.rs:98). That is the default spec of every plan; the arg-max itself is fused into the
+ * smoothing epilogue (out_peak_bin of omb_spectrum_execute_*). */
+typedef struct omb_spectrum_peak_spec {
+  uint32_t trace;  /* 0 = A-weighted trace (default), 1 = raw trace: SpectrumWeightingMode, state.rs:426-431 */
+  float min_hz;    /* default 20 (state.rs:21) */
+  float max_hz;    /* <= 0 (default): frequency_bins[last].max(min_hz * 1.02) (state.rs:107) */
+} omb_spectrum_peak_spec;
+void omb_spectrum_default_peak_spec(omb_spectrum_peak_spec* out);
+int omb_spectrum_plan_set_peak_spec(omb_spectrum_plan* p, const omb_spectrum_peak_spec* spec);
+int omb_spectrum_plan_get_peak_spec(const omb_spectrum_plan* p, omb_spectrum_peak_spec* out);
+
+/* interpolated_peak(bins, db, bin) (state.rs:327-356): parabolic refinement of a peak bin from its two
+ * neighbours, in the reference's f32 operation order. d_db: one dB trace [rows][bins] (the one the peak bins were
+ * taken from); d_peak_bin: [rows]. Outputs [rows]: frequency in Hz (>= 0) and level in dB; both NaN where the
+ * reference returns None (bin < 1, bin + 1 >= bins, non-finite centre value). */
+int omb_spectrum_interpolate_peaks_device(omb_spectrum_plan* p, const float* d_db, const int32_t* d_peak_bin,
+                                          uint64_t rows, float* d_out_freq_hz, float* d_out_level_db,
+                                          void* cuda_stream);
+/* omb_spectrum_execute_host + the interpolated peaks of the plan's peak spec, taken on the device before the
+ * traces are copied back. Any of the three peak outputs may be NULL. */
+int omb_spectrum_execute_host_peaks(omb_spectrum_plan* p, const float* h_lanes, uint32_t n_lanes,
+                                    uint64_t samples_per_lane, uint64_t lane_stride,
+                                    float* h_out_weighted, float* h_out_raw, int32_t* h_out_peak_bin,
+                                    float* h_out_peak_freq_hz, float* h_out_peak_level_db);
 
 typedef struct omb_loudness_plan omb_loudness_plan;
 

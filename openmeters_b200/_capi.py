@@ -87,6 +87,11 @@ class SpectrumSnapshot(C.Structure):
     ]
 
 
+class SpectrumPeakSpec(C.Structure):
+    """omb_spectrum_peak_spec: trace 0 = A-weighted / 1 = raw; min_hz; max_hz <= 0 -> Nyquist (state.rs:106-107)."""
+    _fields_ = [("trace", C.c_uint32), ("min_hz", C.c_float), ("max_hz", C.c_float)]
+
+
 class LoudnessConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_float), ("floor_db", C.c_float)]
 
@@ -218,6 +223,12 @@ HEADER_SYMBOLS = {
     "spectrum_plan_destroy": (None, [_vp]),
     "spectrum_execute_device": (C.c_int, [_vp, _vp, _u32, _u64, _u64, _vp, _vp, _vp, _vp]),
     "spectrum_execute_host": (C.c_int, [_vp, _vp, _u32, _u64, _u64, _vp, _vp, _vp]),
+    # row f3: peak label (peak_bin range / trace selection, interpolated_peak)
+    "spectrum_default_peak_spec": (None, [C.POINTER(SpectrumPeakSpec)]),
+    "spectrum_plan_set_peak_spec": (C.c_int, [_vp, C.POINTER(SpectrumPeakSpec)]),
+    "spectrum_plan_get_peak_spec": (C.c_int, [_vp, C.POINTER(SpectrumPeakSpec)]),
+    "spectrum_interpolate_peaks_device": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "spectrum_execute_host_peaks": (C.c_int, [_vp, _vp, _u32, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "loudness_plan_create": (C.c_int, [C.POINTER(LoudnessConfig), _u32, _u8p, C.POINTER(_vp)]),
     "loudness_plan_destroy": (None, [_vp]),
     "loudness_execute_device": (C.c_int, [_vp, _vp, _u32, _u64, _u64, _u64, _vp, _vp]),

@@ -85,6 +85,36 @@ class SpectrumPlan:
                                                           pk.ctypes.data if want_peak else None), "spectrum_execute_host")
         return w, r, pk
 
+    def set_peak_spec(self, trace: int = 0, min_hz: float = 20.0, max_hz: float = 0.0) -> None:
+        """Peak label spec (spectrum/state.rs:106-107,134-136): trace 0 = A-weighted / 1 = raw, candidate range in Hz
+        (max_hz <= 0: up to the last bin)."""
+        spec = capi.SpectrumPeakSpec(trace, min_hz, max_hz)
+        _check(self._api, self._api.spectrum_plan_set_peak_spec(self._h, C.byref(spec)), "spectrum_plan_set_peak_spec")
+
+    def peak_spec(self):
+        spec = capi.SpectrumPeakSpec()
+        _check(self._api, self._api.spectrum_plan_get_peak_spec(self._h, C.byref(spec)), "spectrum_plan_get_peak_spec")
+        return int(spec.trace), float(spec.min_hz), float(spec.max_hz)
+
+    def execute_host_peaks(self, lanes: np.ndarray):
+        """execute_host + interpolated_peak (state.rs:327-356) of every hop -> (weighted, raw, peak_bin, freq_hz, level_db)."""
+        lanes = np.ascontiguousarray(lanes, np.float32)
+        L, S = lanes.shape
+        H = self.hops_per_lane(S)
+        w = np.zeros((L, H, self.bins), np.float32)
+        r = np.zeros((L, H, self.bins), np.float32)
+        pk = np.full((L, H), -1, np.int32)
+        f = np.full((L, H), np.nan, np.float32)
+        m = np.full((L, H), np.nan, np.float32)
+        _check(self._api, self._api.spectrum_execute_host_peaks(self._h, lanes.ctypes.data, L, S, S, w.ctypes.data, r.ctypes.data,
+                                                                pk.ctypes.data, f.ctypes.data, m.ctypes.data),
+               "spectrum_execute_host_peaks")
+        return w, r, pk, f, m
+
+    def interpolate_peaks_device(self, db_ptr: int, peak_ptr: int, rows: int, freq_ptr: int, level_ptr: int, stream: int = 0) -> None:
+        _check(self._api, self._api.spectrum_interpolate_peaks_device(self._h, db_ptr, peak_ptr, rows, freq_ptr, level_ptr,
+                                                                      stream or None), "spectrum_interpolate_peaks_device")
+
     def execute_device(self, lanes_ptr: int, n_lanes: int, samples: int, lane_stride: int, weighted_ptr: int, raw_ptr: int,
                        peak_ptr: int = 0, stream: int = 0) -> None:
         _check(self._api, self._api.spectrum_execute_device(self._h, lanes_ptr, n_lanes, samples, lane_stride, weighted_ptr,

@@ -285,6 +285,40 @@ int omb_spectrum_execute_host(omb_spectrum_plan* p, const float* h_lanes, uint32
   OMB_GUARD_END
 }
 
+void omb_spectrum_default_peak_spec(omb_spectrum_peak_spec* out) {
+  if (!out) return;
+  out->trace = 0u;      // SpectrumWeightingMode::AWeighted (visuals.rs:98)
+  out->min_hz = 20.0f;  // MIN_FREQUENCY (spectrum/state.rs:21)
+  out->max_hz = 0.0f;   // frequency_bins[last].max(min * 1.02) (state.rs:107)
+}
+int omb_spectrum_plan_set_peak_spec(omb_spectrum_plan* p, const omb_spectrum_peak_spec* spec) {
+  OMB_GUARD_BEGIN
+  if (!p || !spec) return fail(OMB_ERR_INVALID, "null argument");
+  return p->p.set_peak_spec(*spec);
+  OMB_GUARD_END
+}
+int omb_spectrum_plan_get_peak_spec(const omb_spectrum_plan* p, omb_spectrum_peak_spec* out) {
+  if (!p || !out) return fail(OMB_ERR_INVALID, "null argument");
+  *out = p->p.peak_spec;
+  return OMB_OK;
+}
+int omb_spectrum_interpolate_peaks_device(omb_spectrum_plan* p, const float* d_db, const int32_t* d_peak_bin, uint64_t rows,
+                                          float* d_out_freq_hz, float* d_out_level_db, void* cuda_stream) {
+  OMB_GUARD_BEGIN
+  if (!p) return fail(OMB_ERR_INVALID, "null plan");
+  return p->p.interpolate_peaks_device(d_db, d_peak_bin, rows, d_out_freq_hz, d_out_level_db, (cudaStream_t)cuda_stream);
+  OMB_GUARD_END
+}
+int omb_spectrum_execute_host_peaks(omb_spectrum_plan* p, const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane,
+                                    uint64_t lane_stride, float* h_out_weighted, float* h_out_raw, int32_t* h_out_peak_bin,
+                                    float* h_out_peak_freq_hz, float* h_out_peak_level_db) {
+  OMB_GUARD_BEGIN
+  if (!p) return fail(OMB_ERR_INVALID, "null plan");
+  return p->p.execute_host(h_lanes, n_lanes, samples_per_lane, lane_stride, h_out_weighted, h_out_raw, h_out_peak_bin, h_out_peak_freq_hz,
+                           h_out_peak_level_db);
+  OMB_GUARD_END
+}
+
 // ---- batched loudness
 int omb_loudness_plan_create(const omb_loudness_config* cfg, uint32_t channels, const uint8_t positions[OMB_MAX_CHANNELS],
                              omb_loudness_plan** out) {

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_smooth(SpectrumSmoothArgs
   if (live && a.state && a.mode != OMB_AVG_NONE) st = a.state[(uint64_t)lane * a.bins + k];
   const float aw = live ? __ldg(&a.a_db[k]) : 0.0f;
   const float one_minus_alpha = __fsub_rn(1.0f, a.alpha);
-  const bool interior = live && k >= 1 && k + 1 < (int)a.bins;
+  const bool interior = live && k >= a.peak_lo && k <= a.peak_hi;  // peak_bin candidates (state.rs:321-324)
   constexpr int kAhead = 8;
   for (uint64_t h0 = 0; h0 < a.hops; h0 += kAhead) {
     // the recurrence is sequential over hops, the loads are not: fetch kAhead hops of power before using them
@@ -166,9 +166,10 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_smooth(SpectrumSmoothArgs
           a.out_raw[o] = raw;
         }
       }
-      if (a.peak_keys && emit) {  // spectrum/state.rs:321-325: bins 1..len-2, finite, last maximum wins
+      if (a.peak_keys && emit) {  // spectrum/state.rs:321-325: bins 1..len-2 inside [min_f, max_f], finite, last maximum wins
         // two warp-wide integer max reductions (REDUX): the largest ordered dB value, then the largest bin holding it
-        const unsigned ob = (interior && isfinite(raw)) ? ordered_bits(raw) : 0u;
+        const float pv = a.peak_raw ? raw : weighted;
+        const unsigned ob = (interior && isfinite(pv)) ? ordered_bits(pv) : 0u;
         const unsigned best = __reduce_max_sync(0xffffffffu, ob);
         const unsigned bin = __reduce_max_sync(0xffffffffu, (ob == best) ? (unsigned)k : 0u);
         if (lane_id == 0 && best)
@@ -177,6 +178,36 @@ __global__ void __launch_bounds__(kThreads) k_spectrum_smooth(SpectrumSmoothArgs
     }
   }
   if (live && a.state && a.mode != OMB_AVG_NONE) a.state[(uint64_t)lane * a.bins + k] = st;
+}
+
+// interpolated_peak (spectrum/state.rs:327-356), one thread per row; every operation is a separately rounded f32
+// operation in the reference's order (no contraction), so identical dB inputs give identical bits.
+__global__ void k_peak_interpolate(const float* db, const int32_t* peak_bin, uint64_t rows, uint32_t bins, float bin_hz, float* out_freq,
+                                   float* out_level) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float nan = __int_as_float(0x7fc00000);
+  float freq = nan, level = nan;
+  const int32_t bin = peak_bin[i];
+  // :328-337 — bin == 0 or no right neighbour, unusable bin spacing, non-finite centre => None
+  if (bin >= 1 && (uint32_t)bin + 1u < bins && isfinite(bin_hz) && bin_hz > 0.0f) {
+    const float* row = db + i * (uint64_t)bins;
+    const float center = row[bin];
+    const float center_freq = __fmul_rn((float)bin, bin_hz);  // frequency_bins[bin] (spectrum/processor.rs:141-146)
+    if (isfinite(center) && isfinite(center_freq)) {
+      const float left = row[bin - 1], right = row[bin + 1];
+      float offset = 0.0f;
+      if (isfinite(left) && isfinite(right)) {  // :340-350
+        const float denom = __fadd_rn(__fsub_rn(left, __fmul_rn(2.0f, center)), right);
+        if (denom < -1e-6f) offset = fminf(fmaxf(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(left, right)), denom), -0.5f), 0.5f);
+      }
+      level = offset == 0.0f ? center  // :351-355
+                             : fmaxf(__fsub_rn(center, __fmul_rn(__fmul_rn(0.25f, __fsub_rn(left, right)), offset)), center);
+      freq = fmaxf(__fadd_rn(center_freq, __fmul_rn(offset, bin_hz)), 0.0f);
+    }
+  }
+  out_freq[i] = freq;
+  out_level[i] = level;
 }
 
 __global__ void k_peak_keys_to_bins(const unsigned long long* keys, uint64_t n, int32_t* out) {
@@ -236,6 +267,7 @@ int SpectrumPlan::init(const omb_spectrum_config& c) {
     h_adb[b] = a_weight_host(h_freq[b]);
   }
   state_floor = smoothing_state_floor_host(h_adb, cfg.floor_db);
+  OMB_TRY(set_peak_spec(peak_spec));
   OMB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   OMB_TRY(d_win.upload(h_win, stream));
   OMB_TRY(d_norm.upload(h_norm, stream));
@@ -311,6 +343,9 @@ static int smooth_launch(SpectrumPlan& p, const float* d_power_in, uint32_t n_la
   a.out_raw = d_raw;
   a.write_all = write_all ? 1 : 0;
   a.peak_keys = keys;  // caller-owned [n_lanes * hops_total], zeroed
+  a.peak_raw = p.peak_spec.trace == 1u ? 1 : 0;
+  a.peak_lo = p.peak_lo;
+  a.peak_hi = p.peak_hi;
   if (keys && !write_all) return fail(OMB_ERR_INVALID, "peak bins are only produced together with per-hop outputs");
   SmoothLayout lay{hops_total, hop0};
   const dim3 grid((unsigned)((a.bins + kThreads - 1) / kThreads), n_lanes);
@@ -385,8 +420,42 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
   return OMB_OK;
 }
 
+// Resolves the peak spec to the inclusive bin range the kernels filter on, with the reference's f32 comparisons:
+// i in 1..bins-1 (exclusive) with (min_f..=max_f).contains(&frequency_bins[i]) (state.rs:106-107,321-324).
+int SpectrumPlan::set_peak_spec(const omb_spectrum_peak_spec& spec) {
+  if (spec.trace > 1u) return fail(OMB_ERR_INVALID, "peak spec: trace must be 0 (A-weighted) or 1 (raw)");
+  peak_spec = spec;
+  peak_lo = 1;
+  peak_hi = 0;
+  const size_t bins = h_freq.size();
+  if (bins < 3) return OMB_OK;
+  const float min_f = spec.min_hz;
+  const float max_f = spec.max_hz > 0.0f ? spec.max_hz : std::fmax(h_freq[bins - 1], min_f * 1.02f);
+  // frequency_bins is non-decreasing, so the members of the range are contiguous
+  int lo = -1, hi = -1;
+  for (size_t i = 1; i + 1 < bins; ++i)
+    if (h_freq[i] >= min_f && h_freq[i] <= max_f) {
+      if (lo < 0) lo = (int)i;
+      hi = (int)i;
+    }
+  if (lo >= 0) { peak_lo = lo; peak_hi = hi; }
+  return OMB_OK;
+}
+
+int SpectrumPlan::interpolate_peaks_device(const float* d_db, const int32_t* d_peak_bin, uint64_t rows, float* d_freq, float* d_level,
+                                           cudaStream_t s) {
+  if (!rows) return OMB_OK;
+  if (!d_db || !d_peak_bin || !d_freq || !d_level) return fail(OMB_ERR_INVALID, "null argument");
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));
+  const float bin_hz = h_freq.size() > 1 ? h_freq[1] - h_freq[0] : 0.0f;  // state.rs:330
+  OMB_LAUNCH(k_peak_interpolate, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, s, d_db, d_peak_bin, rows, (uint32_t)cfg.bins(), bin_hz,
+             d_freq, d_level);
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
 int SpectrumPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
-                               float* h_weighted, float* h_raw, int32_t* h_peak_bin) {
+                               float* h_weighted, float* h_raw, int32_t* h_peak_bin, float* h_peak_freq, float* h_peak_level) {
   const uint64_t hops = cfg.hops_for(samples_per_lane);
   if (!hops || !n_lanes) return OMB_OK;
   if (!h_lanes || !h_weighted || !h_raw) return fail(OMB_ERR_INVALID, "null argument");
@@ -397,8 +466,20 @@ int SpectrumPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t 
   const uint64_t n = hops * n_lanes * cfg.bins();
   OMB_TRY(d_w.reserve((size_t)n));
   OMB_TRY(d_r.reserve((size_t)n));
-  if (h_peak_bin) OMB_TRY(d_peak.reserve((size_t)(hops * n_lanes)));
-  OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, d_w.ptr, d_r.ptr, h_peak_bin ? d_peak.ptr : nullptr, stream));
+  const bool want_interp = h_peak_freq || h_peak_level;
+  const bool want_bins = h_peak_bin || want_interp;
+  if (want_bins) OMB_TRY(d_peak.reserve((size_t)(hops * n_lanes)));
+  OMB_TRY(execute_device(d_in.ptr, n_lanes, samples_per_lane, samples_per_lane, d_w.ptr, d_r.ptr, want_bins ? d_peak.ptr : nullptr, stream));
+  if (want_interp) {
+    OMB_TRY(d_peak_freq.reserve((size_t)(hops * n_lanes)));
+    OMB_TRY(d_peak_level.reserve((size_t)(hops * n_lanes)));
+    OMB_TRY(interpolate_peaks_device(peak_spec.trace == 1u ? d_r.ptr : d_w.ptr, d_peak.ptr, hops * n_lanes, d_peak_freq.ptr, d_peak_level.ptr,
+                                     stream));
+    if (h_peak_freq)
+      OMB_CUDA_TRY(cudaMemcpyAsync(h_peak_freq, d_peak_freq.ptr, sizeof(float) * hops * n_lanes, cudaMemcpyDeviceToHost, stream));
+    if (h_peak_level)
+      OMB_CUDA_TRY(cudaMemcpyAsync(h_peak_level, d_peak_level.ptr, sizeof(float) * hops * n_lanes, cudaMemcpyDeviceToHost, stream));
+  }
   OMB_CUDA_TRY(cudaMemcpyAsync(h_weighted, d_w.ptr, sizeof(float) * n, cudaMemcpyDeviceToHost, stream));
   OMB_CUDA_TRY(cudaMemcpyAsync(h_raw, d_r.ptr, sizeof(float) * n, cudaMemcpyDeviceToHost, stream));
   if (h_peak_bin) OMB_CUDA_TRY(cudaMemcpyAsync(h_peak_bin, d_peak.ptr, sizeof(int32_t) * hops * n_lanes, cudaMemcpyDeviceToHost, stream));

@@ -47,8 +47,10 @@ struct SpectrumSmoothArgs {
   float* state;        // [lane*bins] smoothed power, in/out (may be null for mode None)
   float* out_weighted; // write_all: [(lane*hops+h)*bins+k], else [lane*bins+k] (last hop only)
   float* out_raw;
-  unsigned long long* peak_keys;  // [(lane*hops+h)] packed (ordered raw dB, bin) or null
+  unsigned long long* peak_keys;  // [(lane*hops+h)] packed (ordered dB of the peak trace, bin) or null
   int write_all;
+  int peak_raw;        // peak spec: 1 = raw trace, 0 = weighted trace
+  int peak_lo, peak_hi;  // peak spec: candidate bins peak_lo..peak_hi (inclusive; empty if lo > hi)
 };
 
 struct SpectrumPlan {
@@ -70,7 +72,13 @@ struct SpectrumPlan {
   // host-path staging
   DeviceBuffer<float> d_in, d_w, d_r;
   DeviceBuffer<int32_t> d_peak;
+  DeviceBuffer<float> d_peak_freq, d_peak_level;
   cudaStream_t stream = nullptr;
+  // row f3: peak label spec (spectrum/state.rs:106-107,134-136,321-325) resolved to a bin range on the host
+  omb_spectrum_peak_spec peak_spec{0u, 20.0f, 0.0f};
+  int peak_lo = 1, peak_hi = 0;
+  int set_peak_spec(const omb_spectrum_peak_spec& spec);
+  int interpolate_peaks_device(const float* d_db, const int32_t* d_peak_bin, uint64_t rows, float* d_freq, float* d_level, cudaStream_t s);
 
   ~SpectrumPlan();
   int init(const omb_spectrum_config& c);
@@ -82,7 +90,7 @@ struct SpectrumPlan {
   int execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride, float* d_weighted,
                      float* d_raw, int32_t* d_peak_bin, cudaStream_t s);
   int execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride, float* h_weighted,
-                   float* h_raw, int32_t* h_peak_bin);
+                   float* h_raw, int32_t* h_peak_bin, float* h_peak_freq = nullptr, float* h_peak_level = nullptr);
 };
 
 // spectrum_fast.cu

@@ -166,6 +166,7 @@ struct SpecFusedArgs {
   float* out_weighted;                         // [(lane * hops + h) * 8193 + k]
   float* out_raw;
   int32_t* peak_bin;                           // [lane * hops + h] or null
+  int peak_raw, peak_lo, peak_hi;              // peak spec (spectrum.h): trace selector and inclusive candidate bin range
   int mode;
   float alpha, decay, state_floor, floor_db;
   float norm_ac, norm_dc;
@@ -253,8 +254,9 @@ __device__ __forceinline__ void fused_bin(const SpecFusedArgs& fa, float p, floa
   const float weighted = below ? fa.floor_db : fmaxf(__fadd_rn(db, aw), fa.floor_db);
   ow[bin] = weighted;
   orw[bin] = raw;
-  const bool interior = bin >= 1 && bin + 1 < kN / 2 + 1;
-  const unsigned ob = (interior && isfinite(raw)) ? f_ordered_bits(raw) : 0u;
+  const bool interior = bin >= fa.peak_lo && bin <= fa.peak_hi;
+  const float pv = fa.peak_raw ? raw : weighted;
+  const unsigned ob = (interior && isfinite(pv)) ? f_ordered_bits(pv) : 0u;
   const bool take = ob > best || (ob == best && (unsigned)bin > best_bin);
   best = take ? ob : best;
   best_bin = take ? (unsigned)bin : best_bin;
@@ -474,6 +476,9 @@ int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lane
   fa.out_weighted = d_weighted;
   fa.out_raw = d_raw;
   fa.peak_bin = d_peak_bin;
+  fa.peak_raw = p.peak_spec.trace == 1u ? 1 : 0;
+  fa.peak_lo = p.peak_lo;
+  fa.peak_hi = p.peak_hi;
   fa.mode = (int)cfg.averaging;
   fa.alpha = std::min(std::max(cfg.averaging_param, 0.0f), 0.9999f);
   fa.decay = db_to_power_host(-std::fmax(cfg.averaging_param, 0.0f) * ((float)cfg.hop / cfg.sample_rate));

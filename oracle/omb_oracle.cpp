@@ -1401,6 +1401,65 @@ uint64_t ombo_spectrum_hops_per_lane(const omb_spectrum_config* cfg, uint64_t sa
   return samples >= c.fft_size ? (samples - c.fft_size) / c.hop_size + 1 : 0;
 }
 
+// spectrum/state.rs:321-325 — (1..len-1).filter(in [min_f, max_f] && finite).max_by(total_cmp): the last maximum wins.
+static int32_t peak_bin(const float* bins_hz, const float* db, size_t n, float min_f, float max_f) {
+  int32_t best = -1;
+  for (size_t i = 1; i + 1 < n; ++i) {
+    if (!(bins_hz[i] >= min_f && bins_hz[i] <= max_f) || !std::isfinite(db[i])) continue;
+    if (best < 0) { best = (int32_t)i; continue; }
+    // total_cmp on finite values: numeric order, and -0.0 < +0.0
+    const float a = db[i], b = db[(size_t)best];
+    const bool less = a < b || (a == b && std::signbit(a) && !std::signbit(b));
+    if (!less) best = (int32_t)i;
+  }
+  return best;
+}
+
+// spectrum/state.rs:327-356 — returns false for None.
+static bool interpolated_peak(const float* bins_hz, const float* db, size_t n, int64_t bin, float* out_freq, float* out_level) {
+  const float kEps = 1e-6f;  // state.rs:20
+  if (bin <= 0 || (size_t)bin + 1 >= n) return false;
+  const float bin_hz = bins_hz[1] - bins_hz[0];
+  const float center_freq = bins_hz[bin], center = db[bin];
+  if (!(std::isfinite(bin_hz) && bin_hz > 0.0f) || !std::isfinite(center_freq) || !std::isfinite(center)) return false;
+  const float left = db[bin - 1], right = db[bin + 1];
+  float offset = 0.0f;
+  if (std::isfinite(left) && std::isfinite(right)) {
+    const float denom = left - 2.0f * center + right;
+    if (denom < -kEps) offset = std::fmin(std::fmax(0.5f * (left - right) / denom, -0.5f), 0.5f);
+  }
+  const float level = offset == 0.0f ? center : std::fmax(center - 0.25f * (left - right) * offset, center);
+  *out_freq = std::fmax(center_freq + offset * bin_hz, 0.0f);
+  *out_level = level;
+  return true;
+}
+
+// peak_bin + interpolated_peak over `rows` rows of one dB trace [rows][n_bins]; NaN outputs where the reference has None.
+int ombo_spectrum_peaks(const float* bins_hz, const float* db, uint32_t n_bins, uint64_t rows, float min_f, float max_f, int32_t* out_bin,
+                        float* out_freq, float* out_level) {
+  for (uint64_t r = 0; r < rows; ++r) {
+    const float* row = db + r * n_bins;
+    const int32_t b = peak_bin(bins_hz, row, n_bins, min_f, max_f);
+    float f = std::nanf(""), m = std::nanf("");
+    if (b >= 0) interpolated_peak(bins_hz, row, n_bins, b, &f, &m);
+    if (out_bin) out_bin[r] = b;
+    if (out_freq) out_freq[r] = f;
+    if (out_level) out_level[r] = m;
+  }
+  return OMB_OK;
+}
+// interpolated_peak alone, for given bins (to check a device result on the device's own dB values bit for bit).
+int ombo_spectrum_interpolate_peaks(const float* bins_hz, const float* db, uint32_t n_bins, uint64_t rows, const int32_t* bin,
+                                    float* out_freq, float* out_level) {
+  for (uint64_t r = 0; r < rows; ++r) {
+    float f = std::nanf(""), m = std::nanf("");
+    interpolated_peak(bins_hz, db + r * n_bins, n_bins, bin[r], &f, &m);
+    out_freq[r] = f;
+    out_level[r] = m;
+  }
+  return OMB_OK;
+}
+
 int ombo_spectrum_batch(const omb_spectrum_config* cfg, const float* lanes, uint32_t n_lanes, uint64_t samples_per_lane,
                         uint64_t lane_stride, float* out_weighted, float* out_raw, int32_t* out_peak_bin, int threads) {
   SpectrumConfig c = from_c(*cfg);
@@ -1422,14 +1481,9 @@ int ombo_spectrum_batch(const omb_spectrum_config* cfg, const float* lanes, uint
       const uint64_t slot = lane * hops + h;
       std::copy(p.traces[0][0].begin(), p.traces[0][0].end(), out_weighted + slot * bins);
       std::copy(p.traces[0][1].begin(), p.traces[0][1].end(), out_raw + slot * bins);
-      if (out_peak_bin) {  // spectrum/state.rs:321-325 with the full frequency range: last max wins
-        int32_t best = -1;
-        const auto& db = p.traces[0][1];
-        for (size_t i = 1; i + 1 < bins; ++i) {
-          if (!std::isfinite(db[i])) continue;
-          if (best < 0 || !(db[i] < db[(size_t)best])) best = (int32_t)i;
-        }
-        out_peak_bin[slot] = best;
+      if (out_peak_bin) {  // spectrum/state.rs:106-107,134-136: the default peak label (A-weighted trace, 20 Hz..)
+        const float min_f = 20.0f, max_f = std::fmax(p.freq_bins[bins - 1], min_f * 1.02f);
+        out_peak_bin[slot] = peak_bin(p.freq_bins.data(), p.traces[0][0].data(), bins, min_f, max_f);
       }
     }
   });

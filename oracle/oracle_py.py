@@ -39,6 +39,8 @@ EXTRA = {
     "stft_batch": (C.c_int, [C.POINTER(capi.SpectrogramConfig), _vp, _u32, _u64, _u64, _vp, _u64, _vp, _vp,
                              C.c_int, _u64, _u64]),
     "spectrum_batch": (C.c_int, [C.POINTER(capi.SpectrumConfig), _vp, _u32, _u64, _u64, _vp, _vp, _vp, C.c_int]),
+    "spectrum_peaks": (C.c_int, [_vp, _vp, _u32, _u64, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "spectrum_interpolate_peaks": (C.c_int, [_vp, _vp, _u32, _u64, _vp, _vp, _vp]),
     "loudness_batch": (C.c_int, [C.POINTER(capi.LoudnessConfig), _u32, _u8p, _vp, _u32, _u64, _u64, _u64, _vp,
                                  C.c_int]),
 }
@@ -48,6 +50,7 @@ _SHARED = [k for k in capi.HEADER_SYMBOLS if not (
     k in ("last_error", "device_count", "set_device", "kernel_launch_count") or k.startswith("stft_plan")
     or k.startswith("stft_execute") or k.startswith("spectrum_plan") or k.startswith("spectrum_execute")
     or k.startswith("loudness_plan") or k.startswith("loudness_execute")
+    or k in ("spectrum_default_peak_spec", "spectrum_interpolate_peaks_device")
     # host-side timeline logic: restated in Python (oracle/meter_py.py), not in the C++ oracle
     or k.startswith("timeline_") or k.startswith("meter_")
     # splat accumulation: restated in numpy (oracle/splat_py.py)
@@ -126,6 +129,40 @@ def spectrum_batch(cfg, lanes: np.ndarray, threads: int = 0, want_peak: bool = T
                           pk.ctypes.data if want_peak else None, threads)
     assert rc == 0
     return w, r, pk
+
+
+def spectrum_frequency_bins(sample_rate: float, fft_size: int) -> np.ndarray:
+    """frequency_bins of a SpectrumSnapshot: bin as f32 * (sample_rate / fft_size as f32) (spectrum/processor.rs:138-146)."""
+    bin_hz = np.float32(sample_rate) / np.float32(fft_size)
+    return (np.arange(fft_size // 2 + 1, dtype=np.float32) * bin_hz).astype(np.float32)
+
+
+def spectrum_peaks(bins_hz: np.ndarray, db: np.ndarray, min_hz: float = 20.0, max_hz: float | None = None):
+    """peak_bin + interpolated_peak (spectrum/state.rs:321-356) per row of db[..., bins] -> (bin, freq_hz, level_db)."""
+    a = api()
+    bins_hz = np.ascontiguousarray(bins_hz, np.float32)
+    db = np.ascontiguousarray(db, np.float32)
+    n = db.shape[-1]
+    rows = db.size // n if n else 0
+    if max_hz is None or max_hz <= 0:
+        max_hz = float(max(bins_hz[-1], np.float32(min_hz) * np.float32(1.02)))  # state.rs:107
+    b = np.zeros(db.shape[:-1], np.int32)
+    f = np.zeros(db.shape[:-1], np.float32)
+    m = np.zeros(db.shape[:-1], np.float32)
+    assert a.spectrum_peaks(bins_hz.ctypes.data, db.ctypes.data, n, rows, min_hz, max_hz, b.ctypes.data, f.ctypes.data, m.ctypes.data) == 0
+    return b, f, m
+
+
+def spectrum_interpolate_peaks(bins_hz: np.ndarray, db: np.ndarray, peak_bin: np.ndarray):
+    a = api()
+    bins_hz = np.ascontiguousarray(bins_hz, np.float32)
+    db = np.ascontiguousarray(db, np.float32)
+    pk = np.ascontiguousarray(peak_bin, np.int32)
+    n = db.shape[-1]
+    f = np.zeros(pk.shape, np.float32)
+    m = np.zeros(pk.shape, np.float32)
+    assert a.spectrum_interpolate_peaks(bins_hz.ctypes.data, db.ctypes.data, n, pk.size, pk.ctypes.data, f.ctypes.data, m.ctypes.data) == 0
+    return f, m
 
 
 def loudness_batch(cfg, channels: int, positions, streams: np.ndarray, block_frames: int, threads: int = 0):

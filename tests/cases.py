@@ -26,9 +26,20 @@ def stft_parity(api, cfg: SpectrogramConfig, lanes: np.ndarray, kernel=capi.KERN
     return parity.compare_classic(a, b)
 
 
+def _peak_rows_agree(pka, pkb, db_ref, what):
+    """Peak bins: exact, except where the two candidates are within 1e-4 dB of each other in the reference trace
+    (FFT rounding decides between near-ties)."""
+    diff = pka != pkb
+    for idx in zip(*np.nonzero(diff)):
+        a, b = int(pka[idx]), int(pkb[idx])
+        assert a >= 0 and b >= 0, (what, idx, a, b)
+        assert abs(db_ref[idx + (a,)] - db_ref[idx + (b,)]) < 1e-4, (what, idx, a, b)
+    return int(diff.sum())
+
+
 def spectrum_parity(api, cfg: SpectrumConfig, lanes: np.ndarray):
     plan = batch.SpectrumPlan(cfg, api=api)
-    wa, ra, pka = plan.execute_host(lanes)
+    wa, ra, pka, fa, la = plan.execute_host_peaks(lanes)
     wb, rb, pkb = oracle_py.spectrum_batch(cfg, lanes)
     assert wa.shape == wb.shape
     st = parity.compare_db(ra, rb, cfg.floor_db)
@@ -36,12 +47,34 @@ def spectrum_parity(api, cfg: SpectrumConfig, lanes: np.ndarray):
     # floor membership must agree except within 1e-3 dB of the floor edge
     edge = np.abs(rb - cfg.floor_db) < 1e-3
     assert np.array_equal((ra == cfg.floor_db) | edge, (rb == cfg.floor_db) | edge) or np.mean((ra == cfg.floor_db) != (rb == cfg.floor_db)) < 1e-3
-    # peak bin: exact, except where the two top raw values are within 1e-4 dB of each other (FFT rounding decides)
-    diff = pka != pkb
-    if diff.any():
-        for l, h in zip(*np.nonzero(diff)):
-            assert abs(rb[l, h, pka[l, h]] - rb[l, h, pkb[l, h]]) < 1e-4, (l, h, pka[l, h], pkb[l, h])
-    st["peak_mismatch"] = int(diff.sum())
+    # row f3, default peak spec (spectrum/state.rs:106-107,134-136): A-weighted trace, 20 Hz .. last bin
+    freqs = oracle_py.spectrum_frequency_bins(cfg.sample_rate, cfg.fft_size)
+    pkb2, fb, lb = oracle_py.spectrum_peaks(freqs, wb)
+    assert np.array_equal(pkb, pkb2)
+    st["peak_mismatch"] = _peak_rows_agree(pka, pkb, wb, "default")
+    # the fused arg-max must be the reference's peak_bin of the implementation's OWN trace, exactly
+    own_pk, own_f, own_l = oracle_py.spectrum_peaks(freqs, wa)
+    assert np.array_equal(pka, own_pk)
+    # interpolated_peak (state.rs:327-356) is plain f32 arithmetic on three dB values: bit-exact on identical inputs
+    assert np.array_equal(fa.view(np.uint32), own_f.view(np.uint32)) and np.array_equal(la.view(np.uint32), own_l.view(np.uint32))
+    # ... and close to the oracle's end-to-end result wherever both picked the same bin
+    same = (pka == pkb) & (pka >= 0)
+    if same.any():
+        bin_hz = float(freqs[1] - freqs[0])
+        # the parabola vertex amplifies dB differences by 1/curvature: 0.02 bin / 0.01 dB are far below a display step
+        assert np.max(np.abs(fa[same] - fb[same])) <= 0.02 * bin_hz and np.max(np.abs(la[same] - lb[same])) <= 1e-2
+    # a non-default spec: raw trace, candidates restricted to [300 Hz, 5 kHz]
+    plan.set_peak_spec(trace=1, min_hz=300.0, max_hz=5000.0)
+    assert plan.peak_spec() == (1, 300.0, 5000.0)
+    _, ra2, pk2, f2, l2 = plan.execute_host_peaks(lanes)
+    assert np.array_equal(ra2, ra)
+    e_pk, e_f, e_l = oracle_py.spectrum_peaks(freqs, ra2, 300.0, 5000.0)
+    assert np.array_equal(pk2, e_pk)
+    assert np.array_equal(f2.view(np.uint32), e_f.view(np.uint32)) and np.array_equal(l2.view(np.uint32), e_l.view(np.uint32))
+    inb = pk2 >= 0
+    assert np.all((freqs[pk2[inb]] >= 300.0) & (freqs[pk2[inb]] <= 5000.0))
+    o_pk, _, _ = oracle_py.spectrum_peaks(freqs, rb, 300.0, 5000.0)
+    st["peak_mismatch_raw_range"] = _peak_rows_agree(pk2, o_pk, rb, "raw 300-5000")
     return st
 
 

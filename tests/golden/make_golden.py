@@ -45,7 +45,10 @@ def main():
             np.savez_compressed(os.path.join(HERE, name + ".npz"), codes=oracle_py.stft_batch(c["cfg"], lanes, threads=1))
     scfg = SpectrumConfig(fft_size=2048, hop_size=256, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0)
     w, r, pk = oracle_py.spectrum_batch(scfg, synth.cfg4_streams(1, 0.2).reshape(2, -1), threads=1)
-    np.savez_compressed(os.path.join(HERE, "spectrum_peakhold.npz"), weighted=w, raw=r, peak=pk)
+    freqs = oracle_py.spectrum_frequency_bins(scfg.sample_rate, scfg.fft_size)
+    pk2, pf, pl = oracle_py.spectrum_peaks(freqs, w)  # default peak label spec: A-weighted trace, 20 Hz .. last bin
+    assert np.array_equal(pk, pk2)
+    np.savez_compressed(os.path.join(HERE, "spectrum_peakhold.npz"), weighted=w, raw=r, peak=pk, peak_freq=pf, peak_level=pl)
     x = synth.cfg3_surround(0.7)
     snaps, nb = oracle_py.loudness_batch(LoudnessConfig(), 8, capi.SURROUND, x[None, :], 1024, threads=1)
     np.savez_compressed(os.path.join(HERE, "loudness_surround.npz"), **batch.snapshots_to_arrays(snaps, nb))
