@@ -217,49 +217,55 @@ __device__ __forceinline__ void f_ring_fetch(float* ring, int L, int p0, const f
   }
 }
 
-__device__ __forceinline__ unsigned f_ordered_bits(float f) {
-  const unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// ln(v) from the special-function unit (MUFU.LG2 + one multiply; <= 3 ulp, CUDA __logf) — the epilogue is
-// issue-bound and the ~25-instruction accurate logf was its largest single item.  3 ulp of a dB value is <= 6e-6
-// relative in linear power (the parity budget is 1e-5); never used for the integer-coded classic columns.
+// log2(v) from the special-function unit (MUFU.LG2, <= 3 ulp like CUDA's __logf, of which this is the core) — the epilogue
+// is issue-bound and the ~30-instruction accurate logf was its largest single item.  3 ulp of a dB value is <= 6e-6
+// relative in linear power (the parity budget is 1e-5); never used for the integer-coded classic columns.  The
+// arguments here are 0 or >= state_floor >= FLT_MIN, so __logf's subnormal rescaling (4 more instructions) is dead code.
 __device__ __forceinline__ float fast_ln(float v) {
 #ifdef OMB_EMU
   return logf(v);
 #else
-  return __logf(v);
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return __fmul_rn(r, 0.69314718246459960938f);
 #endif
 }
 
-// One smoothed bin: state update, dB, stores; folds the bin into the running arg-max (best ordered dB bits, its bin;
-// a later bin in ascending order wins ties, state.rs:321-325).  Branch-free apart from the uniform mode switch.
+struct FusedConsts {  // kernel arguments the epilogue reads, copied to registers once
+  float alpha, one_minus_alpha, decay, state_floor, floor_db;
+  bool peak_raw;
+};
+
+// One smoothed bin: state update, dB, stores; folds the bin into the running arg-max key (ordered dB bits << 32 | bin:
+// larger dB wins, a larger bin wins ties, state.rs:321-325).  Branch-free.  `cand`: the bin is a peak candidate.
 template <int kMode>
-__device__ __forceinline__ void fused_bin(const SpecFusedArgs& fa, float p, float& st, int bin, float aw, float* ow, float* orw,
-                                          unsigned& best, unsigned& best_bin) {
-  float v = p;
-  if (kMode == OMB_AVG_EXPONENTIAL) {
-    st = st <= 0.0f ? p : __fadd_rn(__fmul_rn(st, fa.alpha), __fmul_rn(p, __fsub_rn(1.0f, fa.alpha)));
-    st = st < fa.state_floor ? 0.0f : st;
+__device__ __forceinline__ void fused_bin(const FusedConsts& c, float p, float& st, unsigned bin, float aw, float* ow, float* orw, bool cand,
+                                          unsigned long long& best) {
+  float v;
+  if (kMode == OMB_AVG_EXPONENTIAL) {  // spectrum/processor.rs:366-377
+    st = st <= 0.0f ? p : __fadd_rn(__fmul_rn(st, c.alpha), __fmul_rn(p, c.one_minus_alpha));
+    st = st < c.state_floor ? 0.0f : st;
     v = st;
-  } else if (kMode == OMB_AVG_PEAK_HOLD) {
-    st = fmaxf(__fmul_rn(st, fa.decay), p);
-    st = st < fa.state_floor ? 0.0f : st;
+  } else if (kMode == OMB_AVG_PEAK_HOLD) {  // :380-388
+    st = fmaxf(__fmul_rn(st, c.decay), p);
+    st = st < c.state_floor ? 0.0f : st;
     v = st;
+  } else {
+    v = p < c.state_floor ? 0.0f : p;
   }
-  const bool below = v < fa.state_floor;  // :392-401 (NaN powers take the dB path, as in the reference)
-  const float db = __fmul_rn(fast_ln(below ? 1.0f : v), kLnToDb);
-  const float raw = below ? fa.floor_db : fmaxf(db, fa.floor_db);
-  const float weighted = below ? fa.floor_db : fmaxf(__fadd_rn(db, aw), fa.floor_db);
-  ow[bin] = weighted;
-  orw[bin] = raw;
-  const bool interior = bin >= fa.peak_lo && bin <= fa.peak_hi;
-  const float pv = fa.peak_raw ? raw : weighted;
-  const unsigned ob = (interior && isfinite(pv)) ? f_ordered_bits(pv) : 0u;
-  const bool take = ob > best || (ob == best && (unsigned)bin > best_bin);
-  best = take ? ob : best;
-  best_bin = take ? (unsigned)bin : best_bin;
+  // :392-401 — values below the state floor are 0 here: lg2(0) = -inf and both maxima return the floor; NaN powers take
+  // the dB path as in the reference (f32::max ignores NaN, so does fmaxf)
+  const float db = __fmul_rn(fast_ln(v), kLnToDb);
+  const float raw = fmaxf(db, c.floor_db);
+  const float weighted = fmaxf(__fadd_rn(db, aw), c.floor_db);
+  *ow = weighted;
+  *orw = raw;
+  const float pv = c.peak_raw ? raw : weighted;
+  const unsigned u = __float_as_uint(pv);
+  const unsigned ob = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);  // monotone float -> uint map
+  const bool ok = cand & ((u & 0x7fffffffu) < 0x7f800000u);          // candidate bin with a finite value
+  const unsigned long long key = ok ? (((unsigned long long)ob << 32) | bin) : 0ull;
+  best = key > best ? key : best;
 }
 
 template <int kMode>
@@ -293,6 +299,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
   const float2* tw2o = sm.tw2 + (t & 15);
   float cw, sw;  // W_16384^tid = cw - j sw
   sincospif((float)tid / (float)(kN / 2), &sw, &cw);
+  float2 wsl[kSlots];  // W_16384^aa for this thread's four slots (aa = tid + 512 i)
+#pragma unroll
+  for (int i = 0; i < kSlots; ++i) wsl[i] = make_float2(cw * f16::kCos32[i] - sw * f16::kSin32[i], -(sw * f16::kCos32[i] + cw * f16::kSin32[i]));
+  const FusedConsts fc{fa.alpha, __fsub_rn(1.0f, fa.alpha), fa.decay, fa.state_floor, fa.floor_db, fa.peak_raw != 0};
+  // shared-memory positions of this thread's pair inputs: posC(tid + 512 i) = pa + 2 i; posC(4096 - tid - 512 i) = pb - 2 i
+  // (tid = 0: 4096 - 512 i wraps to 0 for i = 0 and sits at 16 - 2 i otherwise)
+  const int pa = posC(tid);
+  const int pb0 = posC((kM - tid) & (kM - 1));
+  const int pb = tid == 0 ? 16 : pb0;
+  // peak candidates among this thread's bins, bit 4 i + b (b: aa, 8192 - aa, 4096 - aa, 4096 + aa); bits 16, 17: bins 2048, 6144
+  unsigned cand = 0;
+#pragma unroll
+  for (int i = 0; i < kSlots; ++i) {
+    const int aa = tid + kThreads * i;
+    const int bins4[4] = {aa, 2 * kM - aa, kM - aa, kM + aa};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) cand |= (bins4[b] >= fa.peak_lo && bins4[b] <= fa.peak_hi) ? (1u << (4 * i + b)) : 0u;
+  }
+  cand |= (kM / 2 >= fa.peak_lo && kM / 2 <= fa.peak_hi) ? (1u << 16) : 0u;
+  cand |= (kM + kM / 2 >= fa.peak_lo && kM + kM / 2 <= fa.peak_hi) ? (1u << 17) : 0u;
+  if (!fa.peak_bin) cand = 0;
+  // |X|^2 = |2X|^2 / 4: the split below works on doubled spectra (exact: powers of two)
+  const float norm_ac = 0.25f * fa.norm_ac, norm_dc = 0.25f * fa.norm_dc;
   __syncthreads();
 
   for (uint32_t lane = blockIdx.x; lane < a.n_lanes; lane += gridDim.x) {
@@ -343,59 +372,61 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
       for (int q = 0; q < 16; ++q) wc[q] = v[q];
       __syncthreads();
       // epilogue: combine + real split + |X|^2 norm + smoothing + dB, four bins per (thread, slot)
-      float* ow = fa.out_weighted + ((uint64_t)lane * a.hops + h) * (uint64_t)(kN / 2 + 1);
-      float* orw = fa.out_raw + ((uint64_t)lane * a.hops + h) * (uint64_t)(kN / 2 + 1);
-      unsigned best = 0, best_bin = 0;
+      float* owp = fa.out_weighted + ((uint64_t)lane * a.hops + h) * (uint64_t)(kN / 2 + 1) + tid;  // bins tid + c
+      float* orp = fa.out_raw + ((uint64_t)lane * a.hops + h) * (uint64_t)(kN / 2 + 1) + tid;
+      float* owm = owp - 2 * tid;                                                                     // bins c - tid
+      float* orm = orp - 2 * tid;
+      unsigned long long best = 0;
 #pragma unroll
       for (int i = 0; i <= kSlots; ++i) {
-        const int aa = (i < kSlots) ? tid + kThreads * i : kM / 2;
         if (i == kSlots && tid != 0) break;
-        const int bb = kM - aa;
-        const float2 Ea = sm.W[0][posC(aa)], Oa = sm.W[1][posC(aa)];
-        const float2 Eb = sm.W[0][posC(bb & (kM - 1))], Ob = sm.W[1][posC(bb & (kM - 1))];
-        // W_16384^aa = W_16384^tid * W_32^i (aa = 2048: W_8)
-        const float ci = (i < kSlots) ? f16::kCos32[i] : f16::kH, si = (i < kSlots) ? f16::kSin32[i] : f16::kH;
-        const float2 w = (i < kSlots) ? make_float2(cw * ci - sw * si, -(sw * ci + cw * si)) : make_float2(ci, -si);
+        // i < 4: aa = tid + 512 i, bb = 4096 - aa;  i = 4 (thread 0 only): aa = bb = 2048
+        const int ia = (i < kSlots) ? pa + 2 * i : posC(kM / 2);
+        const int ib = (i < kSlots) ? (i == 0 ? pb0 : pb - 2 * i) : posC(kM / 2);
+        const float2 Ea = sm.W[0][ia], Oa = sm.W[1][ia];
+        const float2 Eb = sm.W[0][ib], Ob = sm.W[1][ib];
+        const float2 w = (i < kSlots) ? wsl[i < kSlots ? i : 0] : make_float2(f16::kH, -f16::kH);  // W_16384^aa (aa = 2048: W_8)
         const float2 w8 = cmul(w, w);
         const float2 ta = cmul(w8, Oa);
         const float2 tb = cmul(make_float2(-w8.x, w8.y), Ob);
-        const float2 Za = cadd(Ea, ta), Za2 = csub(Ea, ta);
-        const float2 Zb = cadd(Eb, tb), Zb2 = csub(Eb, tb);
+        const float2 Za = f16::cadd2(Ea, ta), Za2 = f16::csub2(Ea, ta);
+        const float2 Zb = f16::cadd2(Eb, tb), Zb2 = f16::csub2(Eb, tb);
         float p0, p1, p2, p3;
         {
-          const float2 A = make_float2(0.5f * (Za.x + Zb2.x), 0.5f * (Za.y - Zb2.y));
-          const float2 d = make_float2(Za.x - Zb2.x, Za.y + Zb2.y);
-          const float2 B = make_float2(0.5f * d.y, -0.5f * d.x);
+          const float2 A = make_float2(Za.x + Zb2.x, Za.y - Zb2.y);   // 2 A
+          const float2 B = make_float2(Za.y + Zb2.y, Zb2.x - Za.x);   // 2 B = (P - conj Q) / j
           const float2 T = cmul(w, B);
-          const float2 X0 = cadd(A, T), X1 = csub(A, T);
-          p0 = (X0.x * X0.x + X0.y * X0.y) * (aa == 0 ? fa.norm_dc : fa.norm_ac);   // bin aa
-          p1 = (X1.x * X1.x + X1.y * X1.y) * (aa == 0 ? fa.norm_dc : fa.norm_ac);   // bin 8192 - aa
+          const float2 X0 = f16::cadd2(A, T), X1 = f16::csub2(A, T);
+          const float nrm = (i == 0 && tid == 0) ? norm_dc : norm_ac;
+          p0 = (X0.x * X0.x + X0.y * X0.y) * nrm;   // bin aa
+          p1 = (X1.x * X1.x + X1.y * X1.y) * nrm;   // bin 8192 - aa
         }
         {
-          const float2 A = make_float2(0.5f * (Zb.x + Za2.x), 0.5f * (Zb.y - Za2.y));
-          const float2 d = make_float2(Zb.x - Za2.x, Zb.y + Za2.y);
-          const float2 B = make_float2(0.5f * d.y, -0.5f * d.x);
+          const float2 A = make_float2(Zb.x + Za2.x, Zb.y - Za2.y);
+          const float2 B = make_float2(Zb.y + Za2.y, Za2.x - Zb.x);
           const float2 wk = make_float2(-w.y, -w.x);
           const float2 T = cmul(wk, B);
-          const float2 X0 = cadd(A, T), X1 = csub(A, T);
-          p2 = (X0.x * X0.x + X0.y * X0.y) * fa.norm_ac;                           // bin 4096 - aa
-          p3 = (X1.x * X1.x + X1.y * X1.y) * fa.norm_ac;                           // bin 4096 + aa
+          const float2 X0 = f16::cadd2(A, T), X1 = f16::csub2(A, T);
+          p2 = (X0.x * X0.x + X0.y * X0.y) * norm_ac;   // bin 4096 - aa
+          p3 = (X1.x * X1.x + X1.y * X1.y) * norm_ac;   // bin 4096 + aa
         }
         if (i < kSlots) {
-          fused_bin<kMode>(fa, p0, st[i][0], aa, sm.adb_lo[aa], ow, orw, best, best_bin);
-          fused_bin<kMode>(fa, p1, st[i][1], 2 * kM - aa, aw_hi[i][0], ow, orw, best, best_bin);
-          fused_bin<kMode>(fa, p2, st[i][2], bb, sm.adb_lo[bb], ow, orw, best, best_bin);
+          const int c = kThreads * i;
+          const unsigned aa = (unsigned)(tid + c);
+          fused_bin<kMode>(fc, p0, st[i][0], aa, sm.adb_lo[aa], owp + c, orp + c, (cand >> (4 * i)) & 1u, best);
+          fused_bin<kMode>(fc, p1, st[i][1], 2 * kM - aa, aw_hi[i][0], owm + (2 * kM - c), orm + (2 * kM - c), (cand >> (4 * i + 1)) & 1u, best);
+          fused_bin<kMode>(fc, p2, st[i][2], kM - aa, sm.adb_lo[kM - aa], owm + (kM - c), orm + (kM - c), (cand >> (4 * i + 2)) & 1u, best);
           // aa = 0: bin 4096 a second time (the same bin from the mirrored pair, as in k_spectrum_power_16k where the
           // later store wins too) — cheaper than a divergent branch for one thread
-          fused_bin<kMode>(fa, p3, st[i][3], kM + aa, aw_hi[i][1], ow, orw, best, best_bin);
-        } else {  // aa = 2048: the two pairs coincide (bins 2048 and 6144)
-          fused_bin<kMode>(fa, p0, st_mid[0], aa, sm.adb_lo[aa], ow, orw, best, best_bin);
-          fused_bin<kMode>(fa, p1, st_mid[1], 2 * kM - aa, aw_mid, ow, orw, best, best_bin);
+          fused_bin<kMode>(fc, p3, st[i][3], kM + aa, aw_hi[i][1], owp + (kM + c), orp + (kM + c), (cand >> (4 * i + 3)) & 1u, best);
+        } else {  // aa = 2048 (thread 0): the two pairs coincide (bins 2048 and 6144)
+          fused_bin<kMode>(fc, p0, st_mid[0], kM / 2, sm.adb_lo[kM / 2], owp + kM / 2, orp + kM / 2, (cand >> 16) & 1u, best);
+          fused_bin<kMode>(fc, p1, st_mid[1], kM + kM / 2, aw_mid, owp + (kM + kM / 2), orp + (kM + kM / 2), (cand >> 17) & 1u, best);
         }
       }
       if (fa.peak_bin) {
-        const unsigned hi32 = __reduce_max_sync(0xffffffffu, best);
-        const unsigned lo32 = __reduce_max_sync(0xffffffffu, (best == hi32) ? best_bin : 0u);
+        const unsigned hi32 = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
+        const unsigned lo32 = __reduce_max_sync(0xffffffffu, ((unsigned)(best >> 32) == hi32) ? (unsigned)best : 0u);
         if (lane_id == 0) sm.wkey[h & 1][tid >> 5] = hi32 ? (((unsigned long long)hi32 << 32) | lo32) : 0ull;
       }
       r0 += hop;

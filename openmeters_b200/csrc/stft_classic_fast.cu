@@ -26,27 +26,37 @@ namespace {
 
 using namespace f16;
 
-constexpr int kN = 1024, kM = 512, kWarps = 8, kTile = 16 * 17 * 2;  // two padded 16 x 16 tiles >= 512 bins
+constexpr int kN = 1024, kM = 512, kWarps = 8, kTile = 16 * 17 * 2;  // two padded 16 x 16 tiles >= 513 entries
 
 struct SmemC {
-  float2 w1024[512];      // W_1024^k
-  float2 w512[256];       // W_512^n
+  float2 w1024[256];      // W_1024^k, k < 256 (the split handles bins k and 512 - k together)
+  float2 wst[2][256];     // first-stage twiddle by half-warp: s = 0 -> 1, s = 1 -> W_512^n
   float2 tw2[15 * 16];    // W_256^{r q}, [(q - 1) * 16 + r]
-  float2 win2[512];       // (h[2n], h[2n+1])
+  float2 win_lo[256];     // (h[2n], h[2n+1]), n < 256
+  float2 win_hi[2][256];  // +-(h[2n+512], h[2n+513]): the radix-2 sign of half-warp s folded into the window
   float2 work[kWarps][kTile];
 };
 
-__device__ __forceinline__ unsigned short to_code(float power) { return pack_classic_db_dev(power_to_db_dev(power, kDbFloor)); }
-
+// Instruction diet of the second version (the kernel is issue-bound: ~1840 -> ~1300 instructions per frame):
+//   * the half-warp's role (sum / twiddled difference) is data, not control flow: its sign lives in win_hi[s] and its
+//     twiddle in wst[s] (1 for s = 0), so the load phase has no selects or predicated duplicates;
+//   * the factors 1/2 of the real-FFT split are folded into the bin normalisation (exact: powers of two);
+//   * Z[0] is mirrored at work[512], so the partner index 512 - k needs no wrap;
+//   * dB + u16 packing through classic_code_dev (device_math.cuh): 25 instructions per bin instead of 45.
 __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs a) {
   OMB_DYN_SMEM(unsigned char, raw);
   SmemC& sm = *reinterpret_cast<SmemC*>(raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 512; i += kWarps * 32) {
+  for (int i = tid; i < 256; i += kWarps * 32) {
     sm.w1024[i] = __ldg(&a.tw_fft[i]);
-    sm.win2[i] = make_float2(__ldg(&a.win[2 * i]), __ldg(&a.win[2 * i + 1]));
+    sm.wst[0][i] = make_float2(1.0f, 0.0f);
+    sm.wst[1][i] = __ldg(&a.tw_fft[2 * i]);
+    const float2 lo = make_float2(__ldg(&a.win[2 * i]), __ldg(&a.win[2 * i + 1]));
+    const float2 hi = make_float2(__ldg(&a.win[2 * i + 512]), __ldg(&a.win[2 * i + 513]));
+    sm.win_lo[i] = lo;
+    sm.win_hi[0][i] = hi;
+    sm.win_hi[1][i] = make_float2(-hi.x, -hi.y);
   }
-  for (int i = tid; i < 256; i += kWarps * 32) sm.w512[i] = __ldg(&a.tw_fft[2 * i]);
   for (int i = tid; i < 240; i += kWarps * 32) {
     const int idx = 4 * (i / 16 + 1) * (i % 16);  // W_256^{rq} = W_1024^{4rq}; the table holds the upper half circle only
     float2 w = __ldg(&a.tw_fft[idx & 511]);
@@ -58,10 +68,14 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs 
   const int s = lane >> 4, r = lane & 15;
   float2* work = sm.work[warp];
   float2* tile = work + s * (16 * 17);
+  const float2* wlo = sm.win_lo + r;
+  const float2* whi = sm.win_hi[s] + r;
+  const float2* wst = sm.wst[s] + r;
   const uint64_t per_lane = a.frames_per_lane - a.first_frame;
   const uint64_t total = per_lane * a.n_lanes;
   const uint64_t stride_items = (uint64_t)gridDim.x * kWarps;
-  const float norm_edge = __ldg(&a.bin_norm[0]), norm_mid = __ldg(&a.bin_norm[1]);
+  // |X|^2 = |2X|^2 / 4: the split below works on 2X
+  const float norm_edge = 0.25f * __ldg(&a.bin_norm[0]), norm_mid = 0.25f * __ldg(&a.bin_norm[1]);
 
   for (uint64_t item = (uint64_t)blockIdx.x * kWarps + warp; item < total; item += stride_items) {
     const uint64_t lane_idx = item / per_lane, frame = a.first_frame + item % per_lane;
@@ -76,19 +90,17 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    const float mean = part / (float)kN;
+    const float mean = part * (1.0f / (float)kN);
 
+    // load + DC removal + window + first radix-2 stage: d = (xa - m) h_lo +- (xb - m) h_hi, times the stage twiddle
     float2 v[16];
+    const float2* xr = x2 + r;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int n = r + 16 * j;
-      const float2 xa = __ldg(&x2[n]), xb = __ldg(&x2[n + 256]);
-      const float2 wa = sm.win2[n], wb = sm.win2[n + 256];
-      const float2 va = make_float2((xa.x - mean) * wa.x, (xa.y - mean) * wa.y);
-      const float2 vb = make_float2((xb.x - mean) * wb.x, (xb.y - mean) * wb.y);
-      const float2 d = s ? csub2(va, vb) : cadd2(va, vb);
-      const float2 w = s ? sm.w512[n] : make_float2(1.0f, 0.0f);
-      v[j] = mul_tw<false>(d, w);
+      const float2 xa = __ldg(&xr[16 * j]), xb = __ldg(&xr[16 * j + 256]);
+      const float2 wa = wlo[16 * j], wb = whi[16 * j];
+      const float2 d = make_float2(fmaf(xb.x - mean, wb.x, (xa.x - mean) * wa.x), fmaf(xb.y - mean, wb.y, (xa.y - mean) * wa.y));
+      v[j] = mul_tw<false>(d, wst[16 * j]);
     }
     dft16<false>(v);  // over j: A[r][q]
     tile[r] = v[0];
@@ -101,24 +113,30 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs 
     __syncwarp();
 #pragma unroll
     for (int p = 0; p < 16; ++p) work[2 * (r + 16 * p) + s] = v[p];  // Z[2 k' + s]
+    if (lane == 0) work[kM] = v[0];                                   // Z[512] := Z[0]
     __syncwarp();
 
     uint16_t* out = a.out_classic + (lane_idx * a.frames_per_lane + frame) * (uint64_t)(kM + 1);
+    const float2* zlo = work + lane;
+    const float2* zhi = work + kM - lane;
+    const float2* wk = sm.w1024 + lane;
+    uint16_t* olo = out + lane;
+    uint16_t* ohi = out + kM - lane;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = lane + 32 * i;  // 0..255, partner bin 512 - k
-      const float2 zk = work[k], zm = work[(kM - k) & (kM - 1)];
-      const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-      const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));  // (zk - conj zm) / (2j)
-      const float2 T = cmul(sm.w1024[k], O);
-      const float2 Xk = cadd(E, T), Xm = csub(E, T);  // |X[512-k]| = |conj(E - T)|
-      const float nk = k == 0 ? norm_edge : norm_mid;
-      out[k] = to_code((Xk.x * Xk.x + Xk.y * Xk.y) * nk);
-      out[kM - k] = to_code((Xm.x * Xm.x + Xm.y * Xm.y) * nk);
+      // k = lane + 32 i (0..255), partner bin 512 - k
+      const float2 zk = zlo[32 * i], zm = zhi[-32 * i];
+      const float2 E = make_float2(zk.x + zm.x, zk.y - zm.y);      // 2 E
+      const float2 O = make_float2(zk.y + zm.y, zm.x - zk.x);      // 2 O = (zk - conj zm) / j
+      const float2 T = cmul(wk[32 * i], O);
+      const float2 Xk = cadd2(E, T), Xm = csub2(E, T);             // |X[512-k]| = |conj(E - T)|
+      const float nk = (i == 0 && lane == 0) ? norm_edge : norm_mid;
+      olo[32 * i] = classic_code_dev((Xk.x * Xk.x + Xk.y * Xk.y) * nk);
+      ohi[-32 * i] = classic_code_dev((Xm.x * Xm.x + Xm.y * Xm.y) * nk);
     }
-    if (lane == 0) {  // bin 256 pairs with itself: X = conj(Z[256])
+    if (lane == 0) {  // bin 256 pairs with itself: X = conj(Z[256]); here |Z|^2 is not doubled
       const float2 z = work[256];
-      out[256] = to_code((z.x * z.x + z.y * z.y) * norm_mid);
+      out[256] = classic_code_dev((z.x * z.x + z.y * z.y) * (4.0f * norm_mid));
     }
     __syncwarp();
   }

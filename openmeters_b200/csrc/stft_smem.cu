@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(1024) k_classic_smem(StftKernelArgs a) {
       const float2 w = k < M ? __ldg(&a.tw_fft[k]) : make_float2(-1.0f, 0.0f);
       const float2 X = cadd(E, cmul(w, O));
       const float p = (X.x * X.x + X.y * X.y) * __ldg(&a.bin_norm[k]);
-      out[k] = pack_classic_db_dev(power_to_db_dev(p, kDbFloor));
+      out[k] = classic_code_dev(p);
     }
     __syncthreads();
   }

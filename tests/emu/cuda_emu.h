@@ -328,6 +328,11 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline unsigned __float2uint_rd(float a) {  // saturating, NaN -> 0, like cvt.rmi.u32.f32
+  if (!(a > 0.0f)) return 0u;
+  const float f = std::floor(a);
+  return f >= 4294967296.0f ? 0xffffffffu : (unsigned)f;
+}
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
