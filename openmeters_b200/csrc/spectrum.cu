@@ -307,7 +307,8 @@ int SpectrumPlan::power_device(const float* d_lanes, uint32_t n_lanes, uint64_t 
     OMB_CUDA_TRY(cudaFuncSetAttribute(k_spectrum_power_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)200 * 1024 / smem));
     const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(dev.sm_count, 1) * per_sm);
-    const uint64_t want = std::max<uint64_t>(256, 2048 / (uint64_t)per_sm);
+    // whole warps only: block_sum / block_rank use full-mask warp collectives (2048 / 6 = 341 threads broke them)
+    const uint64_t want = std::max<uint64_t>(256, (2048 / (uint64_t)per_sm + 31) / 32 * 32);
     const unsigned threads = (unsigned)std::min<uint64_t>(std::min<uint64_t>(1024, want), std::max<uint64_t>(32, N / 8));
     OMB_LAUNCH(k_spectrum_power_smem, dim3(grid), dim3(threads), smem, s, a);
     OMB_CHECK_LAUNCH();

@@ -26,20 +26,27 @@ namespace {
 
 using namespace f16;
 
-constexpr int kN = 1024, kM = 512, kWarps = 8, kTile = 16 * 17 * 2;  // two padded 16 x 16 tiles >= 513 entries
+constexpr int kN = 1024, kM = 512, kWarps = 8, kTile = 16 * 17 * 2 + 8;  // two padded 16 x 16 tiles >= 513 entries
+
+constexpr int kTile1 = 16 * 17 + 8;  // offset of the second half-transform's tile: 8 float2 past a bank period (see below)
 
 struct SmemC {
   float2 w1024[256];      // W_1024^k, k < 256 (the split handles bins k and 512 - k together)
-  float2 wst[2][256];     // first-stage twiddle by half-warp: s = 0 -> 1, s = 1 -> W_512^n
+  float2 w512[256];       // first-stage twiddle W_512^n of the odd half-transform
   float2 tw2[15 * 16];    // W_256^{r q}, [(q - 1) * 16 + r]
   float2 win_lo[256];     // (h[2n], h[2n+1]), n < 256
-  float2 win_hi[2][256];  // +-(h[2n+512], h[2n+513]): the radix-2 sign of half-warp s folded into the window
+  float2 win_hi[256];     // (h[2n+512], h[2n+513])
   float2 work[kWarps][kTile];
 };
 
-// Instruction diet of the second version (the kernel is issue-bound: ~1840 -> ~1300 instructions per frame):
-//   * the half-warp's role (sum / twiddled difference) is data, not control flow: its sign lives in win_hi[s] and its
-//     twiddle in wst[s] (1 for s = 0), so the load phase has no selects or predicated duplicates;
+// Second version, after the first ncu capture (issue-bound, 1840 instructions per frame) and the second (L1 data-pipe
+// wavefronts at 86 % of peak, 14 % of the shared-memory wavefronts bank conflicts):
+//   * the half-transform a lane works for (s: even / odd bins) is data, not control flow: the radix-2 sign enters as
+//     (xb - m) * (+-1) = fma(xb, sgn, -sgn m), exact, and only the odd half multiplies by W_512^n — no selects, no
+//     duplicated predicated code, and the window tables are shared by both halves (broadcast loads);
+//   * lanes are interleaved (s = lane & 1, r = lane >> 1) and the second tile sits 8 float2 past a bank period, so the
+//     16 lanes of each 64-bit shared-memory phase (8 values of r, both s) always touch 16 distinct bank pairs, and
+//     the spectrum store work[lane + 32 p] is contiguous (it was a 2-way conflict with s = lane >> 4);
 //   * the factors 1/2 of the real-FFT split are folded into the bin normalisation (exact: powers of two);
 //   * Z[0] is mirrored at work[512], so the partner index 512 - k needs no wrap;
 //   * dB + u16 packing through classic_code_dev (device_math.cuh): 25 instructions per bin instead of 45.
@@ -49,13 +56,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 256; i += kWarps * 32) {
     sm.w1024[i] = __ldg(&a.tw_fft[i]);
-    sm.wst[0][i] = make_float2(1.0f, 0.0f);
-    sm.wst[1][i] = __ldg(&a.tw_fft[2 * i]);
-    const float2 lo = make_float2(__ldg(&a.win[2 * i]), __ldg(&a.win[2 * i + 1]));
-    const float2 hi = make_float2(__ldg(&a.win[2 * i + 512]), __ldg(&a.win[2 * i + 513]));
-    sm.win_lo[i] = lo;
-    sm.win_hi[0][i] = hi;
-    sm.win_hi[1][i] = make_float2(-hi.x, -hi.y);
+    sm.w512[i] = __ldg(&a.tw_fft[2 * i]);
+    sm.win_lo[i] = make_float2(__ldg(&a.win[2 * i]), __ldg(&a.win[2 * i + 1]));
+    sm.win_hi[i] = make_float2(__ldg(&a.win[2 * i + 512]), __ldg(&a.win[2 * i + 513]));
   }
   for (int i = tid; i < 240; i += kWarps * 32) {
     const int idx = 4 * (i / 16 + 1) * (i % 16);  // W_256^{rq} = W_1024^{4rq}; the table holds the upper half circle only
@@ -65,12 +68,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs 
   }
   __syncthreads();
 
-  const int s = lane >> 4, r = lane & 15;
+  const int s = lane & 1, r = lane >> 1;
   float2* work = sm.work[warp];
-  float2* tile = work + s * (16 * 17);
+  float2* tile = work + s * kTile1;
   const float2* wlo = sm.win_lo + r;
-  const float2* whi = sm.win_hi[s] + r;
-  const float2* wst = sm.wst[s] + r;
+  const float2* whi = sm.win_hi + r;
+  const float2* wst = sm.w512 + r;
+  const float sgn = s ? -1.0f : 1.0f;
   const uint64_t per_lane = a.frames_per_lane - a.first_frame;
   const uint64_t total = per_lane * a.n_lanes;
   const uint64_t stride_items = (uint64_t)gridDim.x * kWarps;
@@ -92,15 +96,18 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs 
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     const float mean = part * (1.0f / (float)kN);
 
-    // load + DC removal + window + first radix-2 stage: d = (xa - m) h_lo +- (xb - m) h_hi, times the stage twiddle
+    // load + DC removal + window + first radix-2 stage: d = (xa - m) h_lo +- (xb - m) h_hi; odd half: times W_512^n
     float2 v[16];
     const float2* xr = x2 + r;
+    const float msgn = -sgn * mean;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float2 xa = __ldg(&xr[16 * j]), xb = __ldg(&xr[16 * j + 256]);
       const float2 wa = wlo[16 * j], wb = whi[16 * j];
-      const float2 d = make_float2(fmaf(xb.x - mean, wb.x, (xa.x - mean) * wa.x), fmaf(xb.y - mean, wb.y, (xa.y - mean) * wa.y));
-      v[j] = mul_tw<false>(d, wst[16 * j]);
+      const float2 d = make_float2(fmaf(fmaf(xb.x, sgn, msgn), wb.x, (xa.x - mean) * wa.x),
+                                   fmaf(fmaf(xb.y, sgn, msgn), wb.y, (xa.y - mean) * wa.y));
+      v[j] = d;
+      if (s) v[j] = mul_tw<false>(d, wst[16 * j]);
     }
     dft16<false>(v);  // over j: A[r][q]
     tile[r] = v[0];
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) k_classic_1024(StftKernelArgs 
     dft16<false>(v);                                         // over r: Z_s[q + 16 p]
     __syncwarp();
 #pragma unroll
-    for (int p = 0; p < 16; ++p) work[2 * (r + 16 * p) + s] = v[p];  // Z[2 k' + s]
+    for (int p = 0; p < 16; ++p) work[lane + 32 * p] = v[p];  // Z[2 k' + s], k' = r + 16 p
     if (lane == 0) work[kM] = v[0];                                   // Z[512] := Z[0]
     __syncwarp();
 

@@ -198,7 +198,8 @@ int launch_stft_smem(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s, De
   // one radix-4 butterfly per thread per stage when possible; when shared memory limits the SM to one or two
   // CTAs, make them wide (up to 1024 threads) so the SM still has 16-32 warps to hide latency
   const uint64_t work = plan.cfg.reassign ? a.fft_len : a.fft_len / 2;
-  const uint64_t want = std::max<uint64_t>(256, 2048 / (uint64_t)per_sm);
+  // whole warps only: block_sum / block_rank use full-mask warp collectives (2048 / 6 = 341 threads broke them)
+  const uint64_t want = std::max<uint64_t>(256, (2048 / (uint64_t)per_sm + 31) / 32 * 32);
   const unsigned threads = (unsigned)std::min<uint64_t>(std::min<uint64_t>(1024, want), std::max<uint64_t>(32, work / 4));
   if (plan.cfg.reassign) {
     const uint64_t stride = 3ull * a.bins + 1;  // floats: S (2 per bin) + nd (1 per bin)

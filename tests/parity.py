@@ -15,7 +15,7 @@ REL = 1e-5
 
 
 def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_len: int, window: int, hop: int,
-                              power_floor: float = 1e-14):
+                              power_floor: float = 1e-14, rel: float = REL):
     """a = implementation points (n,3), b = oracle points (m,3) as [time, freq, power], both in ascending
     source-bin order. The two sequences are aligned with a small look-ahead; a point present on one side
     only must sit on a decision threshold (power at the 1e-14 analysis floor, or frequency at 0 / sr/2).
@@ -27,8 +27,8 @@ def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_le
     if peak == 0.0:
         assert len(a) == len(b) == 0
         return stats
-    tol_f0 = REL * sr / 2
-    tol_t0 = REL * (window / hop)
+    tol_f0 = rel * sr / 2
+    tol_t0 = rel * (window / hop)
 
     def scale(p):
         # SURVEY §8c states the flat 1e-5 tolerances for bins >= -60 dB re the column peak.  An f32 FFT leaves
@@ -44,7 +44,7 @@ def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_le
     tol_f = tol_f0
 
     def same(pa, pb):
-        return abs(pa[2] - pb[2]) <= REL * max(abs(pb[2]), peak * 1e-3)
+        return abs(pa[2] - pb[2]) <= rel * max(abs(pb[2]), peak * 1e-3)
 
     def on_threshold(p):
         return p[2] <= power_floor * (1 + 1e-3) or p[1] <= 4 * tol_f or sr / 2 - p[1] <= 4 * tol_f
@@ -84,7 +84,7 @@ def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_le
     return stats
 
 
-def compare_reassigned(points_a, counts_a, points_b, counts_b, *, sr, fft_len, window, hop, max_unmatched_frac=2e-3):
+def compare_reassigned(points_a, counts_a, points_b, counts_b, *, sr, fft_len, window, hop, max_unmatched_frac=2e-3, rel=REL):
     """Whole batches: arrays (L,F,stride,3) + counts (L,F)."""
     assert counts_a.shape == counts_b.shape
     L, F = counts_a.shape
@@ -93,7 +93,7 @@ def compare_reassigned(points_a, counts_a, points_b, counts_b, *, sr, fft_len, w
         for f in range(F):
             a = points_a[l, f, : counts_a[l, f]]
             b = points_b[l, f, : counts_b[l, f]]
-            st = compare_reassigned_column(a, b, sr=sr, fft_len=fft_len, window=window, hop=hop)
+            st = compare_reassigned_column(a, b, sr=sr, fft_len=fft_len, window=window, hop=hop, rel=rel)
             tot["cols"] += 1
             tot["pts"] += st["n_b"]
             tot["unmatched"] += st["unmatched"]
@@ -102,7 +102,7 @@ def compare_reassigned(points_a, counts_a, points_b, counts_b, *, sr, fft_len, w
     return tot
 
 
-def compare_classic(codes_a: np.ndarray, codes_b: np.ndarray, min_exact: float = 0.98):
+def compare_classic(codes_a: np.ndarray, codes_b: np.ndarray, min_exact: float = 0.98, rel: float = REL):
     """Packed u16 dB columns (156 dB over 65535 codes, 0.0024 dB per code), judged with the SURVEY §8c rule in the
     linear power domain: |pa - pb| <= 1e-5 * max(pb, column_peak*1e-3), plus the quantisation of the code itself
     (+-1 code).  On bins within 30 dB of the column peak that means: codes equal or +-1, with >= 98 % exact."""
@@ -113,7 +113,7 @@ def compare_classic(codes_a: np.ndarray, codes_b: np.ndarray, min_exact: float =
     pb = 10.0 ** ((ib * step - 144.0) / 10.0)
     peak = pb.max(axis=-1, keepdims=True)
     quant = pb * (10.0 ** (step / 10.0) - 1.0)  # one code
-    tol = 2.0 * REL * np.maximum(pb, peak * 1e-3) + quant
+    tol = 2.0 * rel * np.maximum(pb, peak * 1e-3) + quant
     assert np.all(np.abs(pa - pb) <= tol), float((np.abs(pa - pb) / tol).max())
     strong = pb >= peak * 1e-3
     d = np.abs(ia - ib)

@@ -152,3 +152,10 @@ def test_spectrum_fused_16k(emu, mode, param, monkeypatch):
     lanes = synth.cfg4_streams(1, (16384 + 19 * 1024) / 48000.0).reshape(2, -1)
     st = cases.spectrum_parity(emu.api, cfg, lanes)
     assert st is not None
+
+
+@pytest.mark.parametrize("n,hop,zp,window,reassign", cases.settings_grid())
+def test_settings_grid_emulated(emu, n, hop, zp, window, reassign):
+    """the (size, hop, zero padding, window, mode) grid the settings UI can reach, through whichever kernel
+    tier the plan picks — caught a 341-thread launch (partial warp under full-mask collectives) for F = 4096."""
+    cases.settings_grid_case(emu.api, n, hop, zp, window, reassign)

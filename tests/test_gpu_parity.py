@@ -233,3 +233,11 @@ def test_edge_cases(product):
     big[:, :8192 + 1024] = lanes[2:3, :1].repeat(2, 0) * 0 + synth.cfg2_lanes(2, 0.2)[:, :8192 + 1024]
     p1, c1 = plan.execute_host(np.ascontiguousarray(big[:, :8192 + 1024]))
     assert c1.shape == (2, 2)
+
+
+# ---------------------------------------------------------------- the product's config space
+@pytest.mark.parametrize("n,hop,zp,window,reassign", cases.settings_grid())
+def test_settings_grid(product, n, hop, zp, window, reassign):
+    """Every reachable (size, hop, zero padding, window, mode) combination has a kernel and matches the oracle —
+    whichever tier (specialised / shared-memory / generic) the plan picks."""
+    cases.settings_grid_case(product.api, n, hop, zp, window, reassign)
