@@ -41,6 +41,19 @@ __device__ __forceinline__ double kw_step(double x, double* s, const KWeight& kw
   return y;
 }
 
+// The same section with fused multiply-adds (9 FP64 instructions instead of 17) for the chunk-parallel batch path:
+// its chunk start states come out of a scan and are not bit-identical to the sequential recurrence's anyway, so
+// per-operation rounding fidelity buys nothing there (f64 differences ~1e-16 relative, invisible after `y as f32`
+// except on rounding boundaries; parity budget 1e-5 on the mean squares).  The streaming kernel keeps kw_step.
+__device__ __forceinline__ double kw_step_fma(double x, double* s, const KWeight& kw) {
+  const double y = fma(kw.b[0], x, s[0]);
+  s[0] = fma(-kw.a[1], y, fma(kw.b[1], x, s[1]));
+  s[1] = fma(-kw.a[2], y, fma(kw.b[2], x, s[2]));
+  s[2] = fma(-kw.a[3], y, fma(kw.b[3], x, s[3]));
+  s[3] = fma(-kw.a[4], y, kw.b[4] * x);
+  return y;
+}
+
 // dsp.rs:277-285 Kahan-Babuska-Neumaier
 __device__ __forceinline__ void neumaier_add(double& sum, double& corr, double v) {
   const double next = __dadd_rn(sum, v);
@@ -173,6 +186,7 @@ struct LoudBatchArgs {
   KWeight kw;
   double M[16];      // A^kKwChunk
   double Mseg[16];   // A^(kKwChunk*kKwSeg)
+  const double* resp; // [kKwChunk][4] response of the chunk end state to input sample k (zero-state pass)
   double* seg_state; // [stream][segment][channel][4]
   double* end_state;     // [stream][chunk][channel][4]  zero-state end states
   double* start_state;   // [stream][chunk][channel][4]  true start states
@@ -205,7 +219,19 @@ __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
   double s[4] = {0.0, 0.0, 0.0, 0.0};
   const uint64_t sidx = ((stream * a.n_chunks + chunk) * a.channels + c) * 4;
   if (!kApply) {
-    for (uint64_t t = t0; t < t1; ++t) kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
+    // zero-state end state of the chunk as a linear map of its inputs: s_end = sum_k A^(n-1-k) B x[k] — 4 FMAs per
+    // sample from a table every thread reads at the same index (broadcast), instead of running the 17-operation
+    // recurrence; the pass drops from the FP64 pipe's bound to the bandwidth of reading x
+    const double2* resp = reinterpret_cast<const double2*>(a.resp) + 2 * (kKwChunk - (t1 - t0));
+#pragma unroll 4
+    for (uint64_t t = t0; t < t1; ++t) {
+      const double xv = (double)__ldg(&x[t * a.channels + c]);
+      const double2 r01 = __ldg(&resp[2 * (t - t0)]), r23 = __ldg(&resp[2 * (t - t0) + 1]);
+      s[0] = fma(r01.x, xv, s[0]);
+      s[1] = fma(r01.y, xv, s[1]);
+      s[2] = fma(r23.x, xv, s[2]);
+      s[3] = fma(r23.y, xv, s[3]);
+    }
     a.end_state[sidx + 0] = s[0];
     a.end_state[sidx + 1] = s[1];
     a.end_state[sidx + 2] = s[2];
@@ -220,7 +246,7 @@ __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
   double acc = 0.0;
 #pragma unroll 4
   for (uint64_t t = t0; t < t1; ++t) {
-    const float yf = (float)kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
+    const float yf = (float)kw_step_fma((double)__ldg(&x[t * a.channels + c]), s, a.kw);
     const double v = (double)yf * (double)yf;
     acc += isfinite(v) ? v : 0.0;
     y[t * a.channels + c] = yf;
@@ -561,10 +587,25 @@ int LoudnessPlan::init(const omb_loudness_config& c, uint32_t ch, const uint8_t*
   static_assert(kKwChunk == 256, "chunk matrix uses 8 squarings");
   for (int i = 0; i < 8; ++i) mat4_mul(A, A, A);
   for (int i = 0; i < 16; ++i) chunk_matrix[i] = (double)A[i];
+  {  // response of the chunk end state to each input sample: v_{K-1} = B, v_{k-1} = A v_k  (state' = A state + B x)
+    const long double b0 = kw.b[0];
+    const long double A1[16] = {-(long double)kw.a[1], 1, 0, 0, -(long double)kw.a[2], 0, 1, 0, -(long double)kw.a[3], 0, 0, 1, -(long double)kw.a[4], 0, 0, 0};
+    long double v[4] = {(long double)kw.b[1] - (long double)kw.a[1] * b0, (long double)kw.b[2] - (long double)kw.a[2] * b0,
+                        (long double)kw.b[3] - (long double)kw.a[3] * b0, (long double)kw.b[4] - (long double)kw.a[4] * b0};
+    h_resp.assign((size_t)kKwChunk * 4, 0.0);
+    for (int k = kKwChunk - 1; k >= 0; --k) {
+      for (int r = 0; r < 4; ++r) h_resp[(size_t)k * 4 + r] = (double)v[r];
+      long double n[4];
+      for (int r = 0; r < 4; ++r) n[r] = A1[r * 4 + 0] * v[0] + A1[r * 4 + 1] * v[1] + A1[r * 4 + 2] * v[2] + A1[r * 4 + 3] * v[3];
+      for (int r = 0; r < 4; ++r) v[r] = n[r];
+    }
+  }
   static_assert(kKwSeg == 64, "segment matrix uses 6 more squarings");
   for (int i = 0; i < 6; ++i) mat4_mul(A, A, A);
   for (int i = 0; i < 16; ++i) seg_matrix[i] = (double)A[i];
   OMB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  OMB_TRY(d_resp.upload(h_resp, stream));
+  OMB_CUDA_TRY(cudaStreamSynchronize(stream));
   return OMB_OK;
 }
 
@@ -586,6 +627,7 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   a.kw = kw;
   std::memcpy(a.M, chunk_matrix, sizeof a.M);
   std::memcpy(a.Mseg, seg_matrix, sizeof a.Mseg);
+  a.resp = d_resp.ptr;
   const uint64_t n_seg = (a.n_chunks + kKwSeg - 1) / kKwSeg;
   OMB_TRY(d_seg.reserve((size_t)((uint64_t)n_streams * n_seg * channels * 4)));
   a.seg_state = d_seg.ptr;
