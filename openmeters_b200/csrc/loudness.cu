@@ -186,7 +186,6 @@ struct LoudBatchArgs {
   KWeight kw;
   double M[16];      // A^kKwChunk
   double Mseg[16];   // A^(kKwChunk*kKwSeg)
-  const double* resp; // [kKwChunk][4] response of the chunk end state to input sample k (zero-state pass)
   double* seg_state; // [stream][segment][channel][4]
   double* end_state;     // [stream][chunk][channel][4]  zero-state end states
   double* start_state;   // [stream][chunk][channel][4]  true start states
@@ -219,19 +218,7 @@ __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
   double s[4] = {0.0, 0.0, 0.0, 0.0};
   const uint64_t sidx = ((stream * a.n_chunks + chunk) * a.channels + c) * 4;
   if (!kApply) {
-    // zero-state end state of the chunk as a linear map of its inputs: s_end = sum_k A^(n-1-k) B x[k] — 4 FMAs per
-    // sample from a table every thread reads at the same index (broadcast), instead of running the 17-operation
-    // recurrence; the pass drops from the FP64 pipe's bound to the bandwidth of reading x
-    const double2* resp = reinterpret_cast<const double2*>(a.resp) + 2 * (kKwChunk - (t1 - t0));
-#pragma unroll 4
-    for (uint64_t t = t0; t < t1; ++t) {
-      const double xv = (double)__ldg(&x[t * a.channels + c]);
-      const double2 r01 = __ldg(&resp[2 * (t - t0)]), r23 = __ldg(&resp[2 * (t - t0) + 1]);
-      s[0] = fma(r01.x, xv, s[0]);
-      s[1] = fma(r01.y, xv, s[1]);
-      s[2] = fma(r23.x, xv, s[2]);
-      s[3] = fma(r23.y, xv, s[3]);
-    }
+    for (uint64_t t = t0; t < t1; ++t) kw_step((double)__ldg(&x[t * a.channels + c]), s, a.kw);
     a.end_state[sidx + 0] = s[0];
     a.end_state[sidx + 1] = s[1];
     a.end_state[sidx + 2] = s[2];
@@ -252,6 +239,57 @@ __global__ void __launch_bounds__(128) k_kw_chunks(LoudBatchArgs a) {
     y[t * a.channels + c] = yf;
   }
   a.csum[(stream * a.channels + c) * a.n_chunks + chunk] = acc;
+}
+
+// (1'), the shipped zero-state pass: the chunk's end state from a zero start is a linear map of its inputs,
+// s_end = sum_k A^(K-1-k) B x[k] — 4 FMAs per sample instead of the 17-operation recurrence.  The response table rides in
+// the kernel parameters (constant bank) and the k loop is fully unrolled, so every coefficient is an immediate
+// constant-bank operand of its DFMA: no load instruction, no L1 traffic for the table (a first version that read it with
+// __ldg was bound by the L1 data pipe at 88 % and slower than the recurrence).  A short last chunk is right-aligned
+// (zeros in front), which keeps k uniform across the warp.  Bound: the bandwidth of reading x once.
+struct KwRespTable {
+  double v[kKwChunk * 4];  // [k][r] = (A^(K-1-k) B)[r]
+};
+
+template <int kC>  // channel count at compile time (load offsets become immediates), 0 = any
+__global__ void __launch_bounds__(128) k_kw_zero_state(LoudBatchArgs a, const KwRespTable tab) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t C = kC ? (uint32_t)kC : a.channels;
+  const uint64_t total = (uint64_t)a.n_streams * a.n_chunks * C;
+  if (idx >= total) return;
+  const uint32_t c = (uint32_t)(idx % C);
+  const uint64_t chunk = (idx / C) % a.n_chunks;
+  const uint64_t stream = idx / ((uint64_t)C * a.n_chunks);
+  const uint64_t t0 = chunk * kKwChunk;
+  const uint64_t t1 = t0 + kKwChunk < a.frames ? t0 + kKwChunk : a.frames;
+  const int lead = kKwChunk - (int)(t1 - t0);  // zeros in front of a short last chunk
+  // sample k of the right-aligned chunk is stream frame t1 - K + k (a possibly "negative" pointer that is never dereferenced)
+  const float* x = a.in + stream * a.stream_stride + c + ((int64_t)t1 - kKwChunk) * (int64_t)C;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (lead == 0) {
+#pragma unroll
+    for (int k = 0; k < kKwChunk; ++k) {
+      const double xv = (double)__ldg(&x[(uint32_t)k * C]);
+      s0 = fma(tab.v[4 * k + 0], xv, s0);
+      s1 = fma(tab.v[4 * k + 1], xv, s1);
+      s2 = fma(tab.v[4 * k + 2], xv, s2);
+      s3 = fma(tab.v[4 * k + 3], xv, s3);
+    }
+  } else {
+#pragma unroll 8
+    for (int k = 0; k < kKwChunk; ++k) {
+      const double xv = k >= lead ? (double)__ldg(&x[(uint32_t)k * C]) : 0.0;
+      s0 = fma(tab.v[4 * k + 0], xv, s0);
+      s1 = fma(tab.v[4 * k + 1], xv, s1);
+      s2 = fma(tab.v[4 * k + 2], xv, s2);
+      s3 = fma(tab.v[4 * k + 3], xv, s3);
+    }
+  }
+  const uint64_t sidx = ((stream * a.n_chunks + chunk) * C + c) * 4;
+  a.end_state[sidx + 0] = s0;
+  a.end_state[sidx + 1] = s1;
+  a.end_state[sidx + 2] = s2;
+  a.end_state[sidx + 3] = s3;
 }
 
 // (2): scan over chunks of the affine recurrence start[k+1] = M * start[k] + end0[k], three levels so the
@@ -381,14 +419,30 @@ __global__ void __launch_bounds__(kTpTile) k_true_peak4(LoudBatchArgs a, TruePea
   const uint64_t f1 = f0 + a.block_frames < a.frames ? f0 + a.block_frames : a.frames;
   const int C = kC ? kC : (int)a.channels;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // warp = channel (C <= 8 warps take part in the FIR)
+  const bool vec4 = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);  // 16-byte aligned stream: frames are float4 pairs
   float best = 0.0f;
   for (uint64_t base = f0 + (uint64_t)blockIdx.y * kTpTile; base < f1; base += (uint64_t)gridDim.y * kTpTile) {
     // tile frame index u <-> stream frame base - kTp4Halo + u; frames before the stream start are zeros
-    const int n_el = (kTpTile + kTp4Halo) * C;
-    for (int e = threadIdx.x; e < n_el; e += kTpTile) {
-      const int u = e / C, c = e - u * C;
-      const int64_t fr = (int64_t)base - kTp4Halo + u;
-      tile[c][u + (u >> 3)] = (fr >= 0 && (uint64_t)fr < a.frames) ? __ldg(&x[(uint64_t)fr * C + c]) : 0.0f;
+    if (kC == 8 && vec4) {
+      // 8 interleaved channels = two 16-byte quads per frame: one bounds check and one load per quad
+      for (int e = threadIdx.x; e < (kTpTile + kTp4Halo) * 2; e += kTpTile) {
+        const int u = e >> 1, c = (e & 1) * 4;
+        const int64_t fr = (int64_t)base - kTp4Halo + u;
+        float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (fr >= 0 && (uint64_t)fr < a.frames) q = __ldg(reinterpret_cast<const float4*>(x + (uint64_t)fr * 8 + c));
+        const int col = u + (u >> 3);
+        tile[c + 0][col] = q.x;
+        tile[c + 1][col] = q.y;
+        tile[c + 2][col] = q.z;
+        tile[c + 3][col] = q.w;
+      }
+    } else {
+      const int n_el = (kTpTile + kTp4Halo) * C;
+      for (int e = threadIdx.x; e < n_el; e += kTpTile) {
+        const int u = e / C, c = e - u * C;
+        const int64_t fr = (int64_t)base - kTp4Halo + u;
+        tile[c][u + (u >> 3)] = (fr >= 0 && (uint64_t)fr < a.frames) ? __ldg(&x[(uint64_t)fr * C + c]) : 0.0f;
+      }
     }
     __syncthreads();
     if (warp < C) {
@@ -402,9 +456,11 @@ __global__ void __launch_bounds__(kTpTile) k_true_peak4(LoudBatchArgs a, TruePea
       }
 #pragma unroll
       for (int r = 0; r < kTpRun; ++r) {
-        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+        // first tap: 0.0 + p == p (up to the sign of zero, which |.| discards), so the sums start at the product
+        float o0 = __fmul_rn(w[kTp4Halo + r], fir.fir4[0][0]), o1 = __fmul_rn(w[kTp4Halo + r], fir.fir4[0][1]),
+              o2 = __fmul_rn(w[kTp4Halo + r], fir.fir4[0][2]);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {  // delay[pos + i] == x[t - i]
+        for (int i = 1; i < 12; ++i) {  // delay[pos + i] == x[t - i]
           const float d = w[kTp4Halo + r - i];
           o0 = __fadd_rn(o0, __fmul_rn(d, fir.fir4[i][0]));
           o1 = __fadd_rn(o1, __fmul_rn(d, fir.fir4[i][1]));
@@ -604,8 +660,6 @@ int LoudnessPlan::init(const omb_loudness_config& c, uint32_t ch, const uint8_t*
   for (int i = 0; i < 6; ++i) mat4_mul(A, A, A);
   for (int i = 0; i < 16; ++i) seg_matrix[i] = (double)A[i];
   OMB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  OMB_TRY(d_resp.upload(h_resp, stream));
-  OMB_CUDA_TRY(cudaStreamSynchronize(stream));
   return OMB_OK;
 }
 
@@ -627,7 +681,6 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   a.kw = kw;
   std::memcpy(a.M, chunk_matrix, sizeof a.M);
   std::memcpy(a.Mseg, seg_matrix, sizeof a.Mseg);
-  a.resp = d_resp.ptr;
   const uint64_t n_seg = (a.n_chunks + kKwSeg - 1) / kKwSeg;
   OMB_TRY(d_seg.reserve((size_t)((uint64_t)n_streams * n_seg * channels * 4)));
   a.seg_state = d_seg.ptr;
@@ -654,9 +707,21 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
 
   const uint64_t n_items = (uint64_t)n_streams * a.n_chunks * channels;
   const unsigned g1 = (unsigned)((n_items + 127) / 128);
-  auto k_zero = k_kw_chunks<false>;
   auto k_apply = k_kw_chunks<true>;
-  OMB_LAUNCH(k_zero, dim3(g1), dim3(128), 0, s, a);
+  if (getenv("OMB_KW_ZERO_RECURRENCE")) {  // the recurrence form of the zero-state pass (A/B measurements)
+    auto k_zero = k_kw_chunks<false>;
+    OMB_LAUNCH(k_zero, dim3(g1), dim3(128), 0, s, a);
+  } else {
+    KwRespTable tab;
+    std::memcpy(tab.v, h_resp.data(), sizeof tab.v);
+    if (channels == 8) {
+      OMB_LAUNCH(k_kw_zero_state<8>, dim3(g1), dim3(128), 0, s, a, tab);
+    } else if (channels == 2) {
+      OMB_LAUNCH(k_kw_zero_state<2>, dim3(g1), dim3(128), 0, s, a, tab);
+    } else {
+      OMB_LAUNCH(k_kw_zero_state<0>, dim3(g1), dim3(128), 0, s, a, tab);
+    }
+  }
   OMB_CHECK_LAUNCH();
   {
     auto k_s0 = k_kw_scan<0>;

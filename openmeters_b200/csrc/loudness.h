@@ -64,7 +64,6 @@ struct LoudnessPlan {
   double chunk_matrix[16];               // A^kKwChunk, row-major (state transition over one chunk)
   double seg_matrix[16];                 // A^(kKwChunk*kKwSeg)
   std::vector<double> h_resp;            // [kKwChunk][4]: A^(kKwChunk-1-k) B, the end state's response to input sample k
-  DeviceBuffer<double> d_resp;
   uint64_t caps[kLoudWindows];
   uint32_t tp_delay_len = 0;
   DeviceBuffer<double> d_end, d_start, d_csum, d_cbase, d_seg;
