@@ -401,8 +401,10 @@ __global__ void __launch_bounds__(kTpTile) k_true_peak(LoudBatchArgs a, TruePeak
 // 4x true peak, register-blocked (sample rates below 96 kHz — the common case): the tile is staged like above, then
 // every thread owns kTpRun consecutive frames of ONE channel, keeps their 11-sample history in registers and runs the
 // three 12-tap phases with scalar multiplies and adds in the reference's order (separate roundings, bit-identical sums).
-// (Packed FP32x2 would halve the issue slots, but ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 — one rounding
-// instead of two, even with -fmad=false — so the packed form cannot keep the reference's bits.)
+// (Packed FP32x2 does not help: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 — one rounding instead of two, even
+// with -fmad=false — and the bit-exact alternative, packed multiplies of two adjacent frames (FMUL2) with scalar adds,
+// was measured: 20 % fewer instructions, the same 0.52 ms, because FMUL2 holds the FMA pipe for two cycles and the kernel
+// is bound by that pipe (67 % of its peak), not by issue slots; profiles/r01c_notes.md.)
 // A warp covers 32 runs of one channel: the smem row is padded 9-for-8 so the stride-8 reads are conflict-free, and
 // the max is reduced once per kTpRun frames instead of once per frame.  ~60 instructions per sample-channel instead
 // of ~190 (profiles/r01b_notes.md).
@@ -450,61 +452,9 @@ __global__ void __launch_bounds__(kTpTile) k_true_peak4(LoudBatchArgs a, TruePea
       const float* row = tile[warp];
       const float* lrow = row + 9 * lane;  // this thread's window starts at tile frame 8 lane -> column 9 lane
       const int nvalid = (int)(f1 - base < (uint64_t)kTpTile ? f1 - base : (uint64_t)kTpTile) - kTpRun * lane;  // frames of this run inside the block
-      (void)lrow; (void)nvalid;
-#if !defined(OMB_EMU) && !defined(OMB_NO_F32X2)
-      // Products of TWO adjacent frames with one coefficient are one packed FP32x2 multiply (both correctly rounded, the
-      // reference's value); the additions stay scalar and in the reference's order, so the sums keep its bits.  (A packed
-      // multiply followed by a packed add would be contracted into FFMA2 by ptxas — one rounding — hence scalar adds.)
-      // pe[j] = (w[2j], w[2j+1]), po[j] = (w[2j+1], w[2j+2]): the window pair that starts at an even / odd index.
-      float2 pe[10], po[9];
-#pragma unroll
-      for (int j = 0; j < 10; ++j) {  // tile column of window index k: 9 lane + k + (k >> 3)
-        const int k0 = 2 * j, k1 = k0 + 1;
-        pe[j] = make_float2(lrow[k0 + (k0 >> 3)], j < 9 ? lrow[k1 + (k1 >> 3)] : 0.0f);
-      }
-      // the odd pairs are loaded a second time through a volatile pointer: derived from pe[] the compiler keeps one copy
-      // of every value and assembles each pair with register moves (124 MOVs per 8 frames, the whole gain)
-      const volatile float* vrow = lrow;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int k0 = 2 * j + 1, k1 = k0 + 1;
-        po[j].x = vrow[k0 + (k0 >> 3)];
-        po[j].y = vrow[k1 + (k1 >> 3)];
-      }
-#pragma unroll
-      for (int r = 0; r < kTpRun; r += 2) {
-        float2 o0, o1, o2;  // .x: frame r, .y: frame r + 1
-        {
-          const float2 d = po[(kTp4Halo + r - 1) / 2];  // (w[11 + r], w[12 + r])
-          o0 = __fmul2_rn(d, fir.fir4p[0][0]);
-          o1 = __fmul2_rn(d, fir.fir4p[0][1]);
-          o2 = __fmul2_rn(d, fir.fir4p[0][2]);
-        }
-#pragma unroll
-        for (int i = 1; i < 12; ++i) {  // delay[pos + i] == x[t - i]
-          const int k0 = kTp4Halo + r - i;  // window index of frame r's tap; frame r + 1 uses k0 + 1
-          const float2 d = (k0 & 1) ? po[(k0 - 1) / 2] : pe[k0 / 2];
-          const float2 p0 = __fmul2_rn(d, fir.fir4p[i][0]);
-          const float2 p1 = __fmul2_rn(d, fir.fir4p[i][1]);
-          const float2 p2 = __fmul2_rn(d, fir.fir4p[i][2]);
-          o0.x = __fadd_rn(o0.x, p0.x); o0.y = __fadd_rn(o0.y, p0.y);
-          o1.x = __fadd_rn(o1.x, p1.x); o1.y = __fadd_rn(o1.y, p1.y);
-          o2.x = __fadd_rn(o2.x, p2.x); o2.y = __fadd_rn(o2.y, p2.y);
-        }
-        const float2 x01 = po[(kTp4Halo + r - 1) / 2];
-        // NaN input: fmaxf drops NaN exactly like Rust's f32::max in TruePeakMeter::process.
-        const float pk0 = fmaxf(fmaxf(fmaxf(fabsf(x01.x), fabsf(o0.x)), fabsf(o1.x)), fabsf(o2.x));
-        const float pk1 = fmaxf(fmaxf(fmaxf(fabsf(x01.y), fabsf(o0.y)), fabsf(o1.y)), fabsf(o2.y));
-        if (r < nvalid) best = fmaxf(best, pk0);
-        if (r + 1 < nvalid) best = fmaxf(best, pk1);
-      }
-#else
       float w[kTpRun + kTp4Halo];
 #pragma unroll
-      for (int k = 0; k < kTpRun + kTp4Halo; ++k) {
-        const int u = kTpRun * lane + k;
-        w[k] = row[u + (u >> 3)];
-      }
+      for (int k = 0; k < kTpRun + kTp4Halo; ++k) w[k] = lrow[k + (k >> 3)];  // tile column of window index k: 9 lane + k + (k >> 3)
 #pragma unroll
       for (int r = 0; r < kTpRun; ++r) {
         // first tap: 0.0 + p == p (up to the sign of zero, which |.| discards), so the sums start at the product
@@ -519,9 +469,8 @@ __global__ void __launch_bounds__(kTpTile) k_true_peak4(LoudBatchArgs a, TruePea
         }
         // NaN input: fmaxf drops NaN exactly like Rust's f32::max in TruePeakMeter::process.
         const float pk = fmaxf(fmaxf(fmaxf(fabsf(w[kTp4Halo + r]), fabsf(o0)), fabsf(o1)), fabsf(o2));
-        if (base + (uint64_t)(kTpRun * lane + r) < f1) best = fmaxf(best, pk);
+        if (r < nvalid) best = fmaxf(best, pk);
       }
-#endif
     }
     __syncthreads();
   }
@@ -687,8 +636,6 @@ int LoudnessPlan::init(const omb_loudness_config& c, uint32_t ch, const uint8_t*
   k_weighting_host((double)sample_rate, kw.b, kw.a);
   true_peak_fir4_host(fir.fir4);
   true_peak_fir2_host(fir.fir2);
-  for (int i = 0; i < 12; ++i)
-    for (int ph = 0; ph < 3; ++ph) fir.fir4p[i][ph] = make_float2(fir.fir4[i][ph], fir.fir4[i][ph]);
   static const float kWindows[kLoudWindows] = {3.0f, 0.4f, 0.3f, 1.0f};  // loudness/processor.rs:13
   for (int w = 0; w < kLoudWindows; ++w) caps[w] = std::max<uint64_t>(loudness_window_length(sample_rate, kWindows[w]), 1);
   tp_delay_len = (double)sample_rate < 96000.0 ? 12 : ((double)sample_rate < 192000.0 ? 24 : 0);

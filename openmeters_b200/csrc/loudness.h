@@ -10,7 +10,7 @@ constexpr int kKwChunk = 256;          // samples per chunk of the chunk-paralle
 constexpr int kKwSeg = 64;             // chunks per segment of the three-level state scan
 
 struct KWeight { double b[5], a[5]; };
-struct TruePeakFir { float fir4[12][3]; float fir2[24]; float2 fir4p[12][3]; };  // fir4p: (c, c) pairs for packed FP32x2 multiplies
+struct TruePeakFir { float fir4[12][3]; float fir2[24]; };
 
 // ---- streaming (exact, sequential per channel) state, one per channel, device resident
 struct LoudChannelState {

@@ -11,8 +11,6 @@ LoudnessStream::LoudnessStream(const omb_loudness_config& c) : cfg(c), sample_ra
   sample_rate = c.sample_rate;                           // config kept as given (a NaN rate re-derives on first block)
   true_peak_fir4_host(fir.fir4);
   true_peak_fir2_host(fir.fir2);
-  for (int i = 0; i < 12; ++i)
-    for (int ph = 0; ph < 3; ++ph) fir.fir4p[i][ph] = make_float2(fir.fir4[i][ph], fir.fir4[i][ph]);
 }
 
 LoudnessStream::~LoudnessStream() {
