@@ -91,10 +91,13 @@ __device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const flo
 // between passes 2 and 3 / 1 and 2): frequency-domain ownership becomes tf + 256 j, tf = (t >> 4) + 16 (t & 15).
 // (Pass-1 twiddles are always computed from the 4 rows kept in shared memory: measured fastest, and the 22 KB
 // saved pay for the power-of-two ring.)
+// kVariant bit 2: hop is a multiple of 4 but not of 512 (the settings UI's N/16 ... N/128): a frame's ring origin is then
+// not 512-aligned, so the wrap is applied per thread (one more LOP3 per ring read) instead of per warp-uniform row.
 template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
   constexpr int kTw2 = kVariant & 1;
   constexpr bool kLocal = (kVariant & 2) != 0;
+  constexpr bool kAnyHop = (kVariant & 4) != 0;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
   float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
@@ -161,12 +164,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
       }
       const uint64_t f = fa0 + g;
       if (f < f_end) {
-        const int r0 = (int)(f * (uint64_t)hop) & ring_mask;  // multiple of 512
+        const int r0 = (int)(f * (uint64_t)hop) & ring_mask;  // multiple of 512 unless kAnyHop (then of 4)
         float2 v[16];
         // ---- F: z[n] = x[2n] + j x[2n+1], n = t + 256 j
         // ring position of sample s is s & mask; (r0 + 512 j) & mask is warp-uniform, 2t < 512 never carries
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(ring + ((r0 + 2 * kT * j) & ring_mask) + 2 * t);
+        for (int j = 0; j < 16; ++j)
+          v[j] = kAnyHop ? *reinterpret_cast<const float2*>(ring + ((r0 + 2 * kT * j + 2 * t) & ring_mask))
+                         : *reinterpret_cast<const float2*>(ring + ((r0 + 2 * kT * j) & ring_mask) + 2 * t);
         fft_forward<f16::kAll, kTw2, kLocal>(v, gs.W, tw1t, tw2o, adf, g);
 #pragma unroll
         for (int q = 0; q < 16; ++q) gs.W[adf.pC + q] = v[q];
@@ -234,7 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           for (int j = 0; j < 16; ++j) {
             float wv = win[kT * j];
             if (wsel == 2) wv *= ramp0 + (float)(kT * j);       // t*h window, processor.rs:601-608
-            const float cx = fmaf((float)kM, ring[((r0 + off + kT * j) & ring_mask) + t], bias);
+            const float xs = kAnyHop ? ring[(r0 + off + kT * j + t) & ring_mask] : ring[((r0 + off + kT * j) & ring_mask) + t];
+            const float cx = fmaf((float)kM, xs, bias);
             v[j] = make_float2(cx * wv, gs.Y[t + kT * j] * wv);
           }
           fft_forward<f16::kFirst9, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
@@ -310,7 +316,10 @@ size_t smem_bytes(uint64_t hop) { return sizeof(Smem2) + (size_t)ring_len_for(ho
 
 bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev) {
   if (!cfg.reassign || cfg.window != (uint64_t)kM || cfg.zero_pad != 1) return false;
-  if (cfg.hop < 512 || (cfg.hop % 512) != 0 || cfg.hop > 2048) return false;
+  // hop: multiples of 512 up to 2048 (warp-uniform ring rows), or any multiple of 4 below 512 (per-thread wrap; the
+  // 16-byte async copies need hop % 4 == 0) — of the UI's N/4 ... N/128 only N/6 = 682 falls to the shared-memory tier
+  if (cfg.hop > 2048 || cfg.hop < 4 || (cfg.hop % 4) != 0) return false;
+  if (cfg.hop >= 512 && (cfg.hop % 512) != 0) return false;
   return dev.max_smem_optin == 0 || smem_bytes(cfg.hop) <= (size_t)dev.max_smem_optin;
 }
 
@@ -319,6 +328,7 @@ int stft_fast2_prepare(StftPlan& plan) {
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
 }
 
@@ -343,7 +353,9 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
   static const int variant = [] { const char* e = getenv("OMB_FAST2_VARIANT"); return e ? atoi(e) & 3 : 2; }();
   const size_t smem = smem_bytes(a.hop);
-  if (variant == 1) {
+  if ((a.hop % 512) != 0) {
+    OMB_LAUNCH(k_reassigned_fast2<6>, dim3(grid), dim3(kThreads), smem, s, fa);
+  } else if (variant == 1) {
     OMB_LAUNCH(k_reassigned_fast2<1>, dim3(grid), dim3(kThreads), smem, s, fa);
   } else if (variant >= 2) {
     OMB_LAUNCH(k_reassigned_fast2<2>, dim3(grid), dim3(kThreads), smem, s, fa);

@@ -72,11 +72,12 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
   // OMB_FAST_KERNEL=1|2 pins the specialised kernel generation (measurement / cross-checks); default: newest that fits
   const char* pin = getenv("OMB_FAST_KERNEL");
   const int want = pin ? atoi(pin) : 2;
-  if (choice != OMB_KERNEL_GENERIC && stft_fast_supported(cfg, dev)) {
+  const bool gen1 = stft_fast_supported(cfg, dev), gen2 = want >= 2 && stft_fast2_supported(cfg, dev);
+  if (choice != OMB_KERNEL_GENERIC && (gen1 || gen2)) {
     OMB_TRY(stft_fast_prepare(*this));  // uploads the twiddle tables both generations use
     fast = true;
     fast_kind = 1;
-    if (want >= 2 && stft_fast2_supported(cfg, dev)) {
+    if (gen2) {  // also the only specialised kernel for hops below 512
       OMB_TRY(stft_fast2_prepare(*this));
       fast_kind = 2;
     }

@@ -68,6 +68,19 @@ def test_specialised_kernel_other_hops_and_windows(emu):
         cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
 
 
+@pytest.mark.parametrize("hop", [256, 128, 64, 32, 100])
+def test_specialised_kernel_small_hops(emu, hop):
+    """The settings UI's N/16 ... N/128 hops (and any other multiple of 4 below 512) at N = 4096: frames whose ring origin is
+    not 512-aligned; enough frames that a run walks past the end of the 16384-sample ring (frames x hop + 8192 > 16384) and
+    splits into several runs; odd frame count."""
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=hop, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    frames = max(45, 9000 // hop) | 1
+    n = 8192 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(2, (n + 64) / 48000.0)[:, :n]
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 2 * frames and st["unmatched"] <= 2e-3 * st["pts"] + 2
+
+
 def test_host_path_pipelined_lane_chunks(emu):
     """execute_host pipelines lane chunks over three streams when a specialised kernel is active (>= 4 lanes)."""
     cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)

@@ -215,6 +215,29 @@ def test_cfg5_reassigned_batch(product, kernel):
     assert st["cols"] == 4 * ((96000 * 2 - 16384) // 2048 + 1)
 
 
+# ---------------------------------------------------------------- N = 4096 at the UI's small hops (N/16 ... N/128)
+@pytest.mark.parametrize("hop", [256, 64, 32])
+def test_cfg2_small_hops(product, hop):
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=hop, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    frames = 601
+    n = 8192 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(3, (n + 64) / 48000.0)[:, :n]
+    st = cases.stft_parity(product.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 3 * frames
+    # the streaming processor takes the same kernel (its FIFO stays 16-byte aligned at these hops)
+    p = product.Spectrogram(SpectrogramConfig(fft_size=4096, hop_size=hop, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True,
+                                              history_length=8192))
+    cols = []
+    for s0 in range(0, 8192 + 40 * hop, 1000):
+        up = p.process_block(AudioBlock(lanes[0, s0:min(s0 + 1000, 8192 + 40 * hop)], 1, 48000.0))
+        if up is not None:
+            cols += list(up.new_columns)
+    ref_pts, ref_cnt = cases.oracle_py.stft_batch(cfg, lanes[:1, :8192 + 40 * hop])
+    assert len(cols) == ref_cnt.shape[1] == 41
+    for f, c in enumerate(cols):
+        parity.compare_reassigned_column(np.asarray(c), ref_pts[0, f, :ref_cnt[0, f]], sr=48000.0, fft_len=4096, window=4096, hop=hop)
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_cases(product):
     cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)

@@ -39,7 +39,11 @@ def main():
     dev = torch.device("cuda", 0)
     st = torch.cuda.current_stream(dev).cuda_stream
     # (spectrogram/processor.rs:47-59) product defaults first, then the grid
-    grid = [(2048, 64, 1, capi.WINDOW_HANN, True), (2048, 64, 1, capi.WINDOW_HANN, False)] + settings_grid()
+    grid = [(2048, 64, 1, capi.WINDOW_HANN, True), (2048, 64, 1, capi.WINDOW_HANN, False),
+            # N = 4096 reassigned at every power-of-two hop of the UI (N/4 ... N/128)
+            (4096, 1024, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 512, 1, capi.WINDOW_BLACKMAN_HARRIS, True),
+            (4096, 256, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 128, 1, capi.WINDOW_BLACKMAN_HARRIS, True),
+            (4096, 64, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 32, 1, capi.WINDOW_BLACKMAN_HARRIS, True)] + settings_grid()
     base = synth.cfg2_lanes(8, 4.0)
     res = []
     for n, hop, zp, window, reassign in grid:
