@@ -346,6 +346,7 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.norm_dc = plan.h_norm[0];
   const uint64_t ctas = (uint64_t)std::max(plan.dev.sm_count, 1);
   uint64_t run = 128;  // even, so both groups stay busy; long enough to amortise the ring prime
+  if (a.hop < 512) run *= 512 / a.hop;  // small hops: the prime is worth 8192 / hop frames of new samples
   while (run > 16 && ((per_lane + run - 1) / run) * a.n_lanes < ctas * 6) run >>= 1;
   fa.frames_per_run = (uint32_t)std::min<uint64_t>(run, per_lane);
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);

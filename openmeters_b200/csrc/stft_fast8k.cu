@@ -96,7 +96,7 @@ __device__ __forceinline__ void ring_fetch(float* ring, int L, int p0, const flo
 
 __device__ __forceinline__ int wrap(int p, int L) { return p - ((p >= L) ? L : 0); }
 
-template <int kTw2>
+template <int kTw2, bool kAnyHop>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem8k& sm = *reinterpret_cast<Smem8k*>(smem_raw);
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
   const bool wrap_j = (g == 0 && t == 0);  // partner element index (16 - j) & 15 instead of 15 - j
   const float* dwin = a.dwin + t;
+  const int ts2 = kAnyHop ? 2 * t : 0, ts1 = kAnyHop ? t : 0;
   __syncthreads();
 
   for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
@@ -152,16 +153,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
       async_commit();
 
       // The frame occupies ring positions [r0, r0 + H) mod L: offsets below `split` are reached from lo, the rest
-      // from hi = lo - L (split is a multiple of 512, so a 512-sample block never straddles the wrap).
+      // from hi = lo - L (for hops that are multiples of 512 split is one too, and a 512-sample block never straddles the wrap).
       const float* lo = ring + r0;
       const float* hi = lo - L;
       const int split = L - r0;
+      // hops that are not multiples of 512 (the UI's N/32 ... N/128; always multiples of 4): a 512-sample block may
+      // straddle the wrap, so the side is chosen per thread (kAnyHop; ts2 / ts1 are compile-time 0 for the aligned hops)
       float2 v[16];
       // ---- F: z[n] = x[2n] + j x[2n+1]; group 0: z[n] + z[n+4096], group 1: (z[n] - z[n+4096]) W_8192^n, n = t + 256 j
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float2 za = *reinterpret_cast<const float2*>((512 * j < split ? lo : hi) + 512 * j + 2 * t);
-        const float2 zb = *reinterpret_cast<const float2*>((512 * j + kN8 < split ? lo : hi) + 512 * j + kN8 + 2 * t);
+        const float2 za = *reinterpret_cast<const float2*>((512 * j + ts2 < split ? lo : hi) + 512 * j + 2 * t);
+        const float2 zb = *reinterpret_cast<const float2*>((512 * j + kN8 + ts2 < split ? lo : hi) + 512 * j + kN8 + 2 * t);
         if (g == 0) {
           v[j] = f16::cadd2(za, zb);
         } else {
@@ -266,8 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
             wa_ *= ramp0 + (float)n;
             wb_ *= ramp0 + (float)(n + kSub);
           }
-          const float xa = fmaf((float)kN8, ((off + n < split ? lo : hi) + off + n)[t], bias);
-          const float xb = fmaf((float)kN8, ((off + n + kSub < split ? lo : hi) + off + n + kSub)[t], bias);
+          const float xa = fmaf((float)kN8, ((off + n + ts1 < split ? lo : hi) + off + n)[t], bias);
+          const float xb = fmaf((float)kN8, ((off + n + kSub + ts1 < split ? lo : hi) + off + n + kSub)[t], bias);
           const float2 ca = make_float2(xa * wa_, sm.Y[t + n] * wa_);
           const float2 cb = make_float2(xb * wb_, sm.Y[t + n + kSub] * wb_);
           if (g == 0) {
@@ -360,7 +363,8 @@ size_t smem_bytes(uint64_t hop) { return sizeof(Smem8k) + (size_t)ring_len_for(h
 
 bool stft_fast8k_supported(const StftConfig& cfg, const DeviceInfo& dev) {
   if (!cfg.reassign || cfg.window != (uint64_t)kN8 || cfg.zero_pad != 1) return false;
-  if (cfg.hop < 512 || (cfg.hop % 512) != 0 || cfg.hop > 2048) return false;
+  // multiples of 512 up to 2048, or any multiple of 4 below 512 (per-thread ring wrap; the async copies need hop % 4 == 0)
+  if (cfg.hop > 2048 || cfg.hop < 4 || (cfg.hop % 4) != 0 || (cfg.hop >= 512 && (cfg.hop % 512) != 0)) return false;
   return dev.max_smem_optin == 0 || smem_bytes(cfg.hop) <= (size_t)dev.max_smem_optin;
 }
 
@@ -380,7 +384,10 @@ int stft_fast8k_prepare(StftPlan& plan) {
     }
   OMB_TRY(plan.d_fast_tables.upload(tab, plan.stream));
   const int smem = (int)smem_bytes(plan.cfg.hop);
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_8k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  auto k_aligned = k_reassigned_8k<0, false>;
+  auto k_any = k_reassigned_8k<0, true>;
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_aligned, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_any, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
 }
 
@@ -398,12 +405,19 @@ int launch_stft_fast8k(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) 
   fa.norm_dc = plan.h_norm[0];
   const uint64_t ctas = (uint64_t)std::max(plan.dev.sm_count, 1);
   uint64_t run = 64;  // long enough to amortise the ring prime (H samples vs hop per frame)
+  if (a.hop < 512) run *= 512 / a.hop;  // small hops: the prime is worth 16384 / hop frames of new samples
   while (run > 8 && ((per_lane + run - 1) / run) * a.n_lanes < ctas * 6) run >>= 1;
   fa.frames_per_run = (uint32_t)std::min<uint64_t>(run, per_lane);
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
-  OMB_LAUNCH(k_reassigned_8k<0>, dim3(grid), dim3(kThreads), smem_bytes(a.hop), s, fa);
+  auto k_aligned = k_reassigned_8k<0, false>;
+  auto k_any = k_reassigned_8k<0, true>;
+  if ((a.hop % 512) == 0) {
+    OMB_LAUNCH(k_aligned, dim3(grid), dim3(kThreads), smem_bytes(a.hop), s, fa);
+  } else {
+    OMB_LAUNCH(k_any, dim3(grid), dim3(kThreads), smem_bytes(a.hop), s, fa);
+  }
   OMB_CHECK_LAUNCH();
   return OMB_OK;
 }

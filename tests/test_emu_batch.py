@@ -81,6 +81,18 @@ def test_specialised_kernel_small_hops(emu, hop):
     assert st["cols"] == 2 * frames and st["unmatched"] <= 2e-3 * st["pts"] + 2
 
 
+@pytest.mark.parametrize("hop", [256, 64])
+def test_8k_kernel_small_hops(emu, hop):
+    """stft_fast8k.cu at hops that are not multiples of 512: per-thread ring wrap (ring = 16384 + hop samples, so a run
+    of more than 1 + 16384 / hop ... frames wraps; 70 / 270 frames here)."""
+    cfg = SpectrogramConfig(sample_rate=96000.0, fft_size=8192, hop_size=hop, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    frames = (17000 // hop + 4) | 1
+    n = 16384 + (frames - 1) * hop
+    lanes = synth.cfg5_lanes(1, n)[:, :n]
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == frames
+
+
 def test_host_path_pipelined_lane_chunks(emu):
     """execute_host pipelines lane chunks over three streams when a specialised kernel is active (>= 4 lanes)."""
     cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
