@@ -264,3 +264,78 @@ def test_settings_grid(product, n, hop, zp, window, reassign):
     """Every reachable (size, hop, zero padding, window, mode) combination has a kernel and matches the oracle —
     whichever tier (specialised / shared-memory / generic) the plan picks."""
     cases.settings_grid_case(product.api, n, hop, zp, window, reassign)
+
+
+# ---------------------------------------------------------------- size-independent properties of the other rows, at full BASELINE sizes
+def test_cfg1_properties_large(product):
+    """cfg1 at a size the oracle is not run on (256 lanes x 2^18 samples = 1.3e5 frames): frame independence — a column depends
+    only on its 1024 samples, so a batch shifted by whole hops reproduces the same u16 codes bit for bit — plus the code range."""
+    L, S = 256, 1 << 18
+    base = synth.cfg2_lanes(8, S / 48000.0)[:, :S]
+    lanes = np.concatenate([np.roll(base, 977 * r, axis=1) * np.float32(1.0 - 0.01 * r) for r in range(L // 8)], 0)
+    cfg = SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False)
+    plan = batch.StftPlan(cfg, api=product.api)
+    codes = plan.execute_host(lanes)
+    F = (S - 1024) // 512 + 1
+    assert codes.shape == (L, F, 513)
+    sub = np.ascontiguousarray(lanes[40:43, 200 * 512: 200 * 512 + 1024 + 99 * 512])
+    assert np.array_equal(plan.execute_host(sub), codes[40:43, 200:300])
+    assert codes.min() >= 1680  # -140 dB floor = code round(4 * 65535 / 156); nothing below it (spectrogram/processor.rs:103-108)
+    # a louder copy never codes lower, and +6.0206 dB is 2529.2 codes wherever neither side clips at the floor
+    c2 = plan.execute_host((sub * np.float32(2.0)).astype(np.float32)).astype(np.int64)
+    c1 = codes[40:43, 200:300].astype(np.int64)
+    assert np.all(c2 >= c1)
+    free = c1 > 1680
+    assert np.all(np.abs((c2 - c1)[free] - 2529.24) <= 1.1)
+
+
+def test_cfg3_properties_large(product):
+    """cfg3 at BASELINE size (16 streams x 30 s x 8 ch): gain linearity of every output (x0.5 -> -6.0206 dB exactly where the
+    floor is not hit; f64 mean squares scale exactly by 0.25, true-peak FIR sums scale exactly), stream independence."""
+    x = synth.cfg3_surround(30.0)
+    streams = np.stack([x * np.float32(1.0 - 0.02 * i) for i in range(16)]).astype(np.float32)
+    plan = batch.LoudnessPlan(LoudnessConfig(), 8, capi.SURROUND, api=product.api)
+    sa, nb = plan.execute_host(streams, 1024)
+    A = batch.snapshots_to_arrays(sa, nb * 16)
+    sh, nb2 = plan.execute_host((streams[3:5] * np.float32(0.5)).astype(np.float32), 1024)
+    Hh = batch.snapshots_to_arrays(sh, nb * 2)
+    assert nb2 == nb
+    shift = np.float32(20.0 * np.log10(0.5))
+    for k in A:
+        a = A[k].reshape(16, nb, -1)[3:5].reshape(Hh[k].shape)
+        live = (a > -99.0) & (Hh[k] > -99.0)  # away from the floors (-99.9 LUFS / -140 dB)
+        assert live.mean() > 0.5, k
+        assert np.max(np.abs(Hh[k][live] - (a[live] + shift))) <= 2e-5, (k, float(np.max(np.abs(Hh[k][live] - (a[live] + shift)))))
+    # stream independence: the same two streams alone give the same snapshots bit for bit
+    s2, _ = plan.execute_host(np.ascontiguousarray(streams[3:5]), 1024)
+    B = batch.snapshots_to_arrays(s2, nb * 2)
+    for k in A:
+        assert np.array_equal(B[k], A[k].reshape(16, nb, -1)[3:5].reshape(B[k].shape)), k
+
+
+def test_cfg4_properties_large(product):
+    """cfg4 at BASELINE width (128 lanes x 5 s): the peak-hold trace dominates the unsmoothed one hop by hop and never falls
+    faster than the configured decay; lane independence; x2 gain = +6.0206 dB on every bin above the floor."""
+    L, S = 128, 240000
+    base = synth.cfg4_streams(4, S / 48000.0).reshape(8, -1)[:, :S]
+    lanes = np.concatenate([np.roll(base, 977 * r, axis=1) * np.float32(1.0 - 0.01 * r) for r in range(L // 8)], 0)
+    hold_cfg = SpectrumConfig(fft_size=16384, hop_size=1024, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0, floor_db=-100.0)
+    none_cfg = SpectrumConfig(fft_size=16384, hop_size=1024, averaging=capi.AVG_NONE, floor_db=-100.0)
+    hold = batch.SpectrumPlan(hold_cfg, api=product.api)
+    wh, rh, pkh = hold.execute_host(lanes)
+    sub = np.ascontiguousarray(lanes[17:20])
+    wn, rn, _ = batch.SpectrumPlan(none_cfg, api=product.api).execute_host(sub)
+    rs = rh[17:20]
+    assert np.all(rs >= rn - 1e-4)                              # hold = max(hold * decay, p) >= p
+    step = 12.0 * 1024.0 / 48000.0                               # dB per hop (spectrum/processor.rs:380-388)
+    drop = rs[:, :-1] - rs[:, 1:]
+    falling = rs[:, 1:] > -100.0
+    assert np.max(drop[falling]) <= step + 1e-3
+    # lane independence (the fused kernel serves the big batch, the two-kernel path the small one): same dB within the budget
+    w3, r3, pk3 = hold.execute_host(sub)
+    parity.compare_db(r3, rs, -100.0)
+    parity.compare_db(w3, wh[17:20], -100.0)
+    # gain
+    w2, r2, _ = hold.execute_host((sub * np.float32(2.0)).astype(np.float32))
+    live = (r3 > -90.0)
+    assert np.max(np.abs(r2[live] - r3[live] - 6.0206)) <= 1e-3
