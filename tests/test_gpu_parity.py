@@ -326,7 +326,9 @@ def test_cfg4_properties_large(product):
     sub = np.ascontiguousarray(lanes[17:20])
     wn, rn, _ = batch.SpectrumPlan(none_cfg, api=product.api).execute_host(sub)
     rs = rh[17:20]
-    assert np.all(rs >= rn - 1e-4)                              # hold = max(hold * decay, p) >= p
+    # hold = max(hold * decay, p) >= p — across two kernels (fused batch vs the two-kernel path), so up to the parity budget
+    ph, pn = 10.0 ** (rs.astype(np.float64) / 10.0), 10.0 ** (rn.astype(np.float64) / 10.0)
+    assert np.all(ph >= pn - 2e-5 * np.maximum(pn, pn.max(axis=-1, keepdims=True) * 1e-3))
     step = 12.0 * 1024.0 / 48000.0                               # dB per hop (spectrum/processor.rs:380-388)
     drop = rs[:, :-1] - rs[:, 1:]
     falling = rs[:, 1:] > -100.0

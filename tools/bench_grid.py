@@ -44,6 +44,8 @@ def main():
             (4096, 1024, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 512, 1, capi.WINDOW_BLACKMAN_HARRIS, True),
             (4096, 256, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 128, 1, capi.WINDOW_BLACKMAN_HARRIS, True),
             (4096, 64, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 32, 1, capi.WINDOW_BLACKMAN_HARRIS, True)] + settings_grid()
+    if "--first" in sys.argv:  # e.g. --first 1: only the product default (short enough to run under ncu)
+        grid = grid[:int(sys.argv[sys.argv.index("--first") + 1])]
     base = synth.cfg2_lanes(8, 4.0)
     res = []
     for n, hop, zp, window, reassign in grid:
