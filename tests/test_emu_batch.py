@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from openmeters_b200 import _capi as capi
-from openmeters_b200 import synth
+from openmeters_b200 import batch, synth
 from openmeters_b200.processors import LoudnessConfig, SpectrogramConfig, SpectrumConfig
 from tests import cases, parity
 
@@ -91,6 +91,31 @@ def test_8k_kernel_small_hops(emu, hop):
     lanes = synth.cfg5_lanes(1, n)[:, :n]
     st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
     assert st["cols"] == frames
+
+
+@pytest.mark.parametrize("hop,frames,window", [(512, 9, capi.WINDOW_HANN), (64, 150, capi.WINDOW_BLACKMAN_HARRIS), (100, 45, capi.WINDOW_HAMMING),
+                                               (1024, 6, capi.WINDOW_HANN), (16, 300, capi.WINDOW_HANN)])
+def test_2k_kernel_two_frames_per_transform(emu, hop, frames, window):
+    """stft_fast2k.cu (N = 2048, the product's default size): two interleaved frames per 4096-point transform, separated in
+    registers.  Frame counts of every residue mod 4 (missing second frame / idle second group at the tail of a run), ring
+    wrap-around (ring 8192 or 16384 samples), hops that are not powers of two."""
+    cfg = SpectrogramConfig(fft_size=2048, hop_size=hop, window=window, use_reassignment=True)
+    n = 4096 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(2, (n + 64) / 48000.0)[:, :n]
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 2 * frames and st["unmatched"] <= 2e-3 * st["pts"] + 2
+
+
+def test_2k_kernel_single_frame_and_silence(emu):
+    cfg = SpectrogramConfig(fft_size=2048, hop_size=64, window=capi.WINDOW_HANN, use_reassignment=True)
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=emu.api)
+    assert plan.kernel_generation == 5
+    lanes = np.zeros((3, 4096), np.float32)
+    lanes[1] = 0.25
+    lanes[2] = synth.cfg2_lanes(1, 4096 / 48000.0)[0, :4096]
+    pts, cnt = plan.execute_host(lanes)
+    assert cnt.shape == (3, 1) and cnt[0, 0] == 0 and cnt[1, 0] == 0 and cnt[2, 0] > 500  # silence, DC -> empty columns
+    assert np.all(np.isfinite(pts[2, 0, :cnt[2, 0]]))
 
 
 def test_host_path_pipelined_lane_chunks(emu):

@@ -238,6 +238,24 @@ def test_cfg2_small_hops(product, hop):
         parity.compare_reassigned_column(np.asarray(c), ref_pts[0, f, :ref_cnt[0, f]], sr=48000.0, fft_len=4096, window=4096, hop=hop)
 
 
+# ---------------------------------------------------------------- N = 2048: the product's default analysis size
+@pytest.mark.parametrize("hop,window", [(64, capi.WINDOW_HANN), (512, capi.WINDOW_BLACKMAN_HARRIS), (16, capi.WINDOW_HANN)])
+def test_default_size_2048(product, hop, window):
+    """spectrogram/processor.rs:47-59 defaults (2048 / 64 / Hann / reassigned) and neighbours through stft_fast2k.cu, against the
+    oracle and against the shared-memory tier on the same device."""
+    cfg = SpectrogramConfig(fft_size=2048, hop_size=hop, window=window, use_reassignment=True)
+    frames = 803
+    n = 4096 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(3, (n + 64) / 48000.0)[:, :n]
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=product.api)
+    assert plan.kernel_generation == 5
+    st = cases.stft_parity(product.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 3 * frames
+    pa, ca = plan.execute_host(lanes)
+    pb, cb = batch.StftPlan(cfg, kernel=capi.KERNEL_GENERIC, api=product.api).execute_host(lanes)
+    parity.compare_reassigned(pa, ca, pb, cb, sr=48000.0, fft_len=2048, window=2048, hop=hop)
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_cases(product):
     cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
