@@ -42,7 +42,7 @@ struct Fast2kArgs {
 
 struct GroupSmem {
   float2 W[kWSize];
-  float Y[kFramesPerGroup][kN2];         // Y[fr][n] = Im c_fr[n]
+  float Y[kFramesPerGroup][kN2 + 16];    // Y[fr][n] = Im c_fr[n]; +16: the two frames of a warp access (same n) hit disjoint banks
   int warp_cnt[kFramesPerGroup][kBinGroups * kWarps];
   int offs[kFramesPerGroup][kBinGroups * kWarps + 1];
   float x0_xm[kFramesPerGroup][2];
