@@ -57,7 +57,7 @@ struct StftPlan {
   DeviceInfo dev;
   int kernel_choice = OMB_KERNEL_AUTO;
   bool fast = false;
-  int fast_kind = 0;  // 0 generic, 1 = stft_fast.cu, 2 = stft_fast2.cu, 3 = stft_classic_fast.cu, 4 = stft_fast8k.cu, 5 = stft_fast2k.cu
+  int fast_kind = 0;  // 0 generic, 1 = stft_fast.cu, 2 = stft_fast2.cu, 3 = stft_classic_fast.cu, 4 = stft_fast8k.cu, 5 = stft_fast2k.cu, 6 = stft_fast1k.cu
   bool smem_kernel = false;  // stft_smem.cu (used when no specialised kernel applies and OMB_KERNEL_GENERIC was not forced)
   float power_scale = 1.0f;
   std::vector<float> h_win, h_dwin, h_twin, h_norm;
@@ -94,6 +94,10 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
 bool stft_fast2k_supported(const StftConfig& cfg, const DeviceInfo& dev);
 int stft_fast2k_prepare(StftPlan& plan);
 int launch_stft_fast2k(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
+// stft_fast1k.cu: reassigned N = 1024 (four interleaved frames per 4096-point transform)
+bool stft_fast1k_supported(const StftConfig& cfg, const DeviceInfo& dev);
+int stft_fast1k_prepare(StftPlan& plan);
+int launch_stft_fast1k(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
 // stft_fast8k.cu: reassigned N = 8192 (two 4096-point sub-transforms per CTA)
 bool stft_fast8k_supported(const StftConfig& cfg, const DeviceInfo& dev);
 int stft_fast8k_prepare(StftPlan& plan);

@@ -1,0 +1,392 @@
+// stft_fast1k.cu — specialised kernel for the reassigned STFT at N = 1024.
+//
+// The interleaving of stft_fast2k.cu one level further: every 4096-point transform of the shared engine carries FOUR
+// consecutive frames, a[4n + r] = F_r[n]:
+//     X[k + 1024 m] = sum_r (-j)^{m r} W^{k r} F_r[k]            (W = e^{-2 pi i / 4096}, k < 1024, m, r < 4)
+// and thread t holds X[t + 256 j] for all j, i.e. the four values m = 0..3 of every bin k = t + 256 j (j < 4): the four
+// 1024-point spectra are separated (before the inverse: combined) in registers by one radix-4 butterfly and three twiddle
+// products per bin.  Thread t owns bins t + 256 j, j < 4, of all four frames in the frequency domain and the samples
+// (t >> 2) + 64 j of frame (t & 3) in the time domain.  Factors 4 of the separation are folded into the pair-step
+// coefficients and the bin normalisation (exact).  One 512-thread CTA = two groups = eight consecutive frames per iteration.
+#include "device_math.cuh"
+#include "fft16.cuh"
+#include "fft4096.cuh"
+#include "stft.h"
+
+namespace omb {
+
+namespace {
+
+using namespace f4k;
+
+constexpr int kN2 = 1024;                // window = complex points per frame
+constexpr int kM = 4096;                 // engine length
+constexpr int kGroupsPerCta = 2;
+constexpr int kFramesPerGroup = 4;
+constexpr int kFramesPerIter = kGroupsPerCta * kFramesPerGroup;
+constexpr int kThreads = kT * kGroupsPerCta;
+constexpr int kWarps = kT / 32;          // warps per group
+constexpr int kWSize = f16::phys_size(kM);
+constexpr int kBinGroups = 3;            // bins t + 256 j, j < 2, and bin 512 (t = 0, j = 2)
+constexpr int kJ = 16 / kFramesPerGroup;  // bins per thread and frame after the separation
+
+struct Fast1kArgs {
+  StftKernelArgs a;
+  const float2* tw1;   // global: [15][256] W_4096^{b q}
+  const float2* tw2;   // global: [15][16]  W_256^{o q}
+  uint32_t frames_per_run, runs_per_lane, ring_len;
+  float norm_ac, norm_dc;  // bin_norm / 16 (the separated spectra are scaled by 4)
+};
+
+struct GroupSmem {
+  float2 W[kWSize];
+  float Y[kFramesPerGroup][kN2 + 8];     // Y[fr][n] = Im c_fr[n]; +8: the four frames of a warp access (same n) hit disjoint banks
+  int warp_cnt[kFramesPerGroup][kBinGroups * kWarps];
+  int offs[kFramesPerGroup][kBinGroups * kWarps + 1];
+  float x0_xm[kFramesPerGroup][2];
+};
+
+struct Smem1k {
+  float2 tw1[4 * kT];   // rows q = 1, 2, 4, 8 of W_4096^{b q}
+  float2 tw2[15 * 16];
+  float h[kN2];
+  float dh[kN2];
+  GroupSmem g[kGroupsPerCta];
+  // float ring[ring_len] follows
+};
+
+__device__ __forceinline__ void k1_async_copy16(float* dst_smem, const float* src_gmem) {
+#ifdef OMB_EMU
+  for (int i = 0; i < 4; ++i) dst_smem[i] = src_gmem[i];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem));
+#endif
+}
+__device__ __forceinline__ void k1_async_commit() {
+#ifndef OMB_EMU
+  asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+__device__ __forceinline__ void k1_async_wait_all() {
+#ifndef OMB_EMU
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void k1_ring_fetch(float* ring, int ring_mask, const float* x, uint64_t s0, uint64_t s1) {
+  for (uint64_t s = s0 + 4ull * threadIdx.x; s < s1; s += 4ull * kThreads) k1_async_copy16(ring + ((int)s & ring_mask), x + s);
+}
+
+// After a forward transform of four interleaved frames: v[j + 4 r] <- 4 F_r[t + 256 j], j, r < 4.
+// (c0, s0) = (cos, sin)(2 pi t / 4096); the bin's angle adds 2 pi j / 16.
+__device__ __forceinline__ void separate4(float2 (&v)[16], float c0, float s0) {
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    const float cj = f16::kCos32[2 * j], sj = f16::kSin32[2 * j];
+    const float2 w1 = make_float2(c0 * cj - s0 * sj, s0 * cj + c0 * sj);  // conj(W^k) = (cos, +sin)
+    const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    // sum_m (+j)^{m r} X[k + 1024 m] = 4 W^{k r} F_r[k]
+    f16::radix4<true>(v[j], v[j + 4], v[j + 8], v[j + 12]);
+    v[j + 4] = cmul(v[j + 4], w1);
+    v[j + 8] = cmul(v[j + 8], w2);
+    v[j + 12] = cmul(v[j + 12], w3);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa) {
+  constexpr int kTw2 = 0;
+  OMB_DYN_SMEM(unsigned char, smem_raw);
+  Smem1k& sm = *reinterpret_cast<Smem1k*>(smem_raw);
+  float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem1k));
+  const StftKernelArgs& a = fa.a;
+  const int tid = threadIdx.x, t = tid & (kT - 1), lane_id = t & 31, warp = t >> 5;
+  const int g = __shfl_sync(0xffffffffu, tid >> 8, 0);
+  GroupSmem& gs = sm.g[g];
+  const int hop = (int)a.hop, H = 2 * kN2, ring_mask = (int)fa.ring_len - 1;  // ring_len is a power of two
+  const int off = (H - kN2) / 2;
+  const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
+  const ReassignConsts rc{a.bin_hz, a.max_hz, a.inv_2pi, a.inv_hop, a.latency_hops};
+
+  for (int i = tid; i < 4 * kT; i += kThreads) {
+    const int row = (1 << (i >> 8)) - 1;  // q - 1 for q = 1, 2, 4, 8
+    sm.tw1[i] = __ldg(&fa.tw1[row * kT + (i & (kT - 1))]);
+  }
+  for (int i = tid; i < 15 * 16; i += kThreads) sm.tw2[i] = __ldg(&fa.tw2[i]);
+  for (int i = tid; i < kN2; i += kThreads) {
+    sm.h[i] = __ldg(&a.win[i]);
+    sm.dh[i] = __ldg(&a.dwin[i]);
+  }
+  Addr ad;
+  ad.pA = t + (t >> 4);
+  ad.pB = 273 * (t >> 4) + (t & 15);
+  ad.pC = 273 * (t & 15) + 17 * (t >> 4);
+  const float2* tw1t = sm.tw1 + t;
+  const float2* tw2o = sm.tw2 + (t & 15);
+  float cos_t, sin_t;  // separation twiddle angle of bin t: 2 pi t / 4096 (the Hilbert pair-step angle, H = 2048, is twice that)
+  sincospif((float)t / 2048.0f, &sin_t, &cos_t);
+  const int par = t & 3, hh = t >> 2;  // time domain: this thread's samples are hh + 64 j of frame `par`
+  const float sign = (hh & 1) ? -1.0f : 1.0f;
+  const float ramp0 = (float)hh - (float)(kN2 - 1) * 0.5f;  // n - (N-1)/2 at j = 0
+  const int pt = (kT - t) & (kT - 1);  // owner of the partner bins 1024 - (t + 256 j)
+  const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
+  __syncthreads();
+
+  for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
+    const uint64_t lane = run / fa.runs_per_lane;
+    const uint64_t f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
+    const uint64_t f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+    const float* x = a.lanes + lane * a.lane_stride;
+    const uint64_t s_end = (f_end - 1) * (uint64_t)hop + (uint64_t)H;  // one past the last sample this run reads
+    {  // prime: everything the first eight frames read
+      const uint64_t s0 = f_begin * (uint64_t)hop;
+      const uint64_t want = s0 + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
+      k1_ring_fetch(ring, ring_mask, x, s0, want < s_end ? want : s_end);
+      k1_async_commit();
+    }
+    for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kFramesPerIter) {
+      k1_async_wait_all();
+      __syncthreads();  // ring holds frames fa0 .. fa0+7; both groups are done with the previous eight
+      {                 // prefetch what the next eight frames add: eight hops
+        const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
+        const uint64_t want = s0 + (uint64_t)kFramesPerIter * hop;
+        const uint64_t s1 = want < s_end ? want : s_end;
+        if (s0 < s1) k1_ring_fetch(ring, ring_mask, x, s0, s1);
+        k1_async_commit();
+      }
+      const uint64_t fg = fa0 + (uint64_t)kFramesPerGroup * g;  // this group's frames: fg .. fg + 3
+      if (fg < f_end) {
+        // missing frames at the tail of a run are fed as zeros: the four frames share every transform, so stale ring
+        // contents (possibly NaN bit patterns) would leak into the others
+        const bool fvalid = fg + (uint64_t)par < f_end;
+        const int r0 = (int)((fg + par) * (uint64_t)hop) & ring_mask;  // ring origin of this thread's time-domain frame
+        float2 v[16];
+        // ---- F: z_par[n] = x[2n] + j x[2n+1], n = hh + 64 j  (engine input a[t + 256 j] = z_par[(t + 256 j - par) / 4])
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = *reinterpret_cast<const float2*>(ring + ((r0 + 2 * hh + 128 * j) & ring_mask));
+          if (!fvalid) v[j] = make_float2(0.0f, 0.0f);
+        }
+        fft_forward<f16::kAll, kTw2, false>(v, gs.W, tw1t, tw2o, ad, g);
+        separate4(v, cos_t, sin_t);  // v[j + 4 r] = 4 Z_r[t + 256 j]
+#pragma unroll
+        for (int q = 0; q < 16; ++q) gs.W[ad.pC + q] = v[q];
+        if (t == 0) {  // X[0] and X[H/2] of each frame's real spectrum
+#pragma unroll
+          for (int r = 0; r < kFramesPerGroup; ++r) {
+            gs.x0_xm[r][0] = 0.25f * (v[4 * r].x + v[4 * r].y);
+            gs.x0_xm[r][1] = 0.25f * (v[4 * r].x - v[4 * r].y);
+          }
+        }
+        group_sync(g);
+        // ---- X: Q_r[k] = cos(th_k) conj(Z_r[1024-k]) + j sin(th_k) Z_r[k], th_k = 2 pi k / 2048, per frame; then the four
+        //         inverse inputs are combined: X[k + 1024 m] = sum_r (-j)^{m r} W^{k r} Q_r[k]  (factors 1/4 folded: 1/16)
+        {
+          const float2* wp = gs.W + pPartner;
+          float2 zp[16];
+          if (t == 0) {
+#pragma unroll
+            for (int j = 0; j < kJ; ++j)
+#pragma unroll
+              for (int r = 0; r < kFramesPerGroup; ++r) zp[j + 4 * r] = wp[((kJ - j) & (kJ - 1)) + 4 * r];
+          } else {
+#pragma unroll
+            for (int j = 0; j < kJ; ++j)
+#pragma unroll
+              for (int r = 0; r < kFramesPerGroup; ++r) zp[j + 4 * r] = wp[(kJ - 1 - j) + 4 * r];
+          }
+          group_sync(g);
+#pragma unroll
+          for (int j = 0; j < kJ; ++j) {
+            const float cj = f16::kCos32[2 * j], sj = f16::kSin32[2 * j];
+            const float cu = cos_t * cj - sin_t * sj, su = sin_t * cj + cos_t * sj;  // angle 2 pi k / 4096
+            const float c2 = cu * cu - su * su, s2 = 2.0f * cu * su;                   // angle 2 pi k / 2048
+            const float ck = 0.0625f * c2, sk = 0.0625f * s2;
+            const float2 w1 = make_float2(cu, -su);  // W^k
+            const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+            float2 q[kFramesPerGroup];
+#pragma unroll
+            for (int r = 0; r < kFramesPerGroup; ++r) {
+              const float2 z = v[j + 4 * r], zq = zp[j + 4 * r];
+              q[r] = make_float2(ck * zq.x - sk * z.y, sk * z.x - ck * zq.y);
+              if (t == 0 && j == 0) q[r] = make_float2(0.0f, 0.0f);
+            }
+            q[1] = cmul(q[1], w1);
+            q[2] = cmul(q[2], w2);
+            q[3] = cmul(q[3], w3);
+            f16::radix4<false>(q[0], q[1], q[2], q[3]);  // X[k + 1024 m] = sum_r (-j)^{m r} (W^{k r} Q_r)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) v[j + 4 * m] = q[m];
+          }
+        }
+        // ---- I: inverse, DIT; output a[t + 256 q]: sample hh + 64 q of frame par's packed analytic signal; centre half
+        {
+          f16::dft16<true>(v);
+          float2* wc = gs.W + ad.pC;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) wc[q] = v[q];
+          group_sync(g);
+          float2* wb = gs.W + ad.pB;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
+          twiddle15<true, kTw2, false>(v, tw2o, 16);
+          f16::dft16<true>(v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
+          group_sync(g);
+          const float2* wa = gs.W + ad.pA;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = wa[273 * j];
+          twiddle15<true, 1, true>(v, tw1t, kT);
+          f16::dft16p<true, f16::kMid8>(v);
+          // packed index m = hh + 64 q, q = 4..11 -> centre samples: Y[par] as float2[m - 256]
+          float2* y2 = reinterpret_cast<float2*>(gs.Y[par]) + hh;
+#pragma unroll
+          for (int q = 4; q < 12; ++q) y2[64 * (q - 4)] = v[q];
+          group_sync(g);
+        }
+        // ---- G: three windowed transforms of c_par[n] = (N x[off+n] + bias) + j Y[n], n = hh + 64 j
+        const float bias = sign * 0.5f * gs.x0_xm[par][1] - 0.5f * gs.x0_xm[par][0];
+        float2 S[kFramesPerGroup][kBinGroups];
+        float nd[kFramesPerGroup][kBinGroups];
+#pragma unroll 1
+        for (int wsel = 0; wsel < 3; ++wsel) {
+          const float* win = (wsel == 1 ? sm.dh : sm.h) + hh;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float wv = win[64 * j];
+            if (wsel == 2) wv *= ramp0 + (float)(64 * j);       // t*h window, processor.rs:601-608
+            const float cx = fmaf((float)kN2, ring[(r0 + off + hh + 64 * j) & ring_mask], bias);
+            v[j] = fvalid ? make_float2(cx * wv, gs.Y[par][hh + 64 * j] * wv) : make_float2(0.0f, 0.0f);
+          }
+          fft_forward<f16::kAll, kTw2, false>(v, gs.W, tw1t, tw2o, ad, g);
+          separate4(v, cos_t, sin_t);  // v[j + 4 r] = 4 S_r[t + 256 j]
+          if (wsel == 0) {
+#pragma unroll
+            for (int r = 0; r < kFramesPerGroup; ++r)
+#pragma unroll
+              for (int j = 0; j < kBinGroups; ++j) S[r][j] = v[j + 4 * r];
+          } else if (wsel == 1) {
+#pragma unroll
+            for (int r = 0; r < kFramesPerGroup; ++r)
+#pragma unroll
+              for (int j = 0; j < kBinGroups; ++j) nd[r][j] = v[j + 4 * r].y * S[r][j].x - v[j + 4 * r].x * S[r][j].y;
+          }
+          group_sync(g);  // pass-3 reads done before the next pass-1 stores (and before warp_cnt reuse)
+        }
+        // ---- R: reassignment + ordered compaction, per frame (bin order (j, t) as in stft_fast2.cu)
+        omb_spectrogram_point pts[kFramesPerGroup][kBinGroups];
+        int rank[kFramesPerGroup][kBinGroups];
+        unsigned keep = 0;
+#pragma unroll
+        for (int fr = 0; fr < kFramesPerGroup; ++fr)
+#pragma unroll
+          for (int j = 0; j < kBinGroups; ++j) {
+            const int bin = t + kT * j;
+            bool k = (j < kBinGroups - 1 || t == 0);
+            const float norm = (bin == 0 || j == kBinGroups - 1) ? fa.norm_dc : fa.norm_ac;
+            if (k) k = reassign_bin_nd(S[fr][j], nd[fr][j], v[4 * fr + j], norm, bin, rc, &pts[fr][j]);
+            const unsigned m = __ballot_sync(0xffffffffu, k);
+            if (lane_id == 0) gs.warp_cnt[fr][j * kWarps + warp] = __popc(m);
+            if (k) keep |= 1u << (fr * kBinGroups + j);
+            rank[fr][j] = __popc(m & ((1u << lane_id) - 1u));
+          }
+        group_sync(g);
+        if (warp < kFramesPerGroup) {  // warp fr scans frame fr's 24 (bin group, warp) counts, up to two per lane
+          const int i0 = lane_id * 2;
+          const int n_cnt = kBinGroups * kWarps;
+          const int c0 = i0 < n_cnt ? gs.warp_cnt[warp][i0] : 0;
+          const int c1 = i0 + 1 < n_cnt ? gs.warp_cnt[warp][i0 + 1] : 0;
+          const int tot = c0 + c1;
+          int incl = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane_id >= o) incl += n;
+          }
+          const int excl = incl - tot;
+          if (i0 < n_cnt) gs.offs[warp][i0] = excl;
+          if (i0 + 1 < n_cnt) gs.offs[warp][i0 + 1] = excl + c0;
+          if (lane_id == 31) gs.offs[warp][n_cnt] = incl;
+        }
+        group_sync(g);
+#pragma unroll
+        for (int fr = 0; fr < kFramesPerGroup; ++fr) {
+          const uint64_t f = fg + fr;
+          if (f < f_end) {
+            const uint64_t slot = lane * a.frames_per_lane + f;
+            float* out = reinterpret_cast<float*>(a.out_points + slot * a.point_stride);
+#pragma unroll
+            for (int j = 0; j < kBinGroups; ++j)
+              if (keep & (1u << (fr * kBinGroups + j))) {
+                float* o = out + 3 * (gs.offs[fr][j * kWarps + warp] + rank[fr][j]);
+                o[0] = pts[fr][j].time_offset;
+                o[1] = pts[fr][j].freq_hz;
+                o[2] = pts[fr][j].power;
+              }
+            if (t == 0) a.out_counts[slot] = (uint32_t)gs.offs[fr][kBinGroups * kWarps];
+          }
+        }
+      }
+    }
+    k1_async_wait_all();
+    __syncthreads();
+  }
+}
+
+uint32_t ring_len_for(uint64_t hop) { return (uint32_t)next_pow2(2 * (uint64_t)kN2 + (2 * kFramesPerIter - 1) * hop); }
+size_t smem_bytes(uint64_t hop) { return sizeof(Smem1k) + (size_t)ring_len_for(hop) * sizeof(float); }
+
+}  // namespace
+
+bool stft_fast1k_supported(const StftConfig& cfg, const DeviceInfo& dev) {
+  if (!cfg.reassign || cfg.window != (uint64_t)kN2 || cfg.zero_pad != 1) return false;
+  // any multiple of 4 (16-byte async copies) up to N/2: of the UI's N/4 ... N/128 only N/6 = 170 is excluded
+  if (cfg.hop < 4 || (cfg.hop % 4) != 0 || cfg.hop > 512) return false;
+  return dev.max_smem_optin == 0 || smem_bytes(cfg.hop) <= (size_t)dev.max_smem_optin;
+}
+
+int stft_fast1k_prepare(StftPlan& plan) {
+  // twiddle tables of the 4096-point engine: [15*256] W_4096^{b q} | [15*16] W_256^{o q}
+  std::vector<float2> tab(15 * kT + 15 * 16);
+  const double tau = 6.28318530717958647692;
+  for (int q = 1; q < 16; ++q)
+    for (int b = 0; b < kT; ++b) {
+      const double ang = -tau * (double)((b * q) % kM) / (double)kM;
+      tab[(q - 1) * kT + b] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  for (int q = 1; q < 16; ++q)
+    for (int o = 0; o < 16; ++o) {
+      const double ang = -tau * (double)((o * q) % 256) / 256.0;
+      tab[15 * kT + (q - 1) * 16 + o] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  OMB_TRY(plan.d_fast_tables.upload(tab, plan.stream));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast1k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(plan.cfg.hop)));
+  return OMB_OK;
+}
+
+int launch_stft_fast1k(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  if (per_lane == 0 || a.n_lanes == 0) return OMB_OK;
+  if ((reinterpret_cast<uintptr_t>(a.lanes) & 15u) != 0 || (a.lane_stride % 4) != 0)
+    return fail(OMB_ERR_INVALID, "specialised STFT kernel needs 16-byte aligned lanes (pointer and lane_stride % 4 == 0)");
+  Fast1kArgs fa{};
+  fa.a = a;
+  fa.tw1 = plan.d_fast_tables.ptr;
+  fa.tw2 = fa.tw1 + 15 * kT;
+  fa.ring_len = ring_len_for(a.hop);
+  fa.norm_ac = 0.0625f * (plan.h_norm.size() > 1 ? plan.h_norm[1] : plan.h_norm[0]);
+  fa.norm_dc = 0.0625f * plan.h_norm[0];
+  const uint64_t ctas = (uint64_t)std::max(plan.dev.sm_count, 1);
+  uint64_t run = 512;  // multiple of eight, long enough to amortise the ring prime (2048 samples vs hop per frame)
+  if (a.hop < 512) run *= 512 / a.hop;
+  while (run > 16 && ((per_lane + run - 1) / run) * a.n_lanes < ctas * 6) run >>= 1;
+  fa.frames_per_run = (uint32_t)std::min<uint64_t>(run, per_lane);
+  fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
+  const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
+  const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  OMB_LAUNCH(k_reassigned_fast1k, dim3(grid), dim3(kThreads), smem_bytes(a.hop), s, fa);
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+}  // namespace omb

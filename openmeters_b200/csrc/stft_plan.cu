@@ -89,6 +89,10 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
     OMB_TRY(stft_fast2k_prepare(*this));
     fast = true;
     fast_kind = 5;
+  } else if (choice != OMB_KERNEL_GENERIC && stft_fast1k_supported(cfg, dev) && !getenv("OMB_NO_FAST1K")) {
+    OMB_TRY(stft_fast1k_prepare(*this));
+    fast = true;
+    fast_kind = 6;
   } else if (choice != OMB_KERNEL_GENERIC && stft_classic_fast_supported(cfg, dev)) {
     OMB_TRY(stft_classic_fast_prepare(*this));
     fast = true;
@@ -156,7 +160,8 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   if (fast_kind == 3 && aligned8) return launch_stft_classic_fast(*this, a, s);
   if (fast_kind == 4 && aligned16) return launch_stft_fast8k(*this, a, s);
   if (fast_kind == 5 && aligned16) return launch_stft_fast2k(*this, a, s);
-  if (fast && fast_kind != 3 && fast_kind != 4 && fast_kind != 5 && aligned16) return fast_kind == 2 ? launch_stft_fast2(*this, a, s) : launch_stft_fast(*this, a, s);
+  if (fast_kind == 6 && aligned16) return launch_stft_fast1k(*this, a, s);
+  if (fast && fast_kind <= 2 && aligned16) return fast_kind == 2 ? launch_stft_fast2(*this, a, s) : launch_stft_fast(*this, a, s);
   if (fast && kernel_choice == OMB_KERNEL_FAST)
     return fail(OMB_ERR_INVALID, "OMB_KERNEL_FAST was forced but the lanes are not aligned (reassigned: 16 bytes and lane_stride % 4 == 0; classic: 8 bytes and lane_stride % 2 == 0)");
   if (smem_kernel) return launch_stft_smem(*this, a, s, d_scratch);

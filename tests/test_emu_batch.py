@@ -106,6 +106,20 @@ def test_2k_kernel_two_frames_per_transform(emu, hop, frames, window):
     assert st["cols"] == 2 * frames and st["unmatched"] <= 2e-3 * st["pts"] + 2
 
 
+@pytest.mark.parametrize("hop,frames,window", [(256, 17, capi.WINDOW_HANN), (32, 203, capi.WINDOW_BLACKMAN_HARRIS), (100, 45, capi.WINDOW_HAMMING),
+                                               (512, 12, capi.WINDOW_HANN), (8, 301, capi.WINDOW_BLACKMAN), (32, 6, capi.WINDOW_HANN)])
+def test_1k_kernel_four_frames_per_transform(emu, hop, frames, window):
+    """stft_fast1k.cu (N = 1024): four interleaved frames per 4096-point transform, separated by a radix-4 butterfly in
+    registers.  Frame counts of several residues mod 8 (zero-fed missing frames, idle second group), ring wrap-around."""
+    cfg = SpectrogramConfig(fft_size=1024, hop_size=hop, window=window, use_reassignment=True)
+    n = 2048 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(2, (n + 64) / 48000.0)[:, :n]
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=emu.api)
+    assert plan.kernel_generation == 6
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 2 * frames and st["unmatched"] <= 2e-3 * st["pts"] + 2
+
+
 def test_2k_kernel_single_frame_and_silence(emu):
     cfg = SpectrogramConfig(fft_size=2048, hop_size=64, window=capi.WINDOW_HANN, use_reassignment=True)
     plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=emu.api)

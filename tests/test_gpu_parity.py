@@ -256,6 +256,22 @@ def test_default_size_2048(product, hop, window):
     parity.compare_reassigned(pa, ca, pb, cb, sr=48000.0, fft_len=2048, window=2048, hop=hop)
 
 
+@pytest.mark.parametrize("hop,window", [(256, capi.WINDOW_HANN), (32, capi.WINDOW_BLACKMAN_HARRIS)])
+def test_size_1024_reassigned(product, hop, window):
+    """N = 1024 reassigned through stft_fast1k.cu (four interleaved frames per transform), against the oracle and the generic kernel."""
+    cfg = SpectrogramConfig(fft_size=1024, hop_size=hop, window=window, use_reassignment=True)
+    frames = 1203
+    n = 2048 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(3, (n + 64) / 48000.0)[:, :n]
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=product.api)
+    assert plan.kernel_generation == 6
+    st = cases.stft_parity(product.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 3 * frames
+    pa, ca = plan.execute_host(lanes)
+    pb, cb = batch.StftPlan(cfg, kernel=capi.KERNEL_GENERIC, api=product.api).execute_host(lanes)
+    parity.compare_reassigned(pa, ca, pb, cb, sr=48000.0, fft_len=1024, window=1024, hop=hop)
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_cases(product):
     cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
