@@ -300,6 +300,11 @@ def run_ours(args):
     if rank != 0:
         return 0
     peak_gbs, peak_src = measured_peaks()
+    # second roofline: the FP32 FMA peak of this device, measured by the library's probe kernel after the timed region
+    import ctypes as _C
+    fp32_peak = _C.c_double(0.0)
+    if api.probe_fp32_tflops(_C.byref(fp32_peak)) != 0:
+        fp32_peak.value = 0.0
     kernel_name = {0: "k_reassigned_generic", 1: "k_reassigned_fast", 2: "k_reassigned_fast2"}[plan.kernel_generation]
     achieved_gbs = frames_per_step * ALGO_BYTES_PER_FRAME / (ms_step / 1000.0) / 1e9
     traffic = recorded_traffic(kernel_name)
@@ -315,6 +320,8 @@ def run_ours(args):
                      "traffic": (traffic * frames_per_step if traffic else None), "peak_source": peak_src, "kernel": kernel_name,
                      "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
                      "fp32": {"flops_per_frame": FLOPS_PER_FRAME, "achieved_tflops": frames_per_step * FLOPS_PER_FRAME / (ms_step / 1000.0) / 1e12,
+                              "peak_tflops": fp32_peak.value or None, "peak_source": "measured (omb_probe_fp32_tflops: independent FFMA chains)",
+                              "frac": (frames_per_step * FLOPS_PER_FRAME / (ms_step / 1000.0) / 1e12 / fp32_peak.value) if fp32_peak.value else None,
                               "note": "path is FP32-issue / shared-memory bound, not HBM bound (arithmetic intensity ~45 flop/B); see DESIGN.md"}},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(L * S * 4),
                 "d2h_bytes_per_step": int(frames_per_step * (POINT_STRIDE * 12 + 4)), "steps": e2e_steps, "api": "omb_stft_execute_host"},

@@ -100,6 +100,9 @@ int omb_device_count(void);
 int omb_set_device(int device);
 /* Total kernel launches issued by this library in this process (bench.py's gpu_launches). */
 uint64_t omb_kernel_launch_count(void);
+/* Measured FP32 peak of the current device in TFLOP/s: independent FFMA chains on every SM, timed with CUDA events
+ * (the second roofline of SURVEY.md 8(d): the reassigned path is FP32-issue bound, not HBM bound). */
+int omb_probe_fp32_tflops(double* out_tflops);
 
 /* ------------------------------------------------------------------------ */
 /* Plan set-up pieces (rows a2,a3,a5,a14,a15 of SURVEY.md §8) — host-side,    */

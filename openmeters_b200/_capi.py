@@ -177,6 +177,7 @@ HEADER_SYMBOLS = {
     "device_count": (C.c_int, []),
     "set_device": (C.c_int, [C.c_int]),
     "kernel_launch_count": (_u64, []),
+    "probe_fp32_tflops": (C.c_int, [_f64p]),
     "window_coefficients": (C.c_int, [C.c_int, _sz, _f32p]),
     "fft_bin_normalization": (C.c_int, [_f32p, _sz, _sz, _f32p]),
     "reassignment_windows": (C.c_int, [_f32p, _sz, _f32p, _f32p]),

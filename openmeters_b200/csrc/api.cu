@@ -38,6 +38,11 @@ int omb_set_device(int device) {
   return OMB_OK;
 }
 uint64_t omb_kernel_launch_count(void) { return launch_count().load(); }
+int omb_probe_fp32_tflops(double* out_tflops) {
+  OMB_GUARD_BEGIN
+  return probe_fp32_tflops(out_tflops);
+  OMB_GUARD_END
+}
 
 // ---- plan set-up pieces
 int omb_window_coefficients(int kind, size_t len, float* out) {

@@ -81,6 +81,7 @@ struct DeviceInfo {
 };
 // Fails (OMB_ERR_CUDA) when no usable device exists: there is no CPU fallback.
 int current_device(DeviceInfo* out);
+int probe_fp32_tflops(double* out_tflops);  // runtime.cu: measured FFMA peak of the current device
 
 // ---- RAII device / pinned-host buffers
 template <class T>
