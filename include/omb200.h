@@ -523,6 +523,26 @@ int omb_spectrogram_bank_push(omb_spectrogram_bank* b, const float* samples, uin
 /* Samples pending per stream (the VecDeque length of processor.rs:412-437). */
 size_t omb_spectrogram_bank_pending(const omb_spectrogram_bank* b);
 
+/* ------------------------------------------------------------------------ */
+/* Row f1, device side, loudness: S lock-step LoudnessProcessors               */
+/* (loudness/processor.rs:218-311) sharing config, channel layout and rate.   */
+/* Filter / window / true-peak state of all streams lives on the device; one   */
+/* push = one strided H2D copy + ONE kernel launch (a CTA per stream) + one    */
+/* D2H copy of S snapshots, instead of S x (copy + launch + sync).             */
+/* Snapshot for snapshot identical to S separate omb_loudness handles.         */
+/* ------------------------------------------------------------------------ */
+typedef struct omb_loudness_bank omb_loudness_bank;
+int omb_loudness_bank_create(const omb_loudness_config* cfg, uint32_t n_streams, omb_loudness_bank** out);
+void omb_loudness_bank_destroy(omb_loudness_bank* b);
+/* ::reset_audio of every stream (processor.rs:234-236) */
+int omb_loudness_bank_reset_audio(omb_loudness_bank* b);
+/* ::process_block of every stream (processor.rs:253-311): stream s reads n_samples interleaved samples at
+ * samples + s * stream_stride (floats); out_snapshots[s] (caller-owned, n_streams entries) receives its snapshot.
+ * OMB_NO_DATA when the block holds less than one frame. */
+int omb_loudness_bank_push(omb_loudness_bank* b, const float* samples, uint64_t stream_stride, size_t n_samples,
+                           uint32_t channels, float sample_rate, const uint8_t positions[OMB_MAX_CHANNELS],
+                           omb_loudness_snapshot* out_snapshots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -259,6 +259,10 @@ HEADER_SYMBOLS = {
     "spectrogram_bank_reset_audio": (C.c_int, [_vp]),
     "spectrogram_bank_push": (C.c_int, [_vp, _f32p, _u64, _sz, _u32, C.c_float, _u8p, C.POINTER(SpectrogramBankUpdate)]),
     "spectrogram_bank_pending": (_sz, [_vp]),
+    "loudness_bank_create": (C.c_int, [C.POINTER(LoudnessConfig), _u32, C.POINTER(_vp)]),
+    "loudness_bank_destroy": (None, [_vp]),
+    "loudness_bank_reset_audio": (C.c_int, [_vp]),
+    "loudness_bank_push": (C.c_int, [_vp, _f32p, _u64, _sz, _u32, C.c_float, _u8p, C.POINTER(LoudnessSnapshot)]),
     # row f2: splat accumulation + resolve
     "splat_image_size": (None, [C.POINTER(SplatParams), _u32p, _u32p]),
     "splat_accumulate_device": (C.c_int, [_vp, _u64, _vp, _u32, C.POINTER(SplatParams), _vp, _vp]),

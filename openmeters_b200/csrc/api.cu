@@ -221,6 +221,32 @@ int omb_loudness_process_block(omb_loudness* h, const float* samples, size_t n_s
   OMB_GUARD_END
 }
 
+// ---- loudness bank (row f1, device side)
+struct omb_loudness_bank { LoudnessStream s; explicit omb_loudness_bank(const omb_loudness_config& c, uint32_t n) : s(c) { s.n_streams = n; } };
+int omb_loudness_bank_create(const omb_loudness_config* cfg, uint32_t n_streams, omb_loudness_bank** out) {
+  OMB_GUARD_BEGIN
+  if (!cfg || !out) return fail(OMB_ERR_INVALID, "null argument");
+  if (n_streams == 0 || n_streams > (1u << 20)) return fail(OMB_ERR_INVALID, "loudness bank: n_streams must be in 1..2^20");
+  *out = new omb_loudness_bank(*cfg, n_streams);
+  return OMB_OK;
+  OMB_GUARD_END
+}
+void omb_loudness_bank_destroy(omb_loudness_bank* b) { delete b; }
+int omb_loudness_bank_reset_audio(omb_loudness_bank* b) {
+  OMB_GUARD_BEGIN
+  if (!b) return fail(OMB_ERR_INVALID, "null handle");
+  return b->s.reset_audio();
+  OMB_GUARD_END
+}
+int omb_loudness_bank_push(omb_loudness_bank* b, const float* samples, uint64_t stream_stride, size_t n_samples, uint32_t channels,
+                           float sample_rate, const uint8_t positions[OMB_MAX_CHANNELS], omb_loudness_snapshot* out_snapshots) {
+  OMB_GUARD_BEGIN
+  if (!b) return fail(OMB_ERR_INVALID, "null handle");
+  if (b->s.n_streams > 1 && stream_stride < n_samples) return fail(OMB_ERR_INVALID, "loudness bank: stream_stride < n_samples");
+  return b->s.process_bank(samples, stream_stride, n_samples, channels, sample_rate, positions, out_snapshots);
+  OMB_GUARD_END
+}
+
 // ---- batched STFT
 uint64_t omb_stft_frames_per_lane(const omb_spectrogram_config* cfg, uint64_t samples) {
   if (!cfg) return 0;

@@ -70,8 +70,14 @@ __device__ __forceinline__ float power_to_db_f(float p, float floor_db) {
   return p > 0.0f ? fmaxf(logf(p) * kLnToDb, floor_db) : floor_db;
 }
 
+// One CTA per stream (blockIdx.x; a single stream for omb_loudness, S lock-step streams for omb_loudness_bank).
 __global__ void __launch_bounds__(32) k_loudness_stream(LoudStreamArgs a) {
   const uint32_t c = threadIdx.x;
+  // re-base the per-stream pointers; everything below is the single-stream code
+  a.block += (uint64_t)blockIdx.x * a.block_stride;
+  a.state += (uint64_t)blockIdx.x * a.channels;
+  a.ring += (uint64_t)blockIdx.x * a.channels * a.ring_len;
+  a.out += blockIdx.x;
   if (c < a.channels) {
     LoudChannelState st = a.state[c];
     double* ring = a.ring + (uint64_t)c * a.ring_len;
@@ -616,8 +622,9 @@ void mat4_mul(const long double* A, const long double* B, long double* C) {
 
 }  // namespace
 
-int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s) {
-  OMB_LAUNCH(k_loudness_stream, dim3(1), dim3(32), 0, s, a);
+int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s, uint32_t n_streams) {
+  if (!n_streams) return OMB_OK;
+  OMB_LAUNCH(k_loudness_stream, dim3(n_streams), dim3(32), 0, s, a);
   OMB_CHECK_LAUNCH();
   return OMB_OK;
 }

@@ -28,11 +28,12 @@ struct LoudChannelState {
 };
 
 struct LoudStreamArgs {
-  const float* block;                    // interleaved [frames][channels]
+  const float* block;                    // interleaved [frames][channels]; stream s at block + s * block_stride
+  uint64_t block_stride;                 // floats between streams (0 for a single stream)
   uint64_t frames;
   uint32_t channels;
-  LoudChannelState* state;               // [channels]
-  double* ring;                          // [channels][ring_len] squared K-weighted samples
+  LoudChannelState* state;               // [stream][channels]
+  double* ring;                          // [stream][channels][ring_len] squared K-weighted samples
   uint64_t ring_len;                     // longest window
   uint64_t caps[kLoudWindows];
   uint32_t tp_delay_len;                 // 12 (4x), 24 (2x) or 0
@@ -41,7 +42,7 @@ struct LoudStreamArgs {
   float floor_db;
   double weights[OMB_MAX_CHANNELS];      // channel_weight(position)
   uint8_t positions[OMB_MAX_CHANNELS];
-  omb_loudness_snapshot* out;
+  omb_loudness_snapshot* out;            // [stream]
 };
 
 struct LoudnessStreamCore {              // device objects behind omb_loudness (stream_loudness.cu)
@@ -50,7 +51,7 @@ struct LoudnessStreamCore {              // device objects behind omb_loudness (
   DeviceBuffer<float> d_block;
   DeviceBuffer<omb_loudness_snapshot> d_snap;
 };
-int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s);
+int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s, uint32_t n_streams = 1);
 
 // ---- batched plan
 struct LoudnessPlan {

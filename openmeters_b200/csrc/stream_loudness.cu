@@ -33,8 +33,8 @@ void LoudnessStream::configure_rate(float sr) {
 int LoudnessStream::reset_audio() {  // processor.rs:234-236
   if (!channels) return OMB_OK;
   OMB_TRY(ensure_stream());
-  OMB_CUDA_TRY(cudaMemsetAsync(core.d_state.ptr, 0, sizeof(LoudChannelState) * channels, stream));
-  OMB_CUDA_TRY(cudaMemsetAsync(core.d_ring.ptr, 0, sizeof(double) * ring_len * channels, stream));
+  OMB_CUDA_TRY(cudaMemsetAsync(core.d_state.ptr, 0, sizeof(LoudChannelState) * channels * n_streams, stream));
+  OMB_CUDA_TRY(cudaMemsetAsync(core.d_ring.ptr, 0, sizeof(double) * ring_len * channels * n_streams, stream));
   return OMB_OK;
 }
 
@@ -53,8 +53,8 @@ int LoudnessStream::ensure_state(uint32_t requested, float sr_in) {  // processo
   if (rate_changed || channels != ch || ring_len != longest) {
     channels = ch;
     ring_len = longest;
-    OMB_TRY(core.d_state.reserve(channels));
-    OMB_TRY(core.d_ring.reserve((size_t)(ring_len * channels)));
+    OMB_TRY(core.d_state.reserve((size_t)channels * n_streams));
+    OMB_TRY(core.d_ring.reserve((size_t)(ring_len * channels) * n_streams));
     OMB_TRY(reset_audio());
   }
   return OMB_OK;
@@ -62,16 +62,30 @@ int LoudnessStream::ensure_state(uint32_t requested, float sr_in) {  // processo
 
 int LoudnessStream::process_block(const float* samples, size_t n_samples, uint32_t ch_in, float sr_in, const uint8_t* positions,
                                   omb_loudness_snapshot* out) {
+  if (n_streams != 1) return fail(OMB_ERR_INVALID, "process_block on a bank: use process_bank");
+  return process_bank(samples, 0, n_samples, ch_in, sr_in, positions, out);
+}
+
+int LoudnessStream::process_bank(const float* samples, uint64_t stream_stride, size_t n_samples, uint32_t ch_in, float sr_in,
+                                 const uint8_t* positions, omb_loudness_snapshot* out) {
   const uint32_t ch = std::min<uint32_t>(std::max<uint32_t>(ch_in, 1), OMB_MAX_CHANNELS);
   if (n_samples < ch) return OMB_NO_DATA;
   if (!samples || !out) return fail(OMB_ERR_INVALID, "null argument");
   OMB_TRY(ensure_stream());
   OMB_TRY(ensure_state(ch, sr_in));
   const uint64_t frames = n_samples / ch;
-  OMB_TRY(core.d_block.upload(samples, (size_t)(frames * ch), stream));
-  OMB_TRY(core.d_snap.reserve(1));
+  const size_t per = (size_t)(frames * ch);
+  OMB_TRY(core.d_block.reserve(per * n_streams));
+  if (n_streams == 1) {
+    OMB_CUDA_TRY(cudaMemcpyAsync(core.d_block.ptr, samples, per * sizeof(float), cudaMemcpyHostToDevice, stream));
+  } else {  // one strided copy for all streams
+    OMB_CUDA_TRY(cudaMemcpy2DAsync(core.d_block.ptr, per * sizeof(float), samples, (size_t)stream_stride * sizeof(float), per * sizeof(float),
+                                   n_streams, cudaMemcpyHostToDevice, stream));
+  }
+  OMB_TRY(core.d_snap.reserve(n_streams));
   LoudStreamArgs a{};
   a.block = core.d_block.ptr;
+  a.block_stride = per;
   a.frames = frames;
   a.channels = channels;
   a.state = core.d_state.ptr;
@@ -92,8 +106,8 @@ int LoudnessStream::process_block(const float* samples, size_t n_samples, uint32
     a.weights[i] = channel_weight_host(positions[i]);
   }
   a.out = core.d_snap.ptr;
-  OMB_TRY(launch_loudness_stream(a, stream));
-  OMB_CUDA_TRY(cudaMemcpyAsync(out, core.d_snap.ptr, sizeof(omb_loudness_snapshot), cudaMemcpyDeviceToHost, stream));
+  OMB_TRY(launch_loudness_stream(a, stream, n_streams));
+  OMB_CUDA_TRY(cudaMemcpyAsync(out, core.d_snap.ptr, sizeof(omb_loudness_snapshot) * n_streams, cudaMemcpyDeviceToHost, stream));
   OMB_CUDA_TRY(cudaStreamSynchronize(stream));
   return OMB_OK;
 }

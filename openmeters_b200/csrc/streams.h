@@ -86,6 +86,8 @@ struct LoudnessStream {
   DeviceInfo dev;
   cudaStream_t stream = nullptr;
 
+  uint32_t n_streams = 1;     // > 1: a bank of lock-step streams sharing config, channel layout and rate (omb_loudness_bank)
+
   explicit LoudnessStream(const omb_loudness_config& c);
   ~LoudnessStream();
   int ensure_stream();
@@ -94,6 +96,9 @@ struct LoudnessStream {
   int reset_audio();
   int process_block(const float* samples, size_t n_samples, uint32_t channels, float sample_rate, const uint8_t* positions,
                     omb_loudness_snapshot* out);
+  // n_streams x process_block in one launch: stream s reads samples + s * stream_stride, out[s] receives its snapshot
+  int process_bank(const float* samples, uint64_t stream_stride, size_t n_samples, uint32_t channels, float sample_rate,
+                   const uint8_t* positions, omb_loudness_snapshot* out);
 };
 
 }  // namespace omb

@@ -254,3 +254,35 @@ class SpectrogramBank:
             codes = np.ctypeslib.as_array(up.classic_db, shape=(S, n, bins))
             cols = [[codes[s, c].copy() for c in range(n)] for s in range(S)] if copy else codes
         return BankUpdate(up.fft_size, up.hop_size, up.sample_rate, up.history_length, bool(up.reset), up.reassigned_power_scale, up.kind, cols)
+
+
+class LoudnessBank:
+    """Device-side multi-stream loudness (row f1): S lock-step LoudnessProcessors, one kernel launch per push."""
+
+    def __init__(self, config=None, n_streams: int = 1, api=None):
+        from .processors import LoudnessConfig
+
+        self._api = api or _default_api()
+        self._h = C.c_void_p()
+        self.n_streams = int(n_streams)
+        cfg = config or LoudnessConfig()
+        c = capi.LoudnessConfig(cfg.sample_rate, cfg.floor_db)
+        _check(self._api, self._api.loudness_bank_create(C.byref(c), self.n_streams, C.byref(self._h)), "loudness_bank_create")
+        self._snaps = (capi.LoudnessSnapshot * self.n_streams)()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._api.loudness_bank_destroy(h)
+
+    def reset_audio(self) -> None:
+        _check(self._api, self._api.loudness_bank_reset_audio(self._h), "loudness_bank_reset_audio")
+
+    def push(self, blocks, channels: int = 2, sample_rate: float = 48000.0, positions=None):
+        """blocks: (S, frames * channels) float32, one interleaved block per stream -> ctypes array of S LoudnessSnapshots
+        (valid until the next push), or None when the block is shorter than one frame."""
+        x = np.ascontiguousarray(blocks, np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.n_streams
+        rc = _check(self._api, self._api.loudness_bank_push(self._h, _ptr(x), x.shape[1], x.shape[1], channels, sample_rate,
+                                                            capi.positions_array(positions), self._snaps), "loudness_bank_push")
+        return None if rc == capi.NO_DATA else self._snaps

@@ -78,3 +78,73 @@ def test_bank_gpu_cfg1_stereo_streams(product, oracle):
     cfg = SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False, history_length=64)
     cols, ups = run_bank_vs_processors(product.api, oracle, cfg, 20, 0.5, 2, [256, 768, 1024], seed=5)
     assert cols > 20 * 30
+
+
+# ---------------------------------------------------------------- loudness bank
+def run_loudness_bank_vs_processors(api, oracle, S, seconds, channels, positions, block_choices, seed, sr=48000.0):
+    """omb_loudness_bank_push must return, snapshot for snapshot, what S independent LoudnessProcessors return."""
+    from openmeters_b200.meter import LoudnessBank
+    from openmeters_b200.processors import LoudnessConfig
+
+    rng = np.random.default_rng(seed)
+    if channels == 8:
+        base = synth.cfg3_surround(seconds, sr)
+    else:
+        base = synth.cfg1_stereo(seconds, sr)
+    x = np.stack([(np.roll(base.reshape(-1, channels), 131 * s, axis=0) * np.float32(1 - 0.07 * s)).reshape(-1) for s in range(S)])
+    x[S - 1, : int(0.05 * sr) * channels] = 0.0                       # one stream starts silent: lazy activation (processor.rs:264-274)
+    bank = LoudnessBank(LoudnessConfig(sample_rate=sr), S, api=api)
+    procs = [oracle.Loudness(LoudnessConfig(sample_rate=sr)) for _ in range(S)]
+    n_frames = x.shape[1] // channels
+    o, n_snap = 0, 0
+    worst = 0.0
+    while o < n_frames:
+        nf = min(int(rng.choice(block_choices)), n_frames - o)
+        blk = np.ascontiguousarray(x[:, o * channels:(o + nf) * channels])
+        got = bank.push(blk, channels, sr, positions)
+        want = [p.process_block(AudioBlock(blk[s], channels, sr, positions)) for s, p in enumerate(procs)]
+        assert got is not None and all(w is not None for w in want)
+        for s, w in enumerate(want):
+            g = got[s]
+            assert g.channel_count == channels
+            for a, b in ((g.short_term_loudness, w.short_term_loudness), (g.momentary_loudness, w.momentary_loudness)):
+                worst = max(worst, abs(a - b))
+            for name in ("rms_fast_db", "rms_slow_db", "true_peak_db"):
+                ga = np.array(getattr(g, name)[:channels], np.float32)
+                wa = np.asarray(getattr(w, name), np.float32)[:channels]
+                tol = 1e-5 if name == "true_peak_db" else 5e-5
+                assert np.max(np.abs(ga - wa)) <= tol, (name, s, o, ga, wa)
+            n_snap += 1
+        o += nf
+    assert worst <= 5e-5, worst
+    return n_snap
+
+
+def test_loudness_bank_emulated(emu, oracle):
+    n = run_loudness_bank_vs_processors(emu.api, oracle, S=3, seconds=0.35, channels=8, positions=capi.SURROUND,
+                                        block_choices=(256, 512, 1024, 700), seed=5)
+    assert n >= 3 * 16
+    run_loudness_bank_vs_processors(emu.api, oracle, S=2, seconds=0.2, channels=2, positions=None, block_choices=(480, 1000), seed=6, sr=96000.0)
+
+
+def test_loudness_bank_reset_and_single_stream_equivalence(emu):
+    from openmeters_b200.meter import LoudnessBank
+    from openmeters_b200.processors import LoudnessConfig, LoudnessProcessor
+
+    x = synth.cfg1_stereo(0.1)
+    blocks = np.stack([x, x * np.float32(0.5)])
+    bank = LoudnessBank(LoudnessConfig(), 2, api=emu.api)
+    a = bank.push(blocks[:, :2048], 2, 48000.0)
+    m0 = (a[0].momentary_loudness, a[1].momentary_loudness)
+    bank.reset_audio()
+    b = bank.push(blocks[:, :2048], 2, 48000.0)
+    assert (b[0].momentary_loudness, b[1].momentary_loudness) == m0          # reset restores the initial state of every stream
+    single = LoudnessProcessor(LoudnessConfig(), api=emu.api).process_block(AudioBlock(blocks[1, :2048], 2, 48000.0))
+    assert single.momentary_loudness == b[1].momentary_loudness             # same kernel, same bits
+
+
+@pytest.mark.gpu
+def test_loudness_bank_gpu(product, oracle):
+    n = run_loudness_bank_vs_processors(product.api, oracle, S=16, seconds=1.5, channels=8, positions=capi.SURROUND,
+                                        block_choices=(256, 512, 768, 1024), seed=7)
+    assert n >= 16 * 60

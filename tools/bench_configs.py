@@ -168,6 +168,36 @@ def main():
                                              realtime_streams=(cols / tb) / (48000.0 / 1024.0),
                                              per_stream_handles=dict(streams=S1, columns_per_s=cols1 / t1, ms_per_tick=t1 / ticks * 1e3,
                                                                      note="includes the Python mirror's per-column copies"))
+    if want("loudbank"):
+        # row f1, loudness: 512 lock-step 8-channel streams, 1024-frame blocks: one omb_loudness_bank_push per tick vs one
+        # omb_loudness_process_block per stream per tick
+        import time
+        from openmeters_b200.meter import LoudnessBank
+        from openmeters_b200.processors import AudioBlock, LoudnessProcessor
+        S, nf, ticks = 512, 1024, 24
+        x = synth.cfg3_surround(1.0)[: nf * 8]
+        blocks = np.stack([x * np.float32(1.0 - 0.001 * i) for i in range(S)]).astype(np.float32)
+        bank = LoudnessBank(LoudnessConfig(), S, api=api)
+        for _ in range(4):
+            bank.push(blocks, 8, 48000.0, capi.SURROUND)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            bank.push(blocks, 8, 48000.0, capi.SURROUND)
+        tb = (time.perf_counter() - t0) / ticks
+        S1 = 32
+        procs = [LoudnessProcessor(LoudnessConfig(), api=api) for _ in range(S1)]
+        blks = [AudioBlock(blocks[i], 8, 48000.0, capi.SURROUND) for i in range(S1)]
+        for p_, b_ in zip(procs, blks):
+            p_.process_block(b_)
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            for p_, b_ in zip(procs, blks):
+                p_.process_block(b_)
+        t1 = (time.perf_counter() - t0) / ticks
+        res["bank_loudness_live_streams"] = dict(streams=S, block_frames=nf, channels=8, ms_per_tick=tb * 1e3,
+                                                 sample_channels_per_s=S * nf * 8 / tb, realtime_streams=S * (nf / 48000.0) / tb,
+                                                 per_stream_handles=dict(streams=S1, ms_per_tick=t1 * 1e3, realtime_streams=S1 * (nf / 48000.0) / t1))
     print(json.dumps(res))
 
 
