@@ -543,6 +543,38 @@ int omb_loudness_bank_push(omb_loudness_bank* b, const float* samples, uint64_t 
                            uint32_t channels, float sample_rate, const uint8_t positions[OMB_MAX_CHANNELS],
                            omb_loudness_snapshot* out_snapshots);
 
+/* ------------------------------------------------------------------------ */
+/* Row f1, device side, spectrum analyzer: S lock-step SpectrumProcessors      */
+/* (spectrum/processor.rs:88-323) with one config.  Pending audio of every     */
+/* stream's traces in one device ring [stream * traces][pending], smoothing    */
+/* state resident on the device; one push = one strided H2D copy, one batched  */
+/* fold-down, one power and one smoothing launch for all streams.              */
+/* Trace for trace identical to S separate omb_spectrum handles.               */
+/* ------------------------------------------------------------------------ */
+typedef struct omb_spectrum_bank omb_spectrum_bank;
+
+/* Dense form of S SpectrumSnapshots (processor.rs:31-37), active traces only (processor.rs:174-177). */
+typedef struct omb_spectrum_bank_snapshot {
+  uint32_t bins, n_streams, n_traces;   /* n_traces = 1 or 2 */
+  uint32_t trace_index[2];              /* reference trace (0 = source, 1 = secondary_source) of bank trace i */
+  const float* frequency_bins;          /* [bins] */
+  const float* weighted;                /* [stream][trace][bins] A-weighted dB */
+  const float* raw;                     /* [stream][trace][bins] dB */
+} omb_spectrum_bank_snapshot;
+
+int omb_spectrum_bank_create(const omb_spectrum_config* cfg, uint32_t n_streams, omb_spectrum_bank** out);
+void omb_spectrum_bank_destroy(omb_spectrum_bank* b);
+/* ::reset_audio of every stream (processor.rs:112-118) */
+int omb_spectrum_bank_reset_audio(omb_spectrum_bank* b);
+/* ::process_block of every stream (processor.rs:255-269) with one block each: stream s reads `frames` interleaved frames of
+ * `channels` channels at samples + s * stream_stride (floats).  OMB_NO_DATA when no hop completed.  Output pointers are
+ * library-owned pinned host memory, valid until the next call. */
+int omb_spectrum_bank_push(omb_spectrum_bank* b, const float* samples, uint64_t stream_stride, size_t frames,
+                           uint32_t channels, float sample_rate, const uint8_t positions[OMB_MAX_CHANNELS],
+                           omb_spectrum_bank_snapshot* out);
+/* Samples pending per trace (the VecDeque length of processor.rs:271-298). */
+size_t omb_spectrum_bank_pending(const omb_spectrum_bank* b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,11 @@ class SpectrumPeakSpec(C.Structure):
     _fields_ = [("trace", C.c_uint32), ("min_hz", C.c_float), ("max_hz", C.c_float)]
 
 
+class SpectrumBankSnapshot(C.Structure):
+    _fields_ = [("bins", C.c_uint32), ("n_streams", C.c_uint32), ("n_traces", C.c_uint32), ("trace_index", C.c_uint32 * 2),
+                ("frequency_bins", C.POINTER(C.c_float)), ("weighted", C.POINTER(C.c_float)), ("raw", C.POINTER(C.c_float))]
+
+
 class LoudnessConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_float), ("floor_db", C.c_float)]
 
@@ -259,6 +264,11 @@ HEADER_SYMBOLS = {
     "spectrogram_bank_reset_audio": (C.c_int, [_vp]),
     "spectrogram_bank_push": (C.c_int, [_vp, _f32p, _u64, _sz, _u32, C.c_float, _u8p, C.POINTER(SpectrogramBankUpdate)]),
     "spectrogram_bank_pending": (_sz, [_vp]),
+    "spectrum_bank_create": (C.c_int, [C.POINTER(SpectrumConfig), _u32, C.POINTER(_vp)]),
+    "spectrum_bank_destroy": (None, [_vp]),
+    "spectrum_bank_reset_audio": (C.c_int, [_vp]),
+    "spectrum_bank_push": (C.c_int, [_vp, _f32p, _u64, _sz, _u32, C.c_float, _u8p, C.POINTER(SpectrumBankSnapshot)]),
+    "spectrum_bank_pending": (_sz, [_vp]),
     "loudness_bank_create": (C.c_int, [C.POINTER(LoudnessConfig), _u32, C.POINTER(_vp)]),
     "loudness_bank_destroy": (None, [_vp]),
     "loudness_bank_reset_audio": (C.c_int, [_vp]),

@@ -286,3 +286,44 @@ class LoudnessBank:
         rc = _check(self._api, self._api.loudness_bank_push(self._h, _ptr(x), x.shape[1], x.shape[1], channels, sample_rate,
                                                             capi.positions_array(positions), self._snaps), "loudness_bank_push")
         return None if rc == capi.NO_DATA else self._snaps
+
+
+class SpectrumBank:
+    """Device-side multi-stream spectrum analyzer (row f1): S lock-step SpectrumProcessors, one launch chain per push."""
+
+    def __init__(self, config, n_streams: int, api=None):
+        self._api = api or _default_api()
+        self._h = C.c_void_p()
+        self.n_streams = int(n_streams)
+        c = config.to_c()
+        _check(self._api, self._api.spectrum_bank_create(C.byref(c), self.n_streams, C.byref(self._h)), "spectrum_bank_create")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._api.spectrum_bank_destroy(h)
+
+    def reset_audio(self) -> None:
+        _check(self._api, self._api.spectrum_bank_reset_audio(self._h), "spectrum_bank_reset_audio")
+
+    @property
+    def pending(self) -> int:
+        return int(self._api.spectrum_bank_pending(self._h))
+
+    def push(self, blocks, channels: int = 2, sample_rate: float = 48000.0, positions=None, copy: bool = True):
+        """blocks: (S, frames * channels) float32 -> None, or (trace_index, frequency_bins, weighted[S, T, bins], raw[S, T, bins])."""
+        x = np.ascontiguousarray(blocks, np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.n_streams
+        frames = x.shape[1] // max(channels, 1)
+        snap = capi.SpectrumBankSnapshot()
+        rc = _check(self._api, self._api.spectrum_bank_push(self._h, _ptr(x), x.shape[1], frames, channels, sample_rate,
+                                                            capi.positions_array(positions), C.byref(snap)), "spectrum_bank_push")
+        if rc == capi.NO_DATA:
+            return None
+        S, T, bins = snap.n_streams, snap.n_traces, snap.bins
+        w = np.ctypeslib.as_array(snap.weighted, shape=(S, T, bins))
+        r = np.ctypeslib.as_array(snap.raw, shape=(S, T, bins))
+        f = np.ctypeslib.as_array(snap.frequency_bins, shape=(bins,))
+        if copy:
+            w, r, f = w.copy(), r.copy(), f.copy()
+        return tuple(snap.trace_index[:T]), f, w, r

@@ -56,7 +56,7 @@ _SHARED = [k for k in capi.HEADER_SYMBOLS if not (
     # splat accumulation: restated in numpy (oracle/splat_py.py)
     or k.startswith("splat_")
     # the multi-stream bank is checked against S independent oracle processors
-    or k.startswith("spectrogram_bank_") or k.startswith("loudness_bank_"))]
+    or k.startswith("spectrogram_bank_") or k.startswith("loudness_bank_") or k.startswith("spectrum_bank_"))]
 
 
 def build(force: bool = False) -> str:

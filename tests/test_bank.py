@@ -148,3 +148,69 @@ def test_loudness_bank_gpu(product, oracle):
     n = run_loudness_bank_vs_processors(product.api, oracle, S=16, seconds=1.5, channels=8, positions=capi.SURROUND,
                                         block_choices=(256, 512, 768, 1024), seed=7)
     assert n >= 16 * 60
+
+
+# ---------------------------------------------------------------- spectrum bank
+def run_spectrum_bank_vs_processors(api, oracle, cfg, S, seconds, channels, block_choices, seed, sr=48000.0):
+    """omb_spectrum_bank_push must return, trace for trace, what S independent SpectrumProcessors return."""
+    from openmeters_b200.meter import SpectrumBank
+
+    rng = np.random.default_rng(seed)
+    base = synth.cfg4_streams(S, seconds, sr)                         # (S, 2, n)
+    if channels == 2:
+        x = np.stack([np.stack([base[s, 0], base[s, 1]], 1).reshape(-1) for s in range(S)]).astype(np.float32)
+    else:
+        x = np.ascontiguousarray(base[:, 0, :], np.float32)
+    bank = SpectrumBank(cfg, S, api=api)
+    procs = [oracle.Spectrum(cfg) for _ in range(S)]
+    n_frames = x.shape[1] // channels
+    o, n_snap = 0, 0
+    while o < n_frames:
+        nf = min(int(rng.choice(block_choices)), n_frames - o)
+        blk = np.ascontiguousarray(x[:, o * channels:(o + nf) * channels])
+        got = bank.push(blk, channels, sr)
+        want = [p.process_block(AudioBlock(blk[s], channels, sr)) for s, p in enumerate(procs)]
+        assert (got is None) == all(w is None for w in want), (o, nf)
+        if got is not None:
+            tidx, freqs, w, r = got
+            for s, snap in enumerate(want):
+                assert snap is not None
+                assert np.array_equal(freqs, snap.frequency_bins)
+                for i, t in enumerate(tidx):
+                    parity.compare_db(r[s, i][None], np.asarray(snap.traces[t][1])[None], cfg.floor_db)
+                    parity.compare_db(w[s, i][None], np.asarray(snap.traces[t][0])[None], cfg.floor_db)
+            n_snap += 1
+        o += nf
+    return n_snap
+
+
+@pytest.mark.parametrize("mode,param", [(capi.AVG_PEAK_HOLD, 12.0), (capi.AVG_EXPONENTIAL, 0.6), (capi.AVG_NONE, 0.0)])
+def test_spectrum_bank_emulated(emu, oracle, mode, param):
+    from openmeters_b200.processors import SpectrumConfig
+
+    cfg = SpectrumConfig(fft_size=512, hop_size=128, averaging=mode, averaging_param=param, source=capi.CHANNEL_LEFT,
+                         secondary_source=capi.CHANNEL_SIDE, floor_db=-100.0)
+    n = run_spectrum_bank_vs_processors(emu.api, oracle, cfg, S=3, seconds=0.12, channels=2, block_choices=(100, 256, 700, 1024), seed=3)
+    assert n >= 5
+
+
+def test_spectrum_bank_single_trace_and_large_hop(emu, oracle):
+    from openmeters_b200.processors import SpectrumConfig
+
+    # only the secondary source is active (processor.rs:174-177); hop larger than the window exercises the skip accounting
+    cfg = SpectrumConfig(fft_size=256, hop_size=600, averaging=capi.AVG_PEAK_HOLD, averaging_param=6.0, source=capi.CHANNEL_NONE,
+                         secondary_source=capi.CHANNEL_MID)
+    n = run_spectrum_bank_vs_processors(emu.api, oracle, cfg, S=2, seconds=0.15, channels=2, block_choices=(256, 512, 999), seed=4)
+    assert n >= 4
+    cfg = SpectrumConfig(fft_size=256, hop_size=64, source=capi.CHANNEL_MID)   # mono input, default averaging
+    run_spectrum_bank_vs_processors(emu.api, oracle, cfg, S=2, seconds=0.08, channels=1, block_choices=(333, 512), seed=5)
+
+
+@pytest.mark.gpu
+def test_spectrum_bank_gpu(product, oracle):
+    from openmeters_b200.processors import SpectrumConfig
+
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0, source=capi.CHANNEL_LEFT,
+                         secondary_source=capi.CHANNEL_RIGHT, floor_db=-100.0)
+    n = run_spectrum_bank_vs_processors(product.api, oracle, cfg, S=8, seconds=0.8, channels=2, block_choices=(512, 1024, 2048), seed=8)
+    assert n >= 10

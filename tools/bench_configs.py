@@ -198,6 +198,39 @@ def main():
         res["bank_loudness_live_streams"] = dict(streams=S, block_frames=nf, channels=8, ms_per_tick=tb * 1e3,
                                                  sample_channels_per_s=S * nf * 8 / tb, realtime_streams=S * (nf / 48000.0) / tb,
                                                  per_stream_handles=dict(streams=S1, ms_per_tick=t1 * 1e3, realtime_streams=S1 * (nf / 48000.0) / t1))
+    if want("specbank"):
+        # row f1, spectrum analyzer: 256 lock-step stereo streams (Left + Right traces = 512 lanes), product defaults (16384 / 1024),
+        # 1024-frame blocks: one omb_spectrum_bank_push per tick vs one omb_spectrum_process_block per stream per tick
+        import time
+        from openmeters_b200.meter import SpectrumBank
+        from openmeters_b200.processors import AudioBlock, SpectrumProcessor
+        scfg = SpectrumConfig(fft_size=16384, hop_size=1024, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0, source=capi.CHANNEL_LEFT,
+                              secondary_source=capi.CHANNEL_RIGHT, floor_db=-100.0)
+        S, nf, ticks = 256, 1024, 24
+        rng = np.random.default_rng(0)
+        blocks = rng.uniform(-0.5, 0.5, (S, nf * 2)).astype(np.float32)
+        bank = SpectrumBank(scfg, S, api=api)
+        for _ in range(20):
+            bank.push(blocks, 2, 48000.0, copy=False)      # fills the first window (16 ticks) and warms up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            bank.push(blocks, 2, 48000.0, copy=False)
+        tb = (time.perf_counter() - t0) / ticks
+        S1 = 16
+        procs = [SpectrumProcessor(scfg, api=api) for _ in range(S1)]
+        blks = [AudioBlock(blocks[i], 2, 48000.0) for i in range(S1)]
+        for _ in range(20):
+            for p_, b_ in zip(procs, blks):
+                p_.process_block(b_)
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            for p_, b_ in zip(procs, blks):
+                p_.process_block(b_)
+        t1 = (time.perf_counter() - t0) / ticks
+        res["bank_spectrum_live_streams"] = dict(streams=S, traces=2, block_frames=nf, ms_per_tick=tb * 1e3, lane_hops_per_s=S * 2 / tb,
+                                                 realtime_streams=S * (nf / 48000.0) / tb,
+                                                 per_stream_handles=dict(streams=S1, ms_per_tick=t1 * 1e3, realtime_streams=S1 * (nf / 48000.0) / t1))
     print(json.dumps(res))
 
 
