@@ -212,6 +212,64 @@ class DspBatcher {
   omb_meter* h_ = nullptr;
 };
 
+// Row f1, device side: S lock-step processors of one kind behind one handle (one launch chain per push for all streams).
+// Outputs are the library's dense views (valid until the next push); see omb200.h for the layouts.
+class SpectrogramBank {
+ public:
+  SpectrogramBank(const SpectrogramConfig& cfg, uint32_t n_streams) { check(omb_spectrogram_bank_create(&cfg, n_streams, &h_), "omb_spectrogram_bank_create"); }
+  ~SpectrogramBank() { omb_spectrogram_bank_destroy(h_); }
+  SpectrogramBank(const SpectrogramBank&) = delete;
+  SpectrogramBank& operator=(const SpectrogramBank&) = delete;
+  void reset_audio() { check(omb_spectrogram_bank_reset_audio(h_), "reset_audio"); }
+  // false: no stream has a new column (the reference's None)
+  bool push(const float* samples, uint64_t stream_stride, size_t frames, uint32_t channels, float sample_rate, const uint8_t* positions,
+            omb_spectrogram_bank_update& out) {
+    return check(omb_spectrogram_bank_push(h_, samples, stream_stride, frames, channels, sample_rate, positions, &out), "push") != OMB_NO_DATA;
+  }
+  size_t pending() const { return omb_spectrogram_bank_pending(h_); }
+
+ private:
+  omb_spectrogram_bank* h_ = nullptr;
+};
+
+class SpectrumBank {
+ public:
+  SpectrumBank(const SpectrumConfig& cfg, uint32_t n_streams) { check(omb_spectrum_bank_create(&cfg, n_streams, &h_), "omb_spectrum_bank_create"); }
+  ~SpectrumBank() { omb_spectrum_bank_destroy(h_); }
+  SpectrumBank(const SpectrumBank&) = delete;
+  SpectrumBank& operator=(const SpectrumBank&) = delete;
+  void reset_audio() { check(omb_spectrum_bank_reset_audio(h_), "reset_audio"); }
+  bool push(const float* samples, uint64_t stream_stride, size_t frames, uint32_t channels, float sample_rate, const uint8_t* positions,
+            omb_spectrum_bank_snapshot& out) {
+    return check(omb_spectrum_bank_push(h_, samples, stream_stride, frames, channels, sample_rate, positions, &out), "push") != OMB_NO_DATA;
+  }
+  size_t pending() const { return omb_spectrum_bank_pending(h_); }
+
+ private:
+  omb_spectrum_bank* h_ = nullptr;
+};
+
+class LoudnessBank {
+ public:
+  LoudnessBank(const LoudnessConfig& cfg, uint32_t n_streams) : n_(n_streams) { check(omb_loudness_bank_create(&cfg, n_streams, &h_), "omb_loudness_bank_create"); }
+  ~LoudnessBank() { omb_loudness_bank_destroy(h_); }
+  LoudnessBank(const LoudnessBank&) = delete;
+  LoudnessBank& operator=(const LoudnessBank&) = delete;
+  void reset_audio() { check(omb_loudness_bank_reset_audio(h_), "reset_audio"); }
+  // one LoudnessSnapshot per stream; empty when the block holds less than one frame
+  std::vector<LoudnessSnapshot> push(const float* samples, uint64_t stream_stride, size_t n_samples, uint32_t channels, float sample_rate,
+                                     const uint8_t* positions) {
+    std::vector<LoudnessSnapshot> out(n_);
+    if (check(omb_loudness_bank_push(h_, samples, stream_stride, n_samples, channels, sample_rate, positions, out.data()), "push") == OMB_NO_DATA)
+      out.clear();
+    return out;
+  }
+
+ private:
+  omb_loudness_bank* h_ = nullptr;
+  uint32_t n_ = 0;
+};
+
 // Row f2: accumulation + resolve passes of the spectrogram view (render.rs:104-165, spectrogram.wgsl) on host buffers.
 using SplatParams = omb_splat_params;
 struct SplatImages {
