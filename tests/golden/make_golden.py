@@ -25,6 +25,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = {
     "cfg1_classic": dict(cfg=SpectrogramConfig(fft_size=1024, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False), seconds=0.25, lanes=2),
     "cfg2_reassigned": dict(cfg=SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True), seconds=0.30, lanes=2),
+    # the product's default spectrogram configuration (spectrogram/processor.rs:47-59) and N = 1024 reassigned: the sizes
+    # served by the interleaved-frame kernels (stft_fast2k.cu / stft_fast1k.cu)
+    "default_2048_64": dict(cfg=SpectrogramConfig(fft_size=2048, hop_size=64, window=capi.WINDOW_HANN, use_reassignment=True), seconds=0.10, lanes=2),
+    "reassigned_1024_256": dict(cfg=SpectrogramConfig(fft_size=1024, hop_size=256, window=capi.WINDOW_HANN, use_reassignment=True), seconds=0.08, lanes=2),
     "small_reassigned_zp4": dict(cfg=SpectrogramConfig(fft_size=256, hop_size=64, window=capi.WINDOW_BLACKMAN, use_reassignment=True, zero_padding_factor=4), seconds=0.03, lanes=1),
 }
 
