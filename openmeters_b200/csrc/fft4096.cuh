@@ -67,7 +67,11 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const fl
   twiddle15<false, kTw2, false>(v, tw2o, 16);
 #pragma unroll
   for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
-  group_sync(g);
+  if (kLocal3) {
+    __syncwarp();  // the 256-point block was written by, and is read by, this half-warp only
+  } else {
+    group_sync(g);
+  }
   const float2* wc = W + ad.pC;
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = wc[j];
