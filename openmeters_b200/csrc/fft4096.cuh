@@ -50,8 +50,11 @@ struct Addr {
 };
 
 // DIF forward: v holds elements t + 256 j (access A). On return v[j] = X[t + 256 j] (only the kPrune subset).
-// kLocal3: pass 3 stays inside the half-warp that ran pass 2 (ad.pC = 273 (t >> 4) + 17 (t & 15)): only a warp-level
-// sync separates the two passes, and thread t ends up with bins tf + 256 j, tf = (t >> 4) + 16 (t & 15).
+// kLocal3: pass 3 stays inside the half-warp that ran pass 2 (ad.pC = 273 (t >> 4) + 17 (t & 15)) and thread t ends up with
+// bins tf + 256 j, tf = (t >> 4) + 16 (t & 15), which lets the INVERSE that follows replace its first group barrier by a
+// __syncwarp (stft_fast2.cu).  The barrier between passes 2 and 3 here stays a group barrier: a warp-level sync is
+// sufficient (the block is written and read by one half-warp; racecheck clean) but was measured neutral to slightly slower
+// on cfg2 (1.9437e7 -> 1.9393e7 frames/s) and -6 % in stft_fast2k.cu, where the extra per-thread constants spill.
 template <int kPrune, int kTw2, bool kLocal3 = false>
 __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const float2* tw1t, const float2* tw2o, const Addr& ad, int g) {
   f16::dft16<false>(v);
@@ -67,11 +70,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const fl
   twiddle15<false, kTw2, false>(v, tw2o, 16);
 #pragma unroll
   for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
-  if (kLocal3) {
-    __syncwarp();  // the 256-point block was written by, and is read by, this half-warp only
-  } else {
-    group_sync(g);
-  }
+  group_sync(g);
   const float2* wc = W + ad.pC;
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = wc[j];

@@ -123,18 +123,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
   const float2* tw1t = sm.tw1 + t;
   const float2* tw2o = sm.tw2 + (t & 15);
   float cos_t, sin_t;  // separation twiddle angle of bin t: 2 pi t / 4096 (the Hilbert pair-step angle, H = 2048, is twice that)
-  // F and I keep their 256-point sub-transforms inside one half-warp (fft4096.cuh, kLocal3): between them this thread owns the
-  // bins tf + 256 j instead of t + 256 j, and two of the group barriers per transform pair become __syncwarp
-  const int tf = (t >> 4) + 16 * (t & 15);
-  Addr adf = ad;
-  adf.pC = 273 * (tf & 15) + 17 * (tf >> 4);
-  sincospif((float)tf / 2048.0f, &sin_t, &cos_t);
-  float cos_g, sin_g;  // the analysis transforms keep the ordered ownership t + 256 j (the compaction needs it)
-  sincospif((float)t / 2048.0f, &sin_g, &cos_g);
+  sincospif((float)t / 2048.0f, &sin_t, &cos_t);
   const int par = t & 3, hh = t >> 2;  // time domain: this thread's samples are hh + 64 j of frame `par`
   const float sign = (hh & 1) ? -1.0f : 1.0f;
   const float ramp0 = (float)hh - (float)(kN2 - 1) * 0.5f;  // n - (N-1)/2 at j = 0
-  const int pt = (kT - tf) & (kT - 1);  // owner of the partner bins 1024 - (t + 256 j)
+  const int pt = (kT - t) & (kT - 1);  // owner of the partner bins 1024 - (t + 256 j)
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
   __syncthreads();
 
@@ -173,10 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
           v[j] = *reinterpret_cast<const float2*>(ring + ((r0 + 2 * hh + 128 * j) & ring_mask));
           if (!fvalid) v[j] = make_float2(0.0f, 0.0f);
         }
-        fft_forward<f16::kAll, kTw2, true>(v, gs.W, tw1t, tw2o, adf, g);
+        fft_forward<f16::kAll, kTw2, false>(v, gs.W, tw1t, tw2o, ad, g);
         separate4(v, cos_t, sin_t);  // v[j + 4 r] = 4 Z_r[t + 256 j]
 #pragma unroll
-        for (int q = 0; q < 16; ++q) gs.W[adf.pC + q] = v[q];
+        for (int q = 0; q < 16; ++q) gs.W[ad.pC + q] = v[q];
         if (t == 0) {  // X[0] and X[H/2] of each frame's real spectrum
 #pragma unroll
           for (int r = 0; r < kFramesPerGroup; ++r) {
@@ -228,10 +221,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
         // ---- I: inverse, DIT; output a[t + 256 q]: sample hh + 64 q of frame par's packed analytic signal; centre half
         {
           f16::dft16<true>(v);
-          float2* wc = gs.W + adf.pC;
+          float2* wc = gs.W + ad.pC;
 #pragma unroll
           for (int q = 0; q < 16; ++q) wc[q] = v[q];
-          __syncwarp();  // pass 2 reads the block this half-warp just wrote
+          group_sync(g);
           float2* wb = gs.W + ad.pB;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
@@ -266,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
             v[j] = fvalid ? make_float2(cx * wv, gs.Y[par][hh + 64 * j] * wv) : make_float2(0.0f, 0.0f);
           }
           fft_forward<f16::kAll, kTw2, false>(v, gs.W, tw1t, tw2o, ad, g);
-          separate4(v, cos_g, sin_g);  // v[j + 4 r] = 4 S_r[t + 256 j]
+          separate4(v, cos_t, sin_t);  // v[j + 4 r] = 4 S_r[t + 256 j]
           if (wsel == 0) {
 #pragma unroll
             for (int r = 0; r < kFramesPerGroup; ++r)
