@@ -61,27 +61,31 @@ int probe_fp32_tflops(double* out) {
 #endif
   DeviceInfo dev;
   OMB_TRY(current_device(&dev));
-  float* sink = nullptr;
-  OMB_CUDA_TRY(cudaMalloc(&sink, sizeof(float)));
-  cudaEvent_t e0, e1;
-  OMB_CUDA_TRY(cudaEventCreate(&e0));
-  OMB_CUDA_TRY(cudaEventCreate(&e1));
+  DeviceBuffer<float> sink;  // RAII: released on every return path
+  OMB_TRY(sink.reserve(1));
+  struct Events {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+    }
+  } ev;
+  OMB_CUDA_TRY(cudaEventCreate(&ev.e0));
+  OMB_CUDA_TRY(cudaEventCreate(&ev.e1));
   const int iters = 1 << 14;
   const unsigned grid = (unsigned)std::max(dev.sm_count, 1) * 2u;
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
-    OMB_CUDA_TRY(cudaEventRecord(e0, nullptr));
-    OMB_LAUNCH(k_fp32_probe, dim3(grid), dim3(1024), 0, nullptr, sink, iters, 0.999f, 0.001f);
-    OMB_CUDA_TRY(cudaEventRecord(e1, nullptr));
-    OMB_CUDA_TRY(cudaEventSynchronize(e1));
+    OMB_CUDA_TRY(cudaEventRecord(ev.e0, nullptr));
+    OMB_LAUNCH(k_fp32_probe, dim3(grid), dim3(1024), 0, nullptr, sink.ptr, iters, 0.999f, 0.001f);
+    OMB_CHECK_LAUNCH();
+    OMB_CUDA_TRY(cudaEventRecord(ev.e1, nullptr));
+    OMB_CUDA_TRY(cudaEventSynchronize(ev.e1));
     float ms = 0.0f;
-    OMB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    OMB_CUDA_TRY(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
     const double flops = 2.0 * 16.0 * (double)iters * 1024.0 * (double)grid;
     if (rep > 0 && ms > 0.0f) best = std::max(best, flops / ((double)ms * 1e-3) / 1e12);
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(sink);
   *out = best;
   return OMB_OK;
 }
