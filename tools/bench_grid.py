@@ -77,6 +77,8 @@ def main():
             tier = TIER[plan.kernel_generation]
         elif (not reassign and F <= 16384) or (reassign and F <= 8192):
             tier = "stft_smem.cu"
+        elif n <= 8192:
+            tier = "stft_smem.cu (%d residue transforms)" % (F // 8192)
         else:
             tier = "stft_generic.cu"
         alg = hop * 4 + out_bytes + (4 if reassign else 0)

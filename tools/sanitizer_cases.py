@@ -46,6 +46,16 @@ def main():
     S = 2048 + 5 * 128
     pts, cnt = batch.StftPlan(cfg, api=api).execute_host(synth.cfg2_lanes(2, (S + 64) / 48000.0)[:, :S])
     done.append("reassigned smem 1024 zp2")
+    # residue decomposition of long zero-padded transforms (reassigned F = 16384 -> 2 residues; classic F = 32768 -> 4)
+    cfg = SpectrogramConfig(fft_size=2048, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=True, zero_padding_factor=8)
+    S = 4096 + 3 * 512
+    pts, cnt = batch.StftPlan(cfg, api=api).execute_host(synth.cfg2_lanes(2, (S + 64) / 48000.0)[:, :S])
+    assert cnt.shape == (2, 4) and cnt.min() > 1000
+    cfg = SpectrogramConfig(fft_size=2048, hop_size=512, window=capi.WINDOW_HANN, use_reassignment=False, zero_padding_factor=16)
+    S = 2048 + 3 * 512
+    codes = batch.StftPlan(cfg, api=api).execute_host(synth.cfg2_lanes(2, (S + 64) / 48000.0)[:, :S])
+    assert codes.shape == (2, 4, 16385)
+    done.append("residue tiers")
     # spectrum: fused kernel (pinned on for few lanes) in the three modes, and the two-kernel path
     lanes = synth.cfg4_streams(2, (16384 + 4 * 1024) / 48000.0).reshape(4, -1)
     for mode, param in [(capi.AVG_PEAK_HOLD, 12.0), (capi.AVG_EXPONENTIAL, 0.7), (capi.AVG_NONE, 0.0)]:
