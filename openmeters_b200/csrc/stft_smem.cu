@@ -110,7 +110,9 @@ struct SmemReassignScratch {
 
 // nres = 1: the analysis transforms (F points) run on chip.  nres = R > 1 (F = N * zp > 8192): R residue transforms of
 // Fs = F / R points per window, X[R m + r] = FFT_Fs(c[n] w[n] W_F^{n r})[m]; the third spectrum then also goes through the scratch.
-__global__ void __launch_bounds__(1024) k_reassigned_smem(StftKernelArgs a, float* gscratch, uint64_t gscratch_stride, int nres) {
+template <bool kResidue>  // false: nres_arg == 1 and the residue machinery compiles away (the on-chip path as it was)
+__global__ void __launch_bounds__(1024) k_reassigned_smem(StftKernelArgs a, float* gscratch, uint64_t gscratch_stride, int nres_arg) {
+  const int nres = kResidue ? nres_arg : 1;
   OMB_DYN_SMEM(float2, smem);
   __shared__ int cnt[33];
   __shared__ float x0_xm[2];
@@ -262,7 +264,8 @@ bool stft_smem_supported(const StftConfig& cfg, const DeviceInfo& dev) {
 int stft_smem_prepare(StftPlan& plan) {
   const int smem = (int)smem_for(plan.cfg);
   if (plan.cfg.reassign) {
-    OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (residues_for(plan.cfg) == 1) OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   } else if (residues_for(plan.cfg) == 1) {
     OMB_CUDA_TRY(cudaFuncSetAttribute(k_classic_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   } else {
@@ -289,7 +292,11 @@ int launch_stft_smem(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s, De
     // floats per CTA: S (2 per bin) + nd (1 per bin, padded to an even count) + T (2 per bin, residue mode only)
     const uint64_t stride = R == 1 ? 3ull * a.bins + 1 : 5ull * a.bins + (a.bins & 1);
     OMB_TRY(scratch.reserve((size_t)((stride * grid + 1) / 2)));
-    OMB_LAUNCH(k_reassigned_smem, dim3(grid), dim3(threads), smem, s, a, reinterpret_cast<float*>(scratch.ptr), stride, R);
+    if (R == 1) {
+      OMB_LAUNCH(k_reassigned_smem<false>, dim3(grid), dim3(threads), smem, s, a, reinterpret_cast<float*>(scratch.ptr), stride, 1);
+    } else {
+      OMB_LAUNCH(k_reassigned_smem<true>, dim3(grid), dim3(threads), smem, s, a, reinterpret_cast<float*>(scratch.ptr), stride, R);
+    }
   } else if (R == 1) {
     OMB_LAUNCH(k_classic_smem, dim3(grid), dim3(threads), smem, s, a);
   } else {
