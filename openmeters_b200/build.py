@@ -76,7 +76,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print("\n".join(logs))
     if force or procs or _stale(OUT, objs):
-        cmd = [nvcc(), "-shared", "-o", OUT, *objs, "-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
+        cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT, *objs, "-cudart", "static",
+               "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
         subprocess.run(cmd, check=True)
     return OUT
 
