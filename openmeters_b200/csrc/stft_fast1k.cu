@@ -8,6 +8,7 @@
 // products per bin.  Thread t owns bins t + 256 j, j < 4, of all four frames in the frequency domain and the samples
 // (t >> 2) + 64 j of frame (t & 3) in the time domain.  Factors 4 of the separation are folded into the pair-step
 // coefficients and the bin normalisation (exact).  One 512-thread CTA = two groups = eight consecutive frames per iteration.
+#include "async_copy.cuh"
 #include "device_math.cuh"
 #include "fft16.cuh"
 #include "fft4096.cuh"
@@ -55,26 +56,8 @@ struct Smem1k {
   // float ring[ring_len] follows
 };
 
-__device__ __forceinline__ void k1_async_copy16(float* dst_smem, const float* src_gmem) {
-#ifdef OMB_EMU
-  for (int i = 0; i < 4; ++i) dst_smem[i] = src_gmem[i];
-#else
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem));
-#endif
-}
-__device__ __forceinline__ void k1_async_commit() {
-#ifndef OMB_EMU
-  asm volatile("cp.async.commit_group;\n" ::);
-#endif
-}
-__device__ __forceinline__ void k1_async_wait_all() {
-#ifndef OMB_EMU
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-#endif
-}
 __device__ __forceinline__ void k1_ring_fetch(float* ring, int ring_mask, const float* x, uint64_t s0, uint64_t s1) {
-  for (uint64_t s = s0 + 4ull * threadIdx.x; s < s1; s += 4ull * kThreads) k1_async_copy16(ring + ((int)s & ring_mask), x + s);
+  ring_fetch_pow2(ring, ring_mask, x, s0, s1, kThreads);
 }
 
 // After a forward transform of four interleaved frames: v[j + 4 r] <- 4 F_r[t + 256 j], j, r < 4.
@@ -141,17 +124,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
       const uint64_t s0 = f_begin * (uint64_t)hop;
       const uint64_t want = s0 + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
       k1_ring_fetch(ring, ring_mask, x, s0, want < s_end ? want : s_end);
-      k1_async_commit();
+      async_commit();
     }
     for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kFramesPerIter) {
-      k1_async_wait_all();
+      async_wait_all();
       __syncthreads();  // ring holds frames fa0 .. fa0+7; both groups are done with the previous eight
       {                 // prefetch what the next eight frames add: eight hops
         const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
         const uint64_t want = s0 + (uint64_t)kFramesPerIter * hop;
         const uint64_t s1 = want < s_end ? want : s_end;
         if (s0 < s1) k1_ring_fetch(ring, ring_mask, x, s0, s1);
-        k1_async_commit();
+        async_commit();
       }
       const uint64_t fg = fa0 + (uint64_t)kFramesPerGroup * g;  // this group's frames: fg .. fg + 3
       if (fg < f_end) {
@@ -328,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
         }
       }
     }
-    k1_async_wait_all();
+    async_wait_all();
     __syncthreads();
   }
 }

@@ -19,6 +19,7 @@
 //     of the inverse).
 #include <cstdlib>
 
+#include "async_copy.cuh"
 #include "device_math.cuh"
 #include "fft16.cuh"
 #include "fft4096.cuh"
@@ -62,28 +63,9 @@ struct Smem2 {
   // float ring[ring_len] follows
 };
 
-__device__ __forceinline__ void async_copy16(float* dst_smem, const float* src_gmem) {
-#ifdef OMB_EMU
-  for (int i = 0; i < 4; ++i) dst_smem[i] = src_gmem[i];
-#else
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem));
-#endif
-}
-__device__ __forceinline__ void async_commit() {
-#ifndef OMB_EMU
-  asm volatile("cp.async.commit_group;\n" ::);
-#endif
-}
-__device__ __forceinline__ void async_wait_all() {
-#ifndef OMB_EMU
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-#endif
-}
-
 // Copies lane samples [s0, s1) (multiples of 4) into the ring at (sample index mod ring_len); all CTA threads.
 __device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const float* x, uint64_t s0, uint64_t s1) {
-  for (uint64_t s = s0 + 4ull * threadIdx.x; s < s1; s += 4ull * kThreads) async_copy16(ring + ((int)s & ring_mask), x + s);
+  ring_fetch_pow2(ring, ring_mask, x, s0, s1, kThreads);
 }
 
 // kVariant bit 0: pass-2 twiddles computed from 4 loads (kTw2 = 1) instead of 15 table loads.

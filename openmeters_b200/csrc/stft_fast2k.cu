@@ -11,6 +11,7 @@
 // pruned inverse (outputs 4..11 = the centre half) are unchanged.  Power-of-two factors of the separation (2 FA) are
 // folded into the pair-step coefficients and the bin normalisation (exact).
 // One 512-thread CTA = two groups = four consecutive frames per iteration, sharing one staging ring.
+#include "async_copy.cuh"
 #include "device_math.cuh"
 #include "fft16.cuh"
 #include "fft4096.cuh"
@@ -57,26 +58,8 @@ struct Smem2k {
   // float ring[ring_len] follows
 };
 
-__device__ __forceinline__ void k2_async_copy16(float* dst_smem, const float* src_gmem) {
-#ifdef OMB_EMU
-  for (int i = 0; i < 4; ++i) dst_smem[i] = src_gmem[i];
-#else
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem));
-#endif
-}
-__device__ __forceinline__ void k2_async_commit() {
-#ifndef OMB_EMU
-  asm volatile("cp.async.commit_group;\n" ::);
-#endif
-}
-__device__ __forceinline__ void k2_async_wait_all() {
-#ifndef OMB_EMU
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-#endif
-}
 __device__ __forceinline__ void k2_ring_fetch(float* ring, int ring_mask, const float* x, uint64_t s0, uint64_t s1) {
-  for (uint64_t s = s0 + 4ull * threadIdx.x; s < s1; s += 4ull * kThreads) k2_async_copy16(ring + ((int)s & ring_mask), x + s);
+  ring_fetch_pow2(ring, ring_mask, x, s0, s1, kThreads);
 }
 
 // After a forward transform of two interleaved frames: v[j] <- 2 FA[t + 256 j], v[8 + j] <- 2 FB[t + 256 j], j < 8.
@@ -141,17 +124,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2k(Fast2kArgs fa
       const uint64_t s0 = f_begin * (uint64_t)hop;
       const uint64_t want = s0 + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
       k2_ring_fetch(ring, ring_mask, x, s0, want < s_end ? want : s_end);
-      k2_async_commit();
+      async_commit();
     }
     for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kFramesPerIter) {
-      k2_async_wait_all();
+      async_wait_all();
       __syncthreads();  // ring holds frames fa0 .. fa0+3; both groups are done with the previous four
       {                 // prefetch what the next four frames add: four hops
         const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
         const uint64_t want = s0 + (uint64_t)kFramesPerIter * hop;
         const uint64_t s1 = want < s_end ? want : s_end;
         if (s0 < s1) k2_ring_fetch(ring, ring_mask, x, s0, s1);
-        k2_async_commit();
+        async_commit();
       }
       const uint64_t fg = fa0 + (uint64_t)kFramesPerGroup * g;  // this group's frames: fg, fg + 1
       if (fg < f_end) {
@@ -322,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2k(Fast2kArgs fa
         }
       }
     }
-    k2_async_wait_all();
+    async_wait_all();
     __syncthreads();
   }
 }
