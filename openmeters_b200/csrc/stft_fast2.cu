@@ -242,9 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
 #pragma unroll
         for (int j = 0; j < kBinGroups; ++j) {
           const int bin = t + kT * j;
-          bool k = (j < 8 || t == 0);
           const float norm = (bin == 0 || j == 8) ? fa.norm_dc : fa.norm_ac;
-          if (k) k = reassign_bin_nd(S[j], nd[j], v[j], norm, bin, rc, &pts[j]);
+          const bool k = reassign_bin_nd(S[j], nd[j], v[j], norm, bin, rc, &pts[j]) & (j < 8 || t == 0);  // branch-free
           const unsigned m = __ballot_sync(0xffffffffu, k);
           if (lane_id == 0) gs.warp_cnt[j * kWarps + warp] = __popc(m);
           if (k) keep |= 1u << j;

@@ -259,9 +259,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2k(Fast2kArgs fa
 #pragma unroll
           for (int j = 0; j < kBinGroups; ++j) {
             const int bin = t + kT * j;
-            bool k = (j < 4 || t == 0);
             const float norm = (bin == 0 || j == 4) ? fa.norm_dc : fa.norm_ac;
-            if (k) k = reassign_bin_nd(S[fr][j], nd[fr][j], v[8 * fr + j], norm, bin, rc, &pts[fr][j]);
+            const bool k = reassign_bin_nd(S[fr][j], nd[fr][j], v[8 * fr + j], norm, bin, rc, &pts[fr][j]) & (j < 4 || t == 0);
             const unsigned m = __ballot_sync(0xffffffffu, k);
             if (lane_id == 0) gs.warp_cnt[fr][j * kWarps + warp] = __popc(m);
             if (k) keep |= 1u << (fr * kBinGroups + j);

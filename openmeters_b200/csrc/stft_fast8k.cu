@@ -298,9 +298,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
 #pragma unroll
       for (int j = 0; j < kBinGroups; ++j) {
         const int bin = 2 * (t + kT * j) + g;
-        bool k = (j < 8 || wrap_j);
         const float norm = (bin == 0 || bin == kN8 / 2) ? fa.norm_dc : fa.norm_ac;
-        if (k) k = reassign_bin_nd(S[j], nd[j], v[j], norm, bin, rc, &pts[j]);
+        const bool k = reassign_bin_nd(S[j], nd[j], v[j], norm, bin, rc, &pts[j]) & (j < 8 || wrap_j);
         const unsigned m = __ballot_sync(0xffffffffu, k);
         if (lane_id == 0) sm.ball[g][j * kWarps + warp] = m;
         if (k) keep |= 1u << j;
