@@ -209,6 +209,25 @@ __device__ __forceinline__ void f_async_commit_wait(bool wait) {
   else asm volatile("cp.async.commit_group;\n" ::);
 #endif
 }
+__device__ __forceinline__ void f_async_copy8(float2* dst_smem, const float* src_gmem) {
+#ifdef OMB_EMU
+  *dst_smem = make_float2(src_gmem[0], src_gmem[1]);
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src_gmem));
+#endif
+}
+// Planar ring (experimental, OMB_SPECTRUM_PLANAR=1): the even and odd float2 of every 16-byte quad live in two planes of
+// L / 4 float2 each, so that the group that transforms z[2m + g] reads plane g at unit stride (the interleaved ring is read
+// at a 16-byte stride: a 2-way bank conflict on every 64-bit load, 22 % of the kernel's shared-memory wavefronts).
+__device__ __forceinline__ void f_ring_fetch_planar(float2* plane_e, float2* plane_o, int L, int p0, const float* x, int count) {
+  for (int i = 4 * (int)threadIdx.x; i < count; i += 4 * kThreads) {
+    int p = p0 + i;
+    p -= (p >= L) ? L : 0;
+    f_async_copy8(plane_e + (p >> 2), x + i);
+    f_async_copy8(plane_o + (p >> 2), x + i + 2);
+  }
+}
 __device__ __forceinline__ void f_ring_fetch(float* ring, int L, int p0, const float* x, int count) {
   for (int i = 4 * (int)threadIdx.x; i < count; i += 4 * kThreads) {
     int p = p0 + i;
@@ -268,7 +287,7 @@ __device__ __forceinline__ void fused_bin(const FusedConsts& c, float p, float& 
   best = key > best ? key : best;
 }
 
-template <int kMode>
+template <int kMode, bool kPlanar = false>
 __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArgs fa) {
   OMB_DYN_SMEM(unsigned char, smem_raw);
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
@@ -282,7 +301,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
     sm.tw1[i] = __ldg(&fa.tw1[row * kT + (i & (kT - 1))]);
   }
   for (int i = tid; i < 15 * 16; i += kThreads) sm.tw2[i] = __ldg(&fa.tw2[i]);
-  for (int i = tid; i < kN; i += kThreads) sm.win[i] = __ldg(&a.win[i]);
+  if (kPlanar) {  // window in the same two planes as the ring: plane g holds (h[4m + 2g], h[4m + 2g + 1])
+    float2* wp = reinterpret_cast<float2*>(sm.win);
+    for (int i = tid; i < kN / 4; i += kThreads) {
+      wp[i] = make_float2(__ldg(&a.win[4 * i]), __ldg(&a.win[4 * i + 1]));
+      wp[kN / 4 + i] = make_float2(__ldg(&a.win[4 * i + 2]), __ldg(&a.win[4 * i + 3]));
+    }
+  } else {
+    for (int i = tid; i < kN; i += kThreads) sm.win[i] = __ldg(&a.win[i]);
+  }
   for (int i = tid; i <= kM; i += kThreads) sm.adb_lo[i] = __ldg(&fa.a_db[i]);
   float aw_hi[kSlots][2];  // A-weights of this thread's bins 8192 - aa and 4096 + aa
 #pragma unroll
@@ -334,7 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
 #pragma unroll
       for (int b = 0; b < 4; ++b) st[i][b] = 0.0f;
     int r0 = 0;
-    f_ring_fetch(ring, L, 0, x, kN);
+    float2* const plane_e = reinterpret_cast<float2*>(ring);  // planar ring: L / 4 float2 per plane
+    float2* const plane_o = plane_e + L / 4;
+    if (kPlanar) f_ring_fetch_planar(plane_e, plane_o, L, 0, x, kN);
+    else f_ring_fetch(ring, L, 0, x, kN);
     f_async_commit_wait(false);
     float mean_next = __ldg(&means[0]);
     for (uint64_t h = 0; h < a.hops; ++h) {
@@ -343,7 +373,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
       if (h + 1 < a.hops) {
         int p0 = r0 + kN;
         p0 -= (p0 >= L) ? L : 0;
-        f_ring_fetch(ring, L, p0, x + h * (uint64_t)hop + kN, hop);
+        if (kPlanar) f_ring_fetch_planar(plane_e, plane_o, L, p0, x + h * (uint64_t)hop + kN, hop);
+        else f_ring_fetch(ring, L, p0, x + h * (uint64_t)hop + kN, hop);
       }
       f_async_commit_wait(false);
       if (fa.peak_bin && h > 0 && tid == 0) {  // finish the previous hop's arg-max
@@ -361,9 +392,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
       float2 v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int i0 = 4 * (t + kT * j) + 2 * g;
-        const float2 xv = *reinterpret_cast<const float2*>((i0 < split ? lo : hi) + i0);
-        const float2 wv = *reinterpret_cast<const float2*>(sm.win + i0);
+        float2 xv, wv;
+        if (kPlanar) {  // plane g, quad (r0 / 4 + m) mod (L / 4), m = t + 256 j: unit stride across the warp
+          const int m = t + kT * j;
+          int q = (r0 >> 2) + m;
+          q -= (q >= (L >> 2)) ? (L >> 2) : 0;
+          xv = (g ? plane_o : plane_e)[q];
+          wv = reinterpret_cast<const float2*>(sm.win)[g * (kN / 4) + m];
+        } else {
+          const int i0 = 4 * (t + kT * j) + 2 * g;
+          xv = *reinterpret_cast<const float2*>((i0 < split ? lo : hi) + i0);
+          wv = *reinterpret_cast<const float2*>(sm.win + i0);
+        }
         v[j] = make_float2((xv.x - mean) * wv.x, (xv.y - mean) * wv.y);
       }
       fft_forward<f16::kAll, 0>(v, sm.W[g], tw1t, tw2o, ad, g);
@@ -520,7 +560,17 @@ int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lane
   fa.ring_len = (uint32_t)(kN + cfg.hop);
   const unsigned grid = (unsigned)std::min<uint64_t>(n_lanes, (uint64_t)std::max(p.dev.sm_count, 1));
   const size_t fs = fused_smem_bytes(cfg.hop);
-  if (fa.mode == OMB_AVG_PEAK_HOLD) {
+  // OMB_SPECTRUM_PLANAR=1: experimental planar ring (conflict-free frame loads; not yet measured on hardware, off by default)
+  const char* planar_env = getenv("OMB_SPECTRUM_PLANAR");
+  const bool planar = planar_env && planar_env[0] == '1' && (cfg.hop % 4) == 0;
+  if (planar) {
+    auto kp = k_spectrum_fused_16k<OMB_AVG_PEAK_HOLD, true>;
+    auto ke = k_spectrum_fused_16k<OMB_AVG_EXPONENTIAL, true>;
+    auto kn = k_spectrum_fused_16k<OMB_AVG_NONE, true>;
+    auto k = fa.mode == OMB_AVG_PEAK_HOLD ? kp : (fa.mode == OMB_AVG_EXPONENTIAL ? ke : kn);
+    OMB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+    OMB_LAUNCH(k, dim3(grid), dim3(kThreads), fs, s, fa);
+  } else if (fa.mode == OMB_AVG_PEAK_HOLD) {
     OMB_LAUNCH(k_spectrum_fused_16k<OMB_AVG_PEAK_HOLD>, dim3(grid), dim3(kThreads), fs, s, fa);
   } else if (fa.mode == OMB_AVG_EXPONENTIAL) {
     OMB_LAUNCH(k_spectrum_fused_16k<OMB_AVG_EXPONENTIAL>, dim3(grid), dim3(kThreads), fs, s, fa);

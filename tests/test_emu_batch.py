@@ -218,6 +218,23 @@ def test_spectrum_fused_16k(emu, mode, param, monkeypatch):
     assert st is not None
 
 
+@pytest.mark.parametrize("mode,param,hop", [(capi.AVG_PEAK_HOLD, 12.0, 1024), (capi.AVG_EXPONENTIAL, 0.6, 2048), (capi.AVG_NONE, 0.0, 512)])
+def test_spectrum_fused_16k_planar_ring(emu, mode, param, hop, monkeypatch):
+    """The experimental planar staging ring of the fused kernel (OMB_SPECTRUM_PLANAR=1, off by default): even / odd float2 of
+    every quad in two planes filled by 8-byte async copies, so each transform group reads at unit stride.  Same outputs."""
+    monkeypatch.setenv("OMB_SPECTRUM_FUSED", "1")
+    monkeypatch.setenv("OMB_SPECTRUM_PLANAR", "1")
+    cfg = SpectrumConfig(fft_size=16384, hop_size=hop, window=capi.WINDOW_HANN, averaging=mode, averaging_param=param, floor_db=-100.0)
+    lanes = synth.cfg4_streams(1, (16384 + 19 * hop) / 48000.0).reshape(2, -1)
+    plan = batch.SpectrumPlan(cfg, api=emu.api)
+    wa, ra, pka = plan.execute_host(lanes)
+    monkeypatch.setenv("OMB_SPECTRUM_PLANAR", "0")
+    wb, rb, pkb = batch.SpectrumPlan(cfg, api=emu.api).execute_host(lanes)
+    assert np.array_equal(wa, wb) and np.array_equal(ra, rb) and np.array_equal(pka, pkb)  # same arithmetic, different staging
+    monkeypatch.setenv("OMB_SPECTRUM_PLANAR", "1")
+    cases.spectrum_parity(emu.api, cfg, lanes)
+
+
 @pytest.mark.parametrize("n,hop,zp,window,reassign", cases.settings_grid())
 def test_settings_grid_emulated(emu, n, hop, zp, window, reassign):
     """the (size, hop, zero padding, window, mode) grid the settings UI can reach, through whichever kernel
