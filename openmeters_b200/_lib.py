@@ -13,7 +13,8 @@ from functools import lru_cache
 from . import _capi as capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libomb200.so")
+# OMB_LIB: measurement knob for A/B builds of the same sources (tools/ab_build.py); never set in production.
+LIB_PATH = os.environ.get("OMB_LIB") or os.path.join(HERE, "libomb200.so")
 
 
 class ExtensionMissing(ImportError):

@@ -49,6 +49,27 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """A/B build of the same sources with extra -D flags -> openmeters_b200/build_ab/libomb200_<name>.so (select it with
+    OMB_LIB=<path>; measurement only)."""
+    obj_dir = os.path.join(HERE, "build_ab", name)
+    os.makedirs(obj_dir, exist_ok=True)
+    out = os.path.join(HERE, "build_ab", f"libomb200_{name}.so")
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        cmd = [nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *[f"-D{d}" for d in defines], "-c", src, "-o", obj]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        log, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(log)
+    subprocess.run([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *objs, "-cudart", "static",
+                    "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"], check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + [
@@ -83,4 +104,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:  # python -m openmeters_b200.build --variant adds_only OMB_F32X2_LEVEL=1
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

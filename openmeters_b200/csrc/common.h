@@ -7,6 +7,16 @@
 #include <cuda_runtime.h>
 #endif
 
+// Packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2, see fft16.cuh) in the device helpers.  OMB_F32X2_LEVEL: 0 = scalar code
+// (CPU emulator, -DOMB_NO_F32X2), 1 = packed complex add / subtract only (the round-1 kernels; A/B builds), 2 = every complex
+// primitive packed (default).
+#if defined(OMB_EMU) || defined(OMB_NO_F32X2)
+#define OMB_F32X2_LEVEL 0
+#elif !defined(OMB_F32X2_LEVEL)
+#define OMB_F32X2_LEVEL 2
+#endif
+#define OMB_F32X2 (OMB_F32X2_LEVEL >= 2)
+
 #include <atomic>
 #include <cstdarg>
 #include <cstdint>

@@ -31,21 +31,71 @@ __device__ constexpr float kSin32[16] = {0.0f, 0.19509032201612826785f, 0.382683
                                          1.0f, 0.98078528040323044913f, 0.92387953251128673848f, 0.83146961230254523708f,
                                          0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508978178f, 0.19509032201612826785f};
 
-// Complex add / subtract as ONE packed FP32x2 instruction (Blackwell FADD2: both lanes of an aligned register
-// pair in a single issue slot).  The kernels are issue-bound, so halving the issue cost of the ~130 complex
-// additions per radix-16 butterfly matters more than anything else.  OMB_NO_F32X2 restores scalar code.
+// Packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: both lanes of an aligned register pair in ONE issue slot).
+// The SASS operand modifiers make every complex primitive of an FFT a one- or two-instruction sequence with no
+// register shuffling: `.F32x2.LO_HI` swaps the lanes of a source pair, `.NP` negates one lane, `.F32` broadcasts a
+// scalar register (or an immediate) to both lanes.  So
+//     a + b, a - b                       1 FADD2
+//     a -+ j b   (radix-4 rotation)      1 FADD2  (b.LO_HI.NP)              — two scalar FADDs before
+//     a * w      (complex)               1 FMUL2 (a, w.x bcast) + 1 FFMA2 (a.LO_HI, w.y bcast with .NP, acc)  — four before
+// A packed instruction holds the FMA pipe for two cycles, so the pipe time is unchanged; what halves is the ISSUE cost,
+// and the freed issue slots are what lets the load / store phases of the other warps run under the butterflies
+// (round-2 ncu: FMUL + FFMA + FADD were 50 % of all issued instructions, profiles/r02a_*).  ptxas folds the
+// make_float2(...) swizzles below into those modifiers (checked with cuobjdump: no MOV / PRMT).  OMB_NO_F32X2 or the CPU
+// emulator (OMB_EMU) restore scalar code with separately rounded multiplies and adds.
+// (OMB_F32X2 is defined in common.h.)
 __device__ __forceinline__ float2 cadd2(float2 a, float2 b) {
-#if defined(OMB_EMU) || defined(OMB_NO_F32X2)
-  return make_float2(a.x + b.x, a.y + b.y);
-#else
+#if OMB_F32X2_LEVEL >= 1
   return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
 #endif
 }
 __device__ __forceinline__ float2 csub2(float2 a, float2 b) {
-#if defined(OMB_EMU) || defined(OMB_NO_F32X2)
-  return make_float2(a.x - b.x, a.y - b.y);
-#else
+#if OMB_F32X2_LEVEL >= 1
   return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// a + (-j) b = (a.x + b.y, a.y - b.x)   and   a + (+j) b = (a.x - b.y, a.y + b.x)
+__device__ __forceinline__ float2 cadd_mj(float2 a, float2 b) {
+#if OMB_F32X2
+  return __fadd2_rn(a, make_float2(b.y, -b.x));
+#else
+  return make_float2(a.x + b.y, a.y - b.x);
+#endif
+}
+__device__ __forceinline__ float2 cadd_pj(float2 a, float2 b) {
+#if OMB_F32X2
+  return __fadd2_rn(a, make_float2(-b.y, b.x));
+#else
+  return make_float2(a.x - b.y, a.y + b.x);
+#endif
+}
+// a * (wx + j wy)
+__device__ __forceinline__ float2 cmul2(float2 a, float wx, float wy) {
+#if OMB_F32X2
+  return __ffma2_rn(make_float2(a.y, a.x), make_float2(-wy, wy), __fmul2_rn(a, make_float2(wx, wx)));
+#else
+  return make_float2(a.x * wx - a.y * wy, a.y * wx + a.x * wy);
+#endif
+}
+// (ax, ay) * s  (both lanes by one scalar)
+__device__ __forceinline__ float2 cscale2(float2 a, float s) {
+#if OMB_F32X2
+  return __fmul2_rn(a, make_float2(s, s));
+#else
+  return make_float2(a.x * s, a.y * s);
+#endif
+}
+
+// c conj(p) + s (j z) = (c p.x - s z.y, s z.x - c p.y): the Hilbert pair step of the reassigned kernels
+__device__ __forceinline__ float2 pair_q(float2 p, float2 z, float c, float s) {
+#if OMB_F32X2
+  return __ffma2_rn(make_float2(-z.y, z.x), make_float2(s, s), __fmul2_rn(make_float2(p.x, -p.y), make_float2(c, c)));
+#else
+  return make_float2(c * p.x - s * z.y, s * z.x - c * p.y);
 #endif
 }
 
@@ -56,12 +106,12 @@ __device__ __forceinline__ float2 rot_mj(float2 a) {  // a * (-j) forward, a * (
 // a * (c - j s) forward, a * (c + j s) inverse
 template <bool INV>
 __device__ __forceinline__ float2 mul_cs(float2 a, float c, float s) {
-  return INV ? make_float2(a.x * c - a.y * s, a.y * c + a.x * s) : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+  return INV ? cmul2(a, c, s) : cmul2(a, c, -s);
 }
 // a * w forward, a * conj(w) inverse, w = (cos, -sin) table entry
 template <bool INV>
 __device__ __forceinline__ float2 mul_tw(float2 a, float2 w) {
-  return INV ? make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y) : make_float2(a.x * w.x - a.y * w.y, a.y * w.x + a.x * w.y);
+  return INV ? cmul2(a, w.x, -w.y) : cmul2(a, w.x, w.y);
 }
 
 template <bool INV>
@@ -72,14 +122,14 @@ __device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float
   const float2 d = csub2(a1, a3);
   a0 = cadd2(s0, s2);
   a2 = csub2(s0, s2);
-  // y1 = s1 + rot(d), y3 = s1 - rot(d), rot = multiply by -j (forward) / +j (inverse): component-swapped,
-  // so these four stay scalar
+  // y1 = s1 + rot(d), y3 = s1 - rot(d), rot = multiply by -j (forward) / +j (inverse): lane swap + one negation,
+  // both operand modifiers of the packed add
   if (INV) {
-    a1 = make_float2(s1.x - d.y, s1.y + d.x);
-    a3 = make_float2(s1.x + d.y, s1.y - d.x);
+    a1 = cadd_pj(s1, d);
+    a3 = cadd_mj(s1, d);
   } else {
-    a1 = make_float2(s1.x + d.y, s1.y - d.x);
-    a3 = make_float2(s1.x - d.y, s1.y + d.x);
+    a1 = cadd_mj(s1, d);
+    a3 = cadd_pj(s1, d);
   }
 }
 
@@ -131,7 +181,7 @@ __device__ __forceinline__ void radix4_part(float2& a0, float2& a1, float2& a2, 
   } else {  // kMid8
     a2 = csub2(s0, s2);
   }
-  a1 = INV ? make_float2(s1.x - d.y, s1.y + d.x) : make_float2(s1.x + d.y, s1.y - d.x);
+  a1 = INV ? cadd_pj(s1, d) : cadd_mj(s1, d);
 }
 
 template <bool INV, int kPrune>

@@ -37,6 +37,7 @@ constexpr int kThreads = kT * kGroupsPerCta;
 constexpr int kWarps = kT / 32;          // warps per group
 constexpr int kWSize = f16::phys_size(kM);
 constexpr int kBinGroups = 9;            // bins t + 256 j, j < 8, and bin 2048 (t = 0, j = 8)
+constexpr int kDefaultBulk = 3;          // OMB_FAST2_BULK default (see launch_stft_fast2)
 
 struct Fast2Args {
   StftKernelArgs a;
@@ -47,7 +48,7 @@ struct Fast2Args {
 };
 
 struct GroupSmem {
-  float2 W[kWSize];
+  alignas(16) float2 W[kWSize];           // transform buffer; after the last transform of a frame: staging of the output column
   float Y[kM];                           // y[off + n] = Im c[n]
   int warp_cnt[kBinGroups * kWarps];
   int offs[kBinGroups * kWarps + 1];
@@ -60,8 +61,11 @@ struct Smem2 {
   float h[kM];
   float dh[kM];
   GroupSmem g[kGroupsPerCta];
+  alignas(16) uint64_t mbar[2];          // [0]: completion barrier of the ring's bulk copies (kBulkIn)
   // float ring[ring_len] follows
 };
+static_assert(sizeof(Smem2) % 16 == 0 && sizeof(GroupSmem) % 16 == 0, "bulk copies need 16-byte aligned shared addresses");
+static_assert(sizeof(float2) * kWSize >= 12 * (kM / 2 + 1) + 16, "the transform buffer must hold a whole output column");
 
 // Copies lane samples [s0, s1) (multiples of 4) into the ring at (sample index mod ring_len); all CTA threads.
 __device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const float* x, uint64_t s0, uint64_t s1) {
@@ -75,11 +79,20 @@ __device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const flo
 // saved pay for the power-of-two ring.)
 // kVariant bit 2: hop is a multiple of 4 but not of 512 (the settings UI's N/16 ... N/128): a frame's ring origin is then
 // not 512-aligned, so the wrap is applied per thread (one more LOP3 per ring read) instead of per warp-uniform row.
+// kVariant bit 3 (kBulkIn): the hop-overlapped staging ring is filled by the TMA engine — ONE elected thread issues one or two
+// bulk copies (cp.async.bulk.shared.global, 2 hops = 8 KB contiguous per frame pair) completing on an mbarrier, instead of
+// 512 per-thread 16-byte LDGSTS with their 64-bit loop and address arithmetic.
+// kVariant bit 4 (kBulkOut): the compacted column is staged in the (then idle) transform buffer and leaves the SM as ONE bulk
+// copy (cp.async.bulk.global.shared) instead of 27 predicated scalar STG per thread; the staging offset reproduces the slot's
+// misalignment (slots are 12-byte multiples) so the 16-byte aligned body is one copy and <= 3 head / tail floats are stored
+// by three threads each.
 template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
   constexpr int kTw2 = kVariant & 1;
   constexpr bool kLocal = (kVariant & 2) != 0;
   constexpr bool kAnyHop = (kVariant & 4) != 0;
+  constexpr bool kBulkIn = (kVariant & 8) != 0;
+  constexpr bool kBulkOut = (kVariant & 16) != 0;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
   float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
@@ -120,6 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   const float ramp0 = (float)t - (float)(kM - 1) * 0.5f;  // n - (N-1)/2 at j = 0
   const int pt = (kT - tf) & (kT - 1);
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
+  if (kBulkIn && tid == 0) mbar_init(&sm.mbar[0], 1);
+  unsigned ring_phase = 0;  // parity of the mbarrier phase the next wait is for
   __syncthreads();
 
   for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
@@ -132,17 +147,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
     {
       const uint64_t s0 = f_begin * (uint64_t)hop;
       const uint64_t s1 = s0 + (uint64_t)H + (uint64_t)hop < s_end ? s0 + (uint64_t)H + (uint64_t)hop : s_end;
-      ring_fetch(ring, ring_mask, x, s0, s1);
-      async_commit();
+      if (kBulkIn) {
+        if (tid == 0) {
+          mbar_expect_tx(&sm.mbar[0], ring_bytes(s0, s1));
+          ring_fetch_bulk(ring, ring_mask, x, s0, s1, &sm.mbar[0]);
+        }
+      } else {
+        ring_fetch(ring, ring_mask, x, s0, s1);
+        async_commit();
+      }
     }
     for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kGroupsPerCta) {
-      async_wait_all();
+      if (kBulkIn) {
+        mbar_wait(&sm.mbar[0], ring_phase);
+        ring_phase ^= 1u;
+      } else {
+        async_wait_all();
+      }
+      if (kBulkOut && t == 0) bulk_wait_read();  // the previous column has left the transform buffer
       __syncthreads();  // ring holds frames fa0, fa0+1; both groups are done with the previous pair
       {                 // prefetch what the next pair adds: two hops
         const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)hop;
         const uint64_t s1 = s0 + 2ull * hop < s_end ? s0 + 2ull * hop : s_end;
-        if (s0 < s1) ring_fetch(ring, ring_mask, x, s0, s1);
-        async_commit();
+        if (kBulkIn) {
+          if (tid == 0) {  // every phase is armed (with 0 bytes at the end of a run) so the parity bookkeeping stays uniform
+            mbar_expect_tx(&sm.mbar[0], ring_bytes(s0, s1));
+            ring_fetch_bulk(ring, ring_mask, x, s0, s1, &sm.mbar[0]);
+          }
+        } else {
+          if (s0 < s1) ring_fetch(ring, ring_mask, x, s0, s1);
+          async_commit();
+        }
       }
       const uint64_t f = fa0 + g;
       if (f < f_end) {
@@ -176,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           group_sync(g);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
+            // (ck, sk) = e^{j th_t} e^{j 2 pi j / 32} (immediate operands);  Q = ck conj(zp) + sk (j z): FMUL2 + FFMA2
             const float cj = f16::kCos32[j], sj = f16::kSin32[j];
             const float ck = cos_t * cj - sin_t * sj;
             const float sk = sin_t * cj + cos_t * sj;
@@ -223,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
             if (wsel == 2) wv *= ramp0 + (float)(kT * j);       // t*h window, processor.rs:601-608
             const float xs = kAnyHop ? ring[(r0 + off + kT * j + t) & ring_mask] : ring[((r0 + off + kT * j) & ring_mask) + t];
             const float cx = fmaf((float)kM, xs, bias);
-            v[j] = make_float2(cx * wv, gs.Y[t + kT * j] * wv);
+            v[j] = f16::cscale2(make_float2(cx, gs.Y[t + kT * j]), wv);
           }
           fft_forward<f16::kFirst9, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
           if (wsel == 0) {
@@ -273,21 +309,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         {
           const uint64_t slot = lane * a.frames_per_lane + f;
           float* out = reinterpret_cast<float*>(a.out_points + slot * a.point_stride);
+          // kBulkOut: same stores, into the idle transform buffer at the slot's own offset from a 16-byte boundary
+          const int mis = kBulkOut ? (int)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u) : 0;
+          float* dst = kBulkOut ? reinterpret_cast<float*>(gs.W) + mis : out;
 #pragma unroll
           for (int j = 0; j < kBinGroups; ++j)
             if (keep & (1u << j)) {
-              float* o = out + 3 * (gs.offs[j * kWarps + warp] + rank[j]);
+              float* o = dst + 3 * (gs.offs[j * kWarps + warp] + rank[j]);
               o[0] = pts[j].time_offset;
               o[1] = pts[j].freq_hz;
               o[2] = pts[j].power;
             }
-          if (t == 0) a.out_counts[slot] = (uint32_t)gs.offs[kBinGroups * kWarps];
+          const int count = gs.offs[kBinGroups * kWarps];
+          if (t == 0) a.out_counts[slot] = (uint32_t)count;
+          if (kBulkOut) {
+            fence_async_smem();  // this thread's staging stores -> visible to the copy engine
+            group_sync(g);
+            const int n = 3 * count;                       // floats of the column
+            const int head = ((4 - mis) & 3) < n ? ((4 - mis) & 3) : n;       // floats before the first 16-byte boundary of the slot
+            const int body = (n - head) & ~3;
+            const int tail = n - head - body;
+            if (t == 0 && body > 0) {
+              bulk_s2g(out + head, dst + head, (unsigned)body * 4u);
+              bulk_commit();
+            }
+            if (t >= 32 && t < 35 && t - 32 < head) out[t - 32] = dst[t - 32];
+            if (t >= 64 && t < 67 && t - 64 < tail) out[head + body + t - 64] = dst[head + body + t - 64];
+          }
         }
       }
     }
-    async_wait_all();
+    if (kBulkIn) {
+      mbar_wait(&sm.mbar[0], ring_phase);  // the last (empty) phase armed inside the loop
+      ring_phase ^= 1u;
+    } else {
+      async_wait_all();
+    }
     __syncthreads();
   }
+  if (kBulkOut && t == 0) bulk_wait_read();  // shared memory must outlive the copies that read it
 }
 
 uint32_t ring_len_for(uint64_t hop) { return (uint32_t)next_pow2(2 * (uint64_t)kM + 3 * hop); }
@@ -306,10 +366,12 @@ bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev) {
 
 int stft_fast2_prepare(StftPlan& plan) {
   const int smem = (int)smem_bytes(plan.cfg.hop);
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
 }
 
@@ -333,17 +395,20 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
-  static const int variant = [] { const char* e = getenv("OMB_FAST2_VARIANT"); return e ? atoi(e) & 3 : 2; }();
+  // OMB_FAST2_BULK: 0 = per-thread LDGSTS ring + scalar column stores (round 1), 1 = bulk ring fill, 3 = bulk ring fill and bulk
+  // column store (default: kDefaultBulk)
+  static const int bulk = [] { const char* e = getenv("OMB_FAST2_BULK"); return e ? atoi(e) & 3 : kDefaultBulk; }();
   const size_t smem = smem_bytes(a.hop);
-  if ((a.hop % 512) != 0) {
-    OMB_LAUNCH(k_reassigned_fast2<6>, dim3(grid), dim3(kThreads), smem, s, fa);
-  } else if (variant == 1) {
-    OMB_LAUNCH(k_reassigned_fast2<1>, dim3(grid), dim3(kThreads), smem, s, fa);
-  } else if (variant >= 2) {
-    OMB_LAUNCH(k_reassigned_fast2<2>, dim3(grid), dim3(kThreads), smem, s, fa);
+  const bool any_hop = (a.hop % 512) != 0;
+#define OMB_FAST2_LAUNCH(V) OMB_LAUNCH(k_reassigned_fast2<V>, dim3(grid), dim3(kThreads), smem, s, fa)
+  if (bulk == 0) {
+    if (any_hop) OMB_FAST2_LAUNCH(6); else OMB_FAST2_LAUNCH(2);
+  } else if (bulk == 1) {
+    if (any_hop) OMB_FAST2_LAUNCH(14); else OMB_FAST2_LAUNCH(10);
   } else {
-    OMB_LAUNCH(k_reassigned_fast2<0>, dim3(grid), dim3(kThreads), smem, s, fa);
+    if (any_hop) OMB_FAST2_LAUNCH(30); else OMB_FAST2_LAUNCH(26);
   }
+#undef OMB_FAST2_LAUNCH
   OMB_CHECK_LAUNCH();
   return OMB_OK;
 }
