@@ -487,6 +487,17 @@ int omb_splat_resolve_device(const float* d_accum, uint32_t n_rings, const omb_s
 int omb_splat_render_host(const omb_spectrogram_point* h_rings, uint64_t point_stride, const uint32_t* h_slot_counts,
                           uint32_t n_rings, const omb_splat_params* p, float* h_accum, float* h_db);
 
+/* The reassigned STFT chained into the splat passes on the device: what the reference does per frame tick when
+ * SpectrogramUpdate.new_columns go into the point ring and are drawn (spectrogram/render.rs:557-598 -> wgsl:126-147,
+ * 215-237).  Every lane is one view whose ring holds all of the lane's columns: `view`'s ring_capacity / col_count /
+ * newest_col / reassigned_power_scale are SET by the call (frames per lane, last frame newest, the plan's power scale);
+ * its axis, extent, scale_factor and tilt are the caller's.  h_db: n_lanes images [height][width] f32 dB (-inf where nothing
+ * was drawn), omb_splat_image_size(view); h_out_counts (may be NULL): [lane][frame] points per column.  Only PCM goes
+ * up and only images (+ counts) come back: the 24.6 KB of points per column never cross PCIe.  Lane chunks are pipelined
+ * (H2D / kernels / D2H overlap).  Reassigned plans only; at most 65535 columns per lane per call. */
+int omb_stft_render_host(omb_stft_plan* p, const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane,
+                         uint64_t lane_stride, const omb_splat_params* view, float* h_db, uint32_t* h_out_counts);
+
 
 /* ------------------------------------------------------------------------ */
 /* Row f1, device side: the multi-stream ring.  S independent streams that    */

@@ -278,6 +278,7 @@ HEADER_SYMBOLS = {
     "splat_accumulate_device": (C.c_int, [_vp, _u64, _vp, _u32, C.POINTER(SplatParams), _vp, _vp]),
     "splat_resolve_device": (C.c_int, [_vp, _u32, C.POINTER(SplatParams), _vp, _vp]),
     "splat_render_host": (C.c_int, [_vp, _u64, _vp, _u32, C.POINTER(SplatParams), _vp, _vp]),
+    "stft_render_host": (C.c_int, [_vp, _vp, _u32, _u64, _u64, C.POINTER(SplatParams), _vp, _vp]),
 }
 
 

@@ -50,6 +50,22 @@ class StftPlan:
                "stft_execute_host")
         return codes
 
+    def render_host(self, lanes: np.ndarray, view, want_counts: bool = True):
+        """STFT -> splat accumulate -> resolve on the device (omb_stft_render_host): lanes (L, S) float32 and a
+        `splat.SplatParams` view -> dB images (L, H, W) float32 (and counts (L, F)); the points never leave the GPU."""
+        lanes = np.ascontiguousarray(lanes, np.float32)
+        L, S = lanes.shape
+        F = self.frames_per_lane(S)
+        c = view.to_c()
+        c.ring_capacity = max(F, 1)
+        w, h = C.c_uint32(), C.c_uint32()
+        self._api.splat_image_size(C.byref(c), C.byref(w), C.byref(h))
+        db = np.full((L, h.value, w.value), -np.inf, np.float32)
+        cnt = np.zeros((L, F), np.uint32)
+        _check(self._api, self._api.stft_render_host(self._h, lanes.ctypes.data, L, S, S, C.byref(c), db.ctypes.data,
+                                                     cnt.ctypes.data if want_counts else None), "stft_render_host")
+        return (db, cnt) if want_counts else db
+
     def execute_device(self, lanes_ptr: int, n_lanes: int, samples: int, lane_stride: int, points_ptr: int = 0,
                        point_stride: int = 0, counts_ptr: int = 0, classic_ptr: int = 0, stream: int = 0) -> None:
         _check(self._api, self._api.stft_execute_device(self._h, lanes_ptr, n_lanes, samples, lane_stride, points_ptr or None,

@@ -283,6 +283,14 @@ int omb_stft_execute_host(omb_stft_plan* p, const float* h_lanes, uint32_t n_lan
   OMB_GUARD_END
 }
 
+int omb_stft_render_host(omb_stft_plan* p, const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
+                         const omb_splat_params* view, float* h_db, uint32_t* h_out_counts) {
+  OMB_GUARD_BEGIN
+  if (!p || !view) return fail(OMB_ERR_INVALID, "null argument");
+  return p->p.render_host(h_lanes, n_lanes, samples_per_lane, lane_stride, *view, h_db, h_out_counts);
+  OMB_GUARD_END
+}
+
 // ---- batched spectrum
 uint64_t omb_spectrum_hops_per_lane(const omb_spectrum_config* cfg, uint64_t samples) {
   if (!cfg) return 0;

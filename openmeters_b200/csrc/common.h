@@ -7,15 +7,36 @@
 #include <cuda_runtime.h>
 #endif
 
-// Packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2, see fft16.cuh) in the device helpers.  OMB_F32X2_LEVEL: 0 = scalar code
-// (CPU emulator, -DOMB_NO_F32X2), 1 = packed complex add / subtract only (the round-1 kernels; A/B builds), 2 = every complex
-// primitive packed (default).
+// Packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2, see fft16.cuh) in the device helpers.  Each class of primitive has its own
+// switch because they were measured separately on B200 (profiles/r02b_packed_ab.md):
+//   OMB_F32X2_ADD   complex add / subtract as one FADD2                          default 1  (round 1: +8 % on the cfg2 kernel)
+//   OMB_F32X2_ROT   a -+ j b as one FADD2 with lane-swap / negate modifiers      default 0
+//   OMB_F32X2_MUL   complex products of the radix-16 engine as FMUL2 + FFMA2     default 0  (-7 % cfg2, -9 % N = 2048, -12 % N = 1024:
+//                   the engine is bound by the FMA pipe, which a packed instruction holds for two cycles, not by issue slots)
+//   OMB_F32X2_CMUL  device_math.cuh cmul / cmul_conj (Stockham, generic tiers)   default 1  (+1 ... +16 % on those tiers)
+// The CPU emulator and -DOMB_NO_F32X2 force scalar code everywhere.
 #if defined(OMB_EMU) || defined(OMB_NO_F32X2)
-#define OMB_F32X2_LEVEL 0
-#elif !defined(OMB_F32X2_LEVEL)
-#define OMB_F32X2_LEVEL 2
+#undef OMB_F32X2_ADD
+#undef OMB_F32X2_ROT
+#undef OMB_F32X2_MUL
+#undef OMB_F32X2_CMUL
+#define OMB_F32X2_ADD 0
+#define OMB_F32X2_ROT 0
+#define OMB_F32X2_MUL 0
+#define OMB_F32X2_CMUL 0
 #endif
-#define OMB_F32X2 (OMB_F32X2_LEVEL >= 2)
+#ifndef OMB_F32X2_ADD
+#define OMB_F32X2_ADD 1
+#endif
+#ifndef OMB_F32X2_ROT
+#define OMB_F32X2_ROT 0
+#endif
+#ifndef OMB_F32X2_MUL
+#define OMB_F32X2_MUL 0
+#endif
+#ifndef OMB_F32X2_CMUL
+#define OMB_F32X2_CMUL 1
+#endif
 
 #include <atomic>
 #include <cstdarg>

@@ -38,21 +38,23 @@ __device__ constexpr float kSin32[16] = {0.0f, 0.19509032201612826785f, 0.382683
 //     a + b, a - b                       1 FADD2
 //     a -+ j b   (radix-4 rotation)      1 FADD2  (b.LO_HI.NP)              — two scalar FADDs before
 //     a * w      (complex)               1 FMUL2 (a, w.x bcast) + 1 FFMA2 (a.LO_HI, w.y bcast with .NP, acc)  — four before
-// A packed instruction holds the FMA pipe for two cycles, so the pipe time is unchanged; what halves is the ISSUE cost,
-// and the freed issue slots are what lets the load / store phases of the other warps run under the butterflies
-// (round-2 ncu: FMUL + FFMA + FADD were 50 % of all issued instructions, profiles/r02a_*).  ptxas folds the
-// make_float2(...) swizzles below into those modifiers (checked with cuobjdump: no MOV / PRMT).  OMB_NO_F32X2 or the CPU
-// emulator (OMB_EMU) restore scalar code with separately rounded multiplies and adds.
-// (OMB_F32X2 is defined in common.h.)
+// A packed instruction holds the FMA pipe for two cycles, so the pipe time is unchanged; what halves is the ISSUE cost.
+// ptxas folds the make_float2(...) swizzles below into those modifiers (checked with cuobjdump: no MOV / PRMT).
+// MEASURED (B200, profiles/r02b_packed_ab.md): packing the additions pays (round 1), packing the PRODUCTS does not — the
+// radix-16 kernels lose 7-13 % (static instructions 3440 -> 2944 for the cfg2 kernel, yet slower): they are bound by the
+// FMA pipe inside the butterfly phases, not by issue slots, and the two-instruction packed product is a longer dependent
+// chain than the four scalar ones it replaces.  So the switches of common.h default to packed adds only; the packed
+// product forms stay here behind OMB_F32X2_MUL / OMB_F32X2_ROT for A/B builds.
+// (switches: common.h.)
 __device__ __forceinline__ float2 cadd2(float2 a, float2 b) {
-#if OMB_F32X2_LEVEL >= 1
+#if OMB_F32X2_ADD
   return __fadd2_rn(a, b);
 #else
   return make_float2(a.x + b.x, a.y + b.y);
 #endif
 }
 __device__ __forceinline__ float2 csub2(float2 a, float2 b) {
-#if OMB_F32X2_LEVEL >= 1
+#if OMB_F32X2_ADD
   return __fadd2_rn(a, make_float2(-b.x, -b.y));
 #else
   return make_float2(a.x - b.x, a.y - b.y);
@@ -60,14 +62,14 @@ __device__ __forceinline__ float2 csub2(float2 a, float2 b) {
 }
 // a + (-j) b = (a.x + b.y, a.y - b.x)   and   a + (+j) b = (a.x - b.y, a.y + b.x)
 __device__ __forceinline__ float2 cadd_mj(float2 a, float2 b) {
-#if OMB_F32X2
+#if OMB_F32X2_ROT
   return __fadd2_rn(a, make_float2(b.y, -b.x));
 #else
   return make_float2(a.x + b.y, a.y - b.x);
 #endif
 }
 __device__ __forceinline__ float2 cadd_pj(float2 a, float2 b) {
-#if OMB_F32X2
+#if OMB_F32X2_ROT
   return __fadd2_rn(a, make_float2(-b.y, b.x));
 #else
   return make_float2(a.x - b.y, a.y + b.x);
@@ -75,7 +77,7 @@ __device__ __forceinline__ float2 cadd_pj(float2 a, float2 b) {
 }
 // a * (wx + j wy)
 __device__ __forceinline__ float2 cmul2(float2 a, float wx, float wy) {
-#if OMB_F32X2
+#if OMB_F32X2_MUL
   return __ffma2_rn(make_float2(a.y, a.x), make_float2(-wy, wy), __fmul2_rn(a, make_float2(wx, wx)));
 #else
   return make_float2(a.x * wx - a.y * wy, a.y * wx + a.x * wy);
@@ -83,7 +85,7 @@ __device__ __forceinline__ float2 cmul2(float2 a, float wx, float wy) {
 }
 // (ax, ay) * s  (both lanes by one scalar)
 __device__ __forceinline__ float2 cscale2(float2 a, float s) {
-#if OMB_F32X2
+#if OMB_F32X2_MUL
   return __fmul2_rn(a, make_float2(s, s));
 #else
   return make_float2(a.x * s, a.y * s);
@@ -92,7 +94,7 @@ __device__ __forceinline__ float2 cscale2(float2 a, float s) {
 
 // c conj(p) + s (j z) = (c p.x - s z.y, s z.x - c p.y): the Hilbert pair step of the reassigned kernels
 __device__ __forceinline__ float2 pair_q(float2 p, float2 z, float c, float s) {
-#if OMB_F32X2
+#if OMB_F32X2_MUL
   return __ffma2_rn(make_float2(-z.y, z.x), make_float2(s, s), __fmul2_rn(make_float2(p.x, -p.y), make_float2(c, c)));
 #else
   return make_float2(c * p.x - s * z.y, s * z.x - c * p.y);

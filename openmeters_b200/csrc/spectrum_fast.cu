@@ -9,6 +9,14 @@
 //     X[k] = A + W_16384^k B,  X[8192-k] = conj(A - W_16384^k B),  A = (P + conj Q)/2, B = (P - conj Q)/(2j)
 // DC removal uses per-hop f64 block sums from a small pre-kernel (mean = sum of N/hop block sums / N), so the PCM is
 // read once by the FFT kernel.  Rows a4, a12 of SURVEY.md §8; spectrum/processor.rs:215-244.
+// Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): everything packed
+// (adds, rotations, products) — a small gain here (+0.5 ... +1.6 %).
+#ifndef OMB_F32X2_MUL
+#define OMB_F32X2_MUL 1
+#endif
+#ifndef OMB_F32X2_ROT
+#define OMB_F32X2_ROT 1
+#endif
 #include <algorithm>
 #include <cmath>
 

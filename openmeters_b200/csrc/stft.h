@@ -69,6 +69,7 @@ struct StftPlan {
   DeviceBuffer<omb_spectrogram_point> d_points;
   DeviceBuffer<uint32_t> d_counts;
   DeviceBuffer<uint16_t> d_classic;
+  DeviceBuffer<float> d_img_accum, d_img_db;  // render_host: accumulation / dB images of the lane chunks in flight
   cudaStream_t stream = nullptr;  // owned, for the host path
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // host path: H2D / kernel / D2H overlap across lane chunks
 
@@ -80,6 +81,9 @@ struct StftPlan {
                      cudaStream_t s, uint64_t first_frame = 0);
   int execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
                    omb_spectrogram_point* h_points, uint64_t point_stride, uint32_t* h_counts, uint16_t* h_classic);
+  // stft_render.cu: STFT -> splat accumulate -> resolve on the device; only the dB images (and optionally counts) come back
+  int render_host(const float* h_lanes, uint32_t n_lanes, uint64_t samples_per_lane, uint64_t lane_stride,
+                  const omb_splat_params& view, float* h_db, uint32_t* h_counts);
 };
 
 // kernel launchers (stft_generic.cu / stft_fast.cu)

@@ -14,6 +14,14 @@
 //              |X[512-k]| = |E - W_1024^k O|, so every lane converts 16 bins to dB / u16 from 8 pair loads.
 //
 // Algorithmic bytes per frame: hop * 4 read + 513 * 2 written (3074 B at hop 512).
+// Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): everything packed
+// (adds, rotations, products) — a small gain here (+0.5 ... +1.6 %).
+#ifndef OMB_F32X2_MUL
+#define OMB_F32X2_MUL 1
+#endif
+#ifndef OMB_F32X2_ROT
+#define OMB_F32X2_ROT 1
+#endif
 #include "device_math.cuh"
 #include "fft16.cuh"
 #include "stft.h"

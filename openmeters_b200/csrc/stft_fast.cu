@@ -18,6 +18,11 @@
 //   G  : c = centre N samples of a; S, D, T = FFT_M(c*h), FFT_M(c*dh), FFT_M(c*th)
 //   R  : per-bin reassignment + order-preserving compaction (ascending bin) -> points, count
 // 5 complex M-point FFTs per frame instead of the literal 2 x 2M + 3 x M.
+// Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): packed complex adds
+// only — packed products cost this FMA-pipe-bound kernel 2-13 %.
+#ifndef OMB_F32X2_CMUL
+#define OMB_F32X2_CMUL 0
+#endif
 #include "device_math.cuh"
 #include "fft16.cuh"
 #include "stft.h"

@@ -8,6 +8,11 @@
 // products per bin.  Thread t owns bins t + 256 j, j < 4, of all four frames in the frequency domain and the samples
 // (t >> 2) + 64 j of frame (t & 3) in the time domain.  Factors 4 of the separation are folded into the pair-step
 // coefficients and the bin normalisation (exact).  One 512-thread CTA = two groups = eight consecutive frames per iteration.
+// Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): packed complex adds
+// only — packed products cost this FMA-pipe-bound kernel 2-13 %.
+#ifndef OMB_F32X2_CMUL
+#define OMB_F32X2_CMUL 0
+#endif
 #include "async_copy.cuh"
 #include "device_math.cuh"
 #include "fft16.cuh"

@@ -17,6 +17,11 @@
 //   * the pair step uses Q[k] = cos(th_k) conj(Z[M-k]) + j sin(th_k) Z[k], th_k = 2 pi k / H (8 flops per bin),
 //   * last passes are pruned to the outputs that are used (9 of 16 bins per thread <= Nyquist; centre 8 of 16
 //     of the inverse).
+// Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): packed complex adds
+// only — packed products cost this FMA-pipe-bound kernel 2-13 %.
+#ifndef OMB_F32X2_CMUL
+#define OMB_F32X2_CMUL 0
+#endif
 #include <cstdlib>
 
 #include "async_copy.cuh"

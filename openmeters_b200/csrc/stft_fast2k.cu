@@ -11,6 +11,11 @@
 // pruned inverse (outputs 4..11 = the centre half) are unchanged.  Power-of-two factors of the separation (2 FA) are
 // folded into the pair-step coefficients and the bin normalisation (exact).
 // One 512-thread CTA = two groups = four consecutive frames per iteration, sharing one staging ring.
+// Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): packed complex adds
+// only — packed products cost this FMA-pipe-bound kernel 2-13 %.
+#ifndef OMB_F32X2_CMUL
+#define OMB_F32X2_CMUL 0
+#endif
 #include "async_copy.cuh"
 #include "device_math.cuh"
 #include "fft16.cuh"

@@ -20,6 +20,11 @@
 // current frame does not read while the current frame is computed.  Window h, the twiddle rows and Im(c) stay in
 // shared memory (220 KB in total); the derivative window is read through L1/L2 (it does not fit).
 // Rows a8-a10 of SURVEY.md §8; spectrogram/processor.rs:313-347,439-488,546-567.
+// Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): packed complex adds
+// only — packed products cost this FMA-pipe-bound kernel 2-13 %.
+#ifndef OMB_F32X2_CMUL
+#define OMB_F32X2_CMUL 0
+#endif
 #include <algorithm>
 #include <cmath>
 

@@ -658,6 +658,10 @@ struct SpectrogramProcessor {
     const bool hop_changed = prev.hop_size != c.hop_size;
     if (hop_changed) pending_skip = 0;
     reset = reset || rebuild || hop_changed;
+    // The column engine caches the config at rebuild() time; the reference reads self.config.hop_size LIVE in
+    // process_ready_windows / reassigned_points (:283, :446-450), so a hop-only change (no rebuild) must reach it too.
+    eng.cfg.hop_size = c.hop_size;
+    eng.cfg.history_length = c.history_length;
   }
 };
 

@@ -243,7 +243,105 @@ def kat_update_reports_reset_once(b):
     assert p.process_block(AudioBlock(np.zeros(0, np.float32), 1, 48000.0)) is None
 
 
+def kat_hop_change_mid_stream_uses_the_live_hop(b):
+    """spectrogram/processor.rs:283,446-450,518-543 — update_config with ONLY the hop changed does not rebuild the transforms;
+    process_ready_windows and reassigned_points read self.config.hop_size live, so the very next column steps by the new hop
+    and its time_offset is (T.S*/|S|^2 - center_offset) / NEW hop; `reset` is reported once; pending audio is kept."""
+    n = 1024
+    cfg = _cfg(n, 256, True, history_length=64, window=capi.WINDOW_HANN)
+    freq = np.float32(100.0) * np.float32(cfg.sample_rate) / np.float32(n)
+    x = sine_wave(freq, cfg.sample_rate, 2 * n + 8 * 256, 0.5)
+    p = b.Spectrogram(cfg)
+    first = p.process_block(AudioBlock(x[: 2 * n + 256], 1, cfg.sample_rate))
+    assert first is not None and len(first.new_columns) == 2 and first.reset is True and first.hop_size == 256
+    assert abs(float(_peak_point(first.new_columns[-1])[0]) + 2.0) < 0.05   # -(2048-1024)/2/256
+    c = p.config()
+    c.hop_size = 128
+    p.update_config(c)
+    assert p.config().hop_size == 128 and p.config().fft_size == n
+    # pending after two hops of 256: 2n+256-512 = 2n-256 samples; 384 more complete one frame plus one new hop of 128
+    second = p.process_block(AudioBlock(x[2 * n + 256: 2 * n + 256 + 384], 1, cfg.sample_rate))
+    assert second is not None and second.reset is True and second.hop_size == 128
+    assert len(second.new_columns) == 2
+    for col in second.new_columns:
+        pk = _peak_point(col)
+        assert abs(float(pk[0]) + 4.0) < 0.05, pk                              # -(2048-1024)/2/128
+        assert abs(float(pk[1]) - float(freq)) < 2.0
+    third = p.process_block(AudioBlock(x[2 * n + 256 + 384: 2 * n + 256 + 384 + 128], 1, cfg.sample_rate))
+    assert third is not None and third.reset is False and len(third.new_columns) == 1
+
+
+def kat_window_and_mode_change_mid_stream(b):
+    """spectrogram/processor.rs:518-543,229-279 — a window change rebuilds (reset reported, newest pending audio kept:
+    fft_rebuild_keeps_newest_pending_audio :794-805), toggling reassignment switches the column kind, and the columns
+    after each change equal those of a fresh processor with the new config fed the retained audio."""
+    n, hop = 256, 64
+    i = np.arange(6 * n)
+    x = np.sin(((i * i + 5 * i).astype(np.float32) * np.float32(0.0009)), dtype=np.float32)
+    cfg = _cfg(n, hop, False, history_length=64, window=capi.WINDOW_HANN)
+    p = b.Spectrogram(cfg)
+    a = p.process_block(AudioBlock(x[: 2 * n], 1, cfg.sample_rate))
+    assert a is not None and a.kind == capi.COLUMN_CLASSIC and len(a.new_columns) == (2 * n - n) // hop + 1
+    consumed = len(a.new_columns) * hop                       # samples drained so far; pending = 2n - consumed
+    c = p.config()
+    c.window = capi.WINDOW_BLACKMAN_HARRIS
+    p.update_config(c)
+    u = p.process_block(AudioBlock(x[2 * n: 3 * n], 1, cfg.sample_rate))
+    assert u is not None and u.reset is True and u.kind == capi.COLUMN_CLASSIC
+    fresh = b.Spectrogram(_cfg(n, hop, False, history_length=64, window=capi.WINDOW_BLACKMAN_HARRIS))
+    v = fresh.process_block(AudioBlock(x[consumed: 3 * n], 1, cfg.sample_rate))
+    assert len(u.new_columns) == len(v.new_columns) > 0
+    for e, g in zip(v.new_columns, u.new_columns):
+        assert np.array_equal(e, g)
+    consumed += len(u.new_columns) * hop
+    c.use_reassignment = True
+    p.update_config(c)
+    w = p.process_block(AudioBlock(x[3 * n: 5 * n], 1, cfg.sample_rate))
+    assert w is not None and w.reset is True and w.kind == capi.COLUMN_REASSIGNED
+    fresh = b.Spectrogram(_cfg(n, hop, True, history_length=64, window=capi.WINDOW_BLACKMAN_HARRIS))
+    # rebuild_fft drains the pending audio to at most 2 * active_len = 4n samples (:275-277): nothing is dropped here
+    z = fresh.process_block(AudioBlock(x[consumed: 5 * n], 1, cfg.sample_rate))
+    assert len(w.new_columns) == len(z.new_columns) > 0
+    for e, g in zip(z.new_columns, w.new_columns):
+        assert np.array_equal(e, g)
+
+
 # ------------------------------------------------------------------ spectrum
+def kat_changing_averaging_mode_clears_stale_state(b):
+    """spectrum/processor.rs:566-581 (and update_config :300-322).  The reference pokes `levels[0].smoothed_power`; the
+    behavioural statement of the same fact: after PeakHold has accumulated a loud passage, switching to Exponential
+    mid-stream must give — from that hop on — exactly what a FRESH Exponential processor gives on the retained audio
+    (only the level buffers are reset: pending PCM is kept), and a change of the decay PARAMETER alone (same enum
+    discriminant, same floor) must keep the held state."""
+    n, hop, sr = 256, 64, 48000.0
+    loud = sine_wave(3000.0, sr, 4 * n, 0.9)
+    quiet = sine_wave(3000.0, sr, 4 * n, 0.001)
+    base = dict(sample_rate=sr, fft_size=n, hop_size=hop, window=capi.WINDOW_HANN, floor_db=-120.0)
+    p = b.Spectrum(SpectrumConfig(averaging=capi.AVG_PEAK_HOLD, averaging_param=0.5, **base))
+    s0 = p.process_block(AudioBlock(loud, 1, sr))
+    assert s0 is not None
+    hops_done = (loud.size - n) // hop + 1
+    held_peak = float(np.max(s0.traces[0][1]))
+    c = p.config()
+    c.averaging, c.averaging_param = capi.AVG_EXPONENTIAL, 0.5
+    p.update_config(c)
+    s1 = p.process_block(AudioBlock(quiet, 1, sr))
+    fresh = b.Spectrum(SpectrumConfig(averaging=capi.AVG_EXPONENTIAL, averaging_param=0.5, **base))
+    s2 = fresh.process_block(AudioBlock(np.concatenate([loud[hops_done * hop:], quiet]), 1, sr))
+    assert s1 is not None and s2 is not None
+    for w in range(2):
+        assert np.array_equal(s1.traces[0][w], s2.traces[0][w])
+    assert float(np.max(s1.traces[0][1])) < held_peak - 30.0      # stale hold (decaying 0.5 dB/s) would still sit at held_peak
+    # parameter-only change: state survives
+    q = b.Spectrum(SpectrumConfig(averaging=capi.AVG_PEAK_HOLD, averaging_param=0.5, **base))
+    q.process_block(AudioBlock(loud, 1, sr))
+    c = q.config()
+    c.averaging_param = 1.0
+    q.update_config(c)
+    s3 = q.process_block(AudioBlock(quiet, 1, sr))
+    assert float(np.max(s3.traces[0][1])) > held_peak - 1.0
+
+
 def kat_spectrum_normalization(b):
     """spectrum/processor.rs:432-457"""
     p = b.Spectrum(SpectrumConfig(sample_rate=float("nan"), fft_size=0, hop_size=0, floor_db=float("inf")))

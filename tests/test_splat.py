@@ -102,3 +102,47 @@ def test_splat_of_real_reassigned_columns(product):
     total_points = sum(float(rings[r, s, :counts[r, s], 2].astype(np.float64).sum()) for r in range(2) for s in range(frames))
     assert acc.sum() <= total_points * (1 + 1e-5)
     assert acc.sum() >= 0.9 * total_points         # only points reassigned off the visible time / frequency range are lost
+
+
+def _render_vs_two_step(api, n, hop, window, lanes, ext_h=96.0, scale=1.0):
+    """omb_stft_render_host (STFT -> splat -> resolve chained on the device, only images come back) against the two public
+    steps it fuses: omb_stft_execute_host, then omb_splat_render_host on the returned points."""
+    from openmeters_b200 import batch
+    from openmeters_b200.processors import SpectrogramConfig
+
+    cfg = SpectrogramConfig(fft_size=n, hop_size=hop, window=window, use_reassignment=True)
+    plan = batch.StftPlan(cfg, api=api)
+    pts, cnt = plan.execute_host(lanes)
+    L, F = cnt.shape
+    fmin, fmax = splat.display_axis(48000.0)
+    view = splat.SplatParams(freq_min=fmin, freq_max=fmax, ext_w=float(F) * scale + 3.0, ext_h=ext_h, scale_factor=scale)
+    db, cnt2 = plan.render_host(lanes, view)
+    assert np.array_equal(cnt, cnt2)
+    full = splat.SplatParams(**{**view.__dict__, "ring_capacity": F, "newest_col": F - 1, "col_count": F,
+                                "reassigned_power_scale": plan.power_scale})
+    acc_ref, db_ref = splat.render_host(pts, cnt, full, api=api)
+    assert db.shape == db_ref.shape
+    assert np.array_equal(np.isneginf(db), np.isneginf(db_ref))
+    lit = ~np.isneginf(db_ref)
+    assert lit.mean() > 0.05
+    assert np.max(np.abs(db[lit] - db_ref[lit])) < 1e-3      # f32 atomics: summation order differs between the two runs
+    return db
+
+
+def test_stft_render_host_emulated(emu):
+    from openmeters_b200 import synth
+
+    lanes = synth.cfg2_lanes(5, (8192 + 6 * 1024) / 48000.0)
+    _render_vs_two_step(emu.api, 4096, 1024, capi.WINDOW_BLACKMAN_HARRIS, lanes)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,hop,lanes,secs", [(4096, 1024, 13, 2.0), (2048, 64, 2, 0.4)])
+def test_stft_render_host_gpu(product, n, hop, lanes, secs):
+    from openmeters_b200 import synth
+
+    x = synth.cfg2_lanes(lanes, secs)
+    db = _render_vs_two_step(product.api, n, hop, capi.WINDOW_BLACKMAN_HARRIS if n == 4096 else capi.WINDOW_HANN, x, ext_h=300.0, scale=1.5)
+    # a chirp draws a ridge: the brightest pixel of the newest column region is far above the median lit pixel
+    lit = db[np.isfinite(db)]
+    assert lit.max() > np.median(lit) + 30.0
