@@ -54,18 +54,19 @@ def cfg3_surround(seconds: float = 30.0, sr: float = 48000.0) -> np.ndarray:
     return ch.astype(np.float32).reshape(-1)
 
 
-def cfg4_streams(n_streams: int = 64, seconds: float = 20.0, sr: float = 48000.0) -> np.ndarray:
+def cfg4_streams(n_streams: int = 64, seconds: float = 20.0, sr: float = 48000.0, first: int = 0) -> np.ndarray:
     """stream s: two sines at 100(s+1) Hz and 55(s+3) Hz, amplitude-modulated at 0.5 Hz, + noise(seed 3000+s).
     Returns (n_streams, 2, S) planar f32: lane 0 = Left, lane 1 = Right (Right = 0.7*Left + own noise)."""
     n = int(seconds * sr)
     t = np.arange(n, dtype=np.float64) / sr
     out = np.empty((n_streams, 2, n), np.float32)
     am = 0.5 * (1 + np.sin(2 * np.pi * 0.5 * t))
-    for s in range(n_streams):
+    for i in range(n_streams):
+        s = first + i  # global stream index: streams [first, first + n_streams) of the set
         rng = np.random.default_rng(3000 + s)
         base = am * (0.3 * np.sin(2 * np.pi * 100.0 * (s + 1) * t) + 0.2 * np.sin(2 * np.pi * 55.0 * (s + 3) * t))
-        out[s, 0] = (base + 0.01 * rng.uniform(-1, 1, n)).astype(np.float32)
-        out[s, 1] = (0.7 * base + 0.01 * rng.uniform(-1, 1, n)).astype(np.float32)
+        out[i, 0] = (base + 0.01 * rng.uniform(-1, 1, n)).astype(np.float32)
+        out[i, 1] = (0.7 * base + 0.01 * rng.uniform(-1, 1, n)).astype(np.float32)
     return out
 
 

@@ -103,3 +103,53 @@ def test_cpp_mirror_compiles_and_runs(lib, tmp_path):
                     "-L", libdir, "-lomb200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+# ------------------------------------------------------------------ the Rust side (rust/: cannot be compiled here, no cargo)
+def _gen():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_rust_sys_crate_is_generated_from_the_header_and_current():
+    g = _gen()
+    assert open(g.OUT).read() == g.render(g.parse_header()), "rust/omb200-sys/src/lib.rs is stale: python tools/gen_rust_sys.py"
+
+
+def test_rust_externs_match_header_names_and_arity(lib):
+    """Every `extern "C"` declaration of the -sys crate: declared in the header with the same number of parameters, exported
+    by libomb200.so, and with a ctypes twin of the same arity (tests and bench bind through that table)."""
+    g = _gen()
+    rust = g.parse_rust_externs()
+    hdr = {name: len(params) for name, _, params in g.parse_header()["functions"]}
+    assert sorted(rust) == sorted(hdr) == header_functions()
+    assert rust == hdr
+    for name, n in rust.items():
+        assert hasattr(lib, name), name
+        assert len(capi.HEADER_SYMBOLS[name[4:]][1]) == n, (name, n, capi.HEADER_SYMBOLS[name[4:]][1])
+
+
+def test_rust_wrapper_exposes_the_registry_method_set():
+    """src/visuals/registry.rs:100-118 calls new / config / update_config / prepare / process_block / reset_audio on the
+    spectrogram and spectrum processors and new / process_block / reset_audio on loudness: the wrapper must define them,
+    and use only functions the -sys crate declares."""
+    g = _gen()
+    rust = g.parse_rust_externs()
+    want = {"spectrogram.rs": ["new", "config", "update_config", "prepare", "reset_audio", "process_block"],
+            "spectrum.rs": ["new", "config", "update_config", "prepare", "reset_audio", "process_block"],
+            "loudness.rs": ["new", "reset_audio", "process_block"]}
+    for fname, methods in want.items():
+        src = open(os.path.join(ROOT, "rust", "omb200", "src", fname)).read()
+        for m in methods:
+            assert re.search(rf"pub fn {m}\(", src), (fname, m)
+        for used in set(re.findall(r"sys::(omb_\w+)\(", src)):
+            assert used in rust, (fname, used)
+    # struct layouts the wrapper copies field by field: same field names as the header's structs
+    hdr_structs = dict(g.parse_header()["structs"])
+    src = open(os.path.join(ROOT, "rust", "omb200", "src", "spectrogram.rs")).read()
+    for field, _ in hdr_structs["omb_spectrogram_config"]:
+        assert field in src, field
