@@ -545,64 +545,140 @@ def run_ours(args):
 
 
 def run_scatter(args, wl, torch, dist, dev, stream, rank, world, k, fl, units_job, d_lanes, allmax, barrier, checksum_resident):
-    """Rank 0 holds the whole job's PCM rank-major in HBM ([rank][lane][sample]); per step ONE grouped NCCL send/recv
-    (torch batch_isend_irecv = ncclGroupStart ... ncclSend/ncclRecv ... ncclGroupEnd) moves every other rank's block over
-    NVLink into one of its two input buffers on a side stream while the kernels run on the other buffer."""
+    """Scatter-inclusive rates: the job's PCM lives rank-major ([rank][lane][sample]) in rank 0's HBM and every step each rank
+    consumes ITS block of it.  Three transports, all timed the same way (K steps, max over ranks, checksum against the resident run):
+
+      nccl         one grouped ncclSend/ncclRecv per step (torch batch_isend_irecv) on a side stream, double-buffered against the
+                   kernels.  NCCL's copy kernels need SMs, and the cfg2 kernel is persistent with every SM's registers and shared
+                   memory taken, so the two do not overlap: the transfer serialises with the compute.
+      peer_dma     rank 0 exports the buffer with CUDA IPC (omb_peer_alloc / omb_peer_open); every other rank PULLS its block with
+                   its own copy engine (cudaMemcpyAsync over NVLink, no SMs) into one of two input buffers while its kernel runs
+                   on the other.
+      peer_direct  no copy at all: the mapped pointer is the kernel's input — the hop-overlapped staging ring is filled by TMA bulk
+                   copies (cp.async.bulk) that read rank 0's HBM over NVLink one frame pair ahead of the math.  The scatter is
+                   fused into the kernel's own prefetch.
+    """
+    api = wl.plan._api
+    blk = k * fl * 4
     comm = torch.cuda.Stream(dev)
     bufs = [torch.empty((k, fl), dtype=torch.float32, device=dev) for _ in range(2)]
-    all_lanes = None
-    if rank == 0:
-        all_lanes = torch.empty((world, k, fl), dtype=torch.float32, device=dev)
-        all_lanes[0].copy_(d_lanes)
-        for r in range(1, world):
-            all_lanes[r].copy_(torch.from_numpy(wl.host_lanes(r * k, k)).pin_memory(), non_blocking=True)
-        torch.cuda.synchronize(dev)
     free_ev = [torch.cuda.Event() for _ in range(2)]   # compute has finished reading bufs[i]
     ready_ev = [torch.cuda.Event() for _ in range(2)]  # bufs[i] holds a complete block
 
-    def issue(i):
-        with torch.cuda.stream(comm):
-            comm.wait_event(free_ev[i])
-            if rank == 0:
-                ops = [dist.P2POp(dist.isend, all_lanes[r], r) for r in range(1, world)]
-                bufs[i].copy_(all_lanes[0], non_blocking=True)  # rank 0's own share: a device-local copy
-            else:
-                ops = [dist.P2POp(dist.irecv, bufs[i], 0)]
-            for q in dist.batch_isend_irecv(ops):
-                q.wait()   # stream-level wait: orders `comm` after the transfer, does not block the host
-            ready_ev[i].record(comm)
+    # ---- rank 0: the whole job's PCM in an IPC-exportable allocation; everyone else maps it
+    handle = (C.c_uint8 * 64)()
+    base = C.c_void_p()
+    if rank == 0:
+        assert api.peer_alloc(world * blk, C.byref(base), handle) == 0, api.last_error()
+        assert api.copy_async(base.value, d_lanes.data_ptr(), blk, None) == 0
+        for r in range(1, world):
+            pin = torch.from_numpy(wl.host_lanes(r * k, k)).pin_memory()
+            assert api.copy_async(base.value + r * blk, pin.data_ptr(), blk, None) == 0
+            torch.cuda.synchronize(dev)
+    ht = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    dist.broadcast(ht, 0)
+    if rank != 0:
+        handle = (C.c_uint8 * 64)(*ht.cpu().tolist())
+        assert api.peer_open(handle, C.byref(base)) == 0, api.last_error()
+    torch.cuda.synchronize(dev)
+    my_src = base.value + rank * blk
 
-    def run(steps, compute):
+    def timed(steps, prefetch, source, compute=True):
+        """prefetch(i) queues the arrival of the next block into bufs[i] on `comm` (or is None); source(i) is the input pointer."""
         for e in free_ev:
             e.record(stream)
-        issue(0)
+        if prefetch:
+            prefetch(0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
         for s in range(steps):
             i = s & 1
-            issue(i ^ 1)                      # next step's block travels while this step computes
-            stream.wait_event(ready_ev[i])
+            if prefetch:
+                prefetch(i ^ 1)                   # next step's block travels while this step computes
+                stream.wait_event(ready_ev[i])
             if compute:
-                wl.step(bufs[i].data_ptr(), stream.cuda_stream)
+                wl.step(source(i), stream.cuda_stream)
             free_ev[i].record(stream)
-        stream.wait_event(ready_ev[steps & 1])  # the transfer issued by the last step is inside the timed region too
+        if prefetch:
+            stream.wait_event(ready_ev[steps & 1])  # the transfer issued by the last step is inside the timed region too
         e1.record(stream)
         barrier()
         return allmax(e0.elapsed_time(e1)) / steps
 
-    run(args.warmup, True)
-    ms_inc = run(args.steps, True)
-    chk = torch.tensor([wl.checksum(torch)], dtype=torch.int64, device=dev)
-    dist.all_reduce(chk, op=dist.ReduceOp.SUM)
-    ms_alone = run(args.steps, False)
-    bytes_out = (world - 1) * k * fl * 4
-    out = {"scatter_inclusive": {"value": units_job / (ms_inc / 1000.0), "unit": wl.unit, "ms_per_step": ms_inc,
-                                 "checksum_equals_resident": int(chk.item()) == checksum_resident,
-                                 "scatter_alone_ms": ms_alone, "rank0_egress_bytes_per_step": bytes_out,
-                                 "rank0_egress_gbs": bytes_out / (ms_alone / 1000.0) / 1e9,
-                                 "how": "rank 0 -> owners, grouped ncclSend/ncclRecv per step on a side stream, double-buffered against the kernels"}}
-    return out
+    def check():
+        chk = torch.tensor([wl.checksum(torch)], dtype=torch.int64, device=dev)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        return int(chk.item()) == checksum_resident
+
+    bytes_out = (world - 1) * blk
+    modes = {}
+
+    # ---- nccl
+    all_lanes = None
+    if rank == 0:
+        all_lanes = torch.empty((world, k, fl), dtype=torch.float32, device=dev)
+        assert api.copy_async(all_lanes.data_ptr(), base.value, world * blk, None) == 0
+        torch.cuda.synchronize(dev)
+
+    def nccl_prefetch(i):
+        with torch.cuda.stream(comm):
+            comm.wait_event(free_ev[i])
+            if rank == 0:
+                ops = [dist.P2POp(dist.isend, all_lanes[r], r) for r in range(1, world)]
+            else:
+                ops = [dist.P2POp(dist.irecv, bufs[i], 0)]
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()   # stream-level: orders `comm` after the transfer, does not block the host
+            ready_ev[i].record(comm)
+
+    src_buf = lambda i: (d_lanes.data_ptr() if rank == 0 else bufs[i].data_ptr())  # rank 0's own block is resident by definition
+    timed(args.warmup, nccl_prefetch, src_buf)
+    ms = timed(args.steps, nccl_prefetch, src_buf)
+    ok = check()
+    alone = timed(args.steps, nccl_prefetch, src_buf, compute=False)
+    modes["nccl"] = {"value": units_job / (ms / 1000.0), "ms_per_step": ms, "checksum_equals_resident": ok, "transfer_alone_ms": alone,
+                     "rank0_egress_gbs": bytes_out / (alone / 1000.0) / 1e9}
+    del all_lanes
+    torch.cuda.empty_cache()
+
+    # ---- peer_dma: pull with the copy engines
+    def dma_prefetch(i):
+        comm.wait_event(free_ev[i])
+        if rank != 0:
+            assert api.copy_async(bufs[i].data_ptr(), my_src, blk, comm.cuda_stream) == 0, api.last_error()
+        ready_ev[i].record(comm)
+
+    for b in bufs:
+        b.zero_()
+    timed(args.warmup, dma_prefetch, src_buf)
+    ms = timed(args.steps, dma_prefetch, src_buf)
+    ok = check()
+    alone = timed(args.steps, dma_prefetch, src_buf, compute=False)
+    modes["peer_dma"] = {"value": units_job / (ms / 1000.0), "ms_per_step": ms, "checksum_equals_resident": ok, "transfer_alone_ms": alone,
+                         "rank0_egress_gbs": bytes_out / (alone / 1000.0) / 1e9}
+
+    # ---- peer_direct: the kernel's own staging copies read rank 0's HBM
+    direct = lambda i: my_src
+    timed(args.warmup, None, direct)
+    ms = timed(args.steps, None, direct)
+    ok = check()
+    modes["peer_direct"] = {"value": units_job / (ms / 1000.0), "ms_per_step": ms, "checksum_equals_resident": ok,
+                            "rank0_egress_gbs": bytes_out / (ms / 1000.0) / 1e9}
+
+    barrier()
+    if rank != 0:
+        api.peer_close(base)
+    barrier()
+    if rank == 0:
+        api.peer_free(base)
+    best = max(modes, key=lambda m: modes[m]["value"])
+    return {"scatter_inclusive": {"value": modes[best]["value"], "unit": wl.unit, "mode": best, "ms_per_step": modes[best]["ms_per_step"],
+                                  "checksum_equals_resident": all(m["checksum_equals_resident"] for m in modes.values()),
+                                  "rank0_egress_bytes_per_step": bytes_out, "modes": modes,
+                                  "how": "PCM of the whole job rank-major in rank 0's HBM; nccl = grouped send/recv per step on a side stream; "
+                                         "peer_dma = CUDA-IPC mapped buffer pulled by each rank's copy engine, double-buffered; "
+                                         "peer_direct = the kernels' TMA / async staging copies read the mapped buffer over NVLink (no scatter step)"}}
 
 
 def run_e2e(args, wl, api, torch, dev, pin_in, k, units_job, allmax, barrier):

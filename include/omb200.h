@@ -105,6 +105,27 @@ uint64_t omb_kernel_launch_count(void);
 int omb_probe_fp32_tflops(double* out_tflops);
 
 /* ------------------------------------------------------------------------ */
+/* Multi-GPU ingest over peer memory (no reference equivalent: */
+/* the reference is one process on one machine).  One process per GPU: the    */
+/* ingest rank allocates the job's PCM with omb_peer_alloc and hands the       */
+/* 64-byte handle to the other ranks (any transport: torch.distributed, a      */
+/* pipe); they map it with omb_peer_open and either pull their lanes with      */
+/* their own copy engines (omb_copy_async, no SMs involved, overlaps kernels)  */
+/* or pass the mapped pointer straight to omb_*_execute_device — the kernels'  */
+/* staging copies (bulk / 16-byte async) then read the ingest rank's HBM over  */
+/* NVLink while they compute: no separate scatter step exists.                 */
+/* ------------------------------------------------------------------------ */
+#define OMB_PEER_HANDLE_BYTES 64
+/* cudaMalloc + cudaIpcGetMemHandle on the current device. */
+int omb_peer_alloc(size_t bytes, void** d_ptr, uint8_t handle[OMB_PEER_HANDLE_BYTES]);
+/* cudaIpcOpenMemHandle in ANOTHER process (peer access is enabled lazily); the pointer is valid on the current device. */
+int omb_peer_open(const uint8_t handle[OMB_PEER_HANDLE_BYTES], void** d_ptr);
+int omb_peer_close(void* d_ptr);   /* importer side */
+int omb_peer_free(void* d_ptr);    /* exporter side, after every importer has closed */
+/* cudaMemcpyAsync(cudaMemcpyDefault): device, peer-mapped or pinned host pointers; stream may be NULL. */
+int omb_copy_async(void* dst, const void* src, size_t bytes, void* cuda_stream);
+
+/* ------------------------------------------------------------------------ */
 /* Plan set-up pieces (rows a2,a3,a5,a14,a15 of SURVEY.md §8) — host-side,    */
 /* exported so the parity tests can pin them against the oracle.              */
 /* ------------------------------------------------------------------------ */

@@ -183,6 +183,11 @@ HEADER_SYMBOLS = {
     "set_device": (C.c_int, [C.c_int]),
     "kernel_launch_count": (_u64, []),
     "probe_fp32_tflops": (C.c_int, [_f64p]),
+    "peer_alloc": (C.c_int, [_sz, C.POINTER(_vp), _u8p]),
+    "peer_open": (C.c_int, [_u8p, C.POINTER(_vp)]),
+    "peer_close": (C.c_int, [_vp]),
+    "peer_free": (C.c_int, [_vp]),
+    "copy_async": (C.c_int, [_vp, _vp, _sz, _vp]),
     "window_coefficients": (C.c_int, [C.c_int, _sz, _f32p]),
     "fft_bin_normalization": (C.c_int, [_f32p, _sz, _sz, _f32p]),
     "reassignment_windows": (C.c_int, [_f32p, _sz, _f32p, _f32p]),

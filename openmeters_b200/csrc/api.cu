@@ -44,6 +44,64 @@ int omb_probe_fp32_tflops(double* out_tflops) {
   OMB_GUARD_END
 }
 
+// ---- multi-GPU ingest over peer memory (one process per GPU): CUDA IPC export / import of a device buffer
+int omb_peer_alloc(size_t bytes, void** d_ptr, uint8_t handle[OMB_PEER_HANDLE_BYTES]) {
+  OMB_GUARD_BEGIN
+  if (!d_ptr || !handle || !bytes) return fail(OMB_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == OMB_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+  DeviceInfo dev;
+  OMB_TRY(current_device(&dev));
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(OMB_ERR_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
+  }
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    cudaGetLastError();
+    return fail(OMB_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  std::memcpy(handle, &h, sizeof(h));
+  *d_ptr = p;
+  return OMB_OK;
+  OMB_GUARD_END
+}
+int omb_peer_open(const uint8_t handle[OMB_PEER_HANDLE_BYTES], void** d_ptr) {
+  OMB_GUARD_BEGIN
+  if (!d_ptr || !handle) return fail(OMB_ERR_INVALID, "null argument");
+  DeviceInfo dev;
+  OMB_TRY(current_device(&dev));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(OMB_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  }
+  *d_ptr = p;
+  return OMB_OK;
+  OMB_GUARD_END
+}
+int omb_peer_close(void* d_ptr) {
+  if (!d_ptr) return OMB_OK;
+  OMB_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+  return OMB_OK;
+}
+int omb_peer_free(void* d_ptr) {
+  if (!d_ptr) return OMB_OK;
+  OMB_CUDA_TRY(cudaFree(d_ptr));
+  return OMB_OK;
+}
+int omb_copy_async(void* dst, const void* src, size_t bytes, void* cuda_stream) {
+  if (!bytes) return OMB_OK;
+  if (!dst || !src) return fail(OMB_ERR_INVALID, "null argument");
+  OMB_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(cuda_stream)));
+  return OMB_OK;
+}
+
 // ---- plan set-up pieces
 int omb_window_coefficients(int kind, size_t len, float* out) {
   OMB_GUARD_BEGIN

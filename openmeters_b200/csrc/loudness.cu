@@ -2,10 +2,15 @@
 //
 // Two implementations of the same arithmetic:
 //
-//  * k_loudness_stream — the streaming LoudnessProcessor::process_block: one thread per channel walks
-//    the block sample by sample with the reference's exact operation order (TDF-II in f64, Neumaier
-//    compensated window sums with periodic re-base, polyphase true-peak FIR in tap order).  A block is
-//    256-1024 frames (meter.rs:15-18), so the serial walk is microseconds; channels run in parallel.
+//  * k_loudness_stream_seq — the streaming LoudnessProcessor::process_block as the reference writes it: one thread per
+//    channel walks the block sample by sample (TDF-II in f64, Neumaier compensated window sums with periodic re-base,
+//    polyphase true-peak FIR in tap order).  Every step carries three dependent chains and four global-memory loads of
+//    ring values, ~0.9 us per frame: 8.5 ms for a 9600-frame block.  Kept as the on-GPU cross-check (OMB_LOUDNESS_STREAM_SEQ=1).
+//  * k_loudness_stream — the same arithmetic, operation for operation, with the three chains separated so that each runs at
+//    its own dependency depth and the independent work runs in parallel: warp 0 the IIR (lane = channel), 6 warps the true
+//    peak (a pure function of 12 / 24 consecutive input samples: parallel over samples, max-reduced), then warp 1 the four
+//    window sums of every channel (lane = channel x window, ring loads independent of the chain), then all threads append
+//    the block to the ring.  Bit-identical snapshots and state (max is order-free; every sum keeps its order).
 //
 //  * the batched plan — offline throughput path for long multi-channel streams (BASELINE cfg3).  The IIR
 //    is linear, so time is cut into 256-sample chunks: (1) zero-state end state per chunk, (2) a short
@@ -71,7 +76,7 @@ __device__ __forceinline__ float power_to_db_f(float p, float floor_db) {
 }
 
 // One CTA per stream (blockIdx.x; a single stream for omb_loudness, S lock-step streams for omb_loudness_bank).
-__global__ void __launch_bounds__(32) k_loudness_stream(LoudStreamArgs a) {
+__global__ void __launch_bounds__(32) k_loudness_stream_seq(LoudStreamArgs a) {
   const uint32_t c = threadIdx.x;
   // re-base the per-stream pointers; everything below is the single-stream code
   a.block += (uint64_t)blockIdx.x * a.block_stride;
@@ -182,6 +187,207 @@ __global__ void __launch_bounds__(32) k_loudness_stream(LoudStreamArgs a) {
     snap.channel_count = a.channels;
     *a.out = snap;
   }
+}
+
+
+// ---------------------------------------------------------------------------------- phase-parallel streaming kernel
+constexpr int kStreamThreads = 256;   // warp 0: IIR, warp 1: window sums, warps 2-7: true peak
+
+__device__ __forceinline__ void loud_snapshot(const LoudStreamArgs& a) {  // loudness/processor.rs:287-310 (thread 0)
+  omb_loudness_snapshot snap;
+  const float floor_db = a.floor_db;
+  for (int i = 0; i < OMB_MAX_CHANNELS; ++i) {
+    snap.rms_fast_db[i] = snap.rms_slow_db[i] = snap.true_peak_db[i] = floor_db;
+    snap.positions[i] = a.positions[i];
+  }
+  double wst = 0.0, wm = 0.0;
+  for (uint32_t ch = 0; ch < a.channels; ++ch) {
+    LoudChannelState& st = a.state[ch];
+    if (!st.active) continue;
+    double mean[kLoudWindows];
+    for (int w = 0; w < kLoudWindows; ++w) {
+      uint64_t n = st.count < a.caps[w] ? st.count : a.caps[w];
+      if (n < 1) n = 1;
+      mean[w] = (st.sums[w][0] + st.corr[w][0]) / (double)n;
+    }
+    wst = __dadd_rn(wst, __dmul_rn(mean[0], a.weights[ch]));
+    wm = __dadd_rn(wm, __dmul_rn(mean[1], a.weights[ch]));
+    snap.rms_fast_db[ch] = power_to_db_f((float)mean[2], floor_db);
+    snap.rms_slow_db[ch] = power_to_db_f((float)mean[3], floor_db);
+    const float peak = st.peak;
+    st.peak = 0.0f;
+    snap.true_peak_db[ch] = power_to_db_f(__fmul_rn(peak, peak), floor_db);
+  }
+  snap.short_term_loudness = lufs_dev(wst, floor_db);
+  snap.momentary_loudness = lufs_dev(wm, floor_db);
+  snap.channel_count = a.channels;
+  *a.out = snap;
+}
+
+__global__ void __launch_bounds__(kStreamThreads) k_loudness_stream(LoudStreamArgs a) {
+  __shared__ unsigned long long s_start[OMB_MAX_CHANNELS];   // first frame of the block at which the channel is active
+  __shared__ unsigned long long s_head0[OMB_MAX_CHANNELS], s_count0[OMB_MAX_CHANNELS];
+  __shared__ unsigned s_peak[OMB_MAX_CHANNELS];               // bits of the block's peak (non-negative floats order as integers)
+  __shared__ float s_hist[OMB_MAX_CHANNELS][24];              // [j]: the sample pushed j + 1 steps before the block's first active one
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  a.block += (uint64_t)blockIdx.x * a.block_stride;
+  a.state += (uint64_t)blockIdx.x * a.channels;
+  a.ring += (uint64_t)blockIdx.x * a.channels * a.ring_len;
+  a.vnew += (uint64_t)blockIdx.x * a.channels * a.frames;
+  a.out += blockIdx.x;
+  const uint32_t C = a.channels, dl = a.tp_delay_len;
+  const uint64_t frames = a.frames;
+
+  // ---- phase 0: lazy activation (loudness/processor.rs:264-274) and the constants of this block
+  if (tid < C) {
+    LoudChannelState& st = a.state[tid];
+    uint64_t start = 0;
+    if (!st.active) {
+      uint64_t f = 0;
+      while (f < frames && __float_as_uint(a.block[f * C + tid]) == 0u) ++f;
+      st.silent_frames += f;
+      start = f;
+      if (f < frames) {
+        st.active = 1;
+        st.head = st.silent_frames % a.ring_len;  // WindowedMeans::with_leading_zeros, dsp.rs:359-365
+        st.count = st.silent_frames < a.ring_len ? st.silent_frames : a.ring_len;
+        for (int w = 0; w < kLoudWindows; ++w) {
+          st.refresh[w] = st.silent_frames % a.caps[w];
+          st.sums[w][0] = st.sums[w][1] = st.corr[w][0] = st.corr[w][1] = 0.0;
+        }
+        for (int i = 0; i < 4; ++i) st.filter[i] = 0.0;
+        for (int i = 0; i < 48; ++i) st.delay[i] = 0.0f;
+        st.write = dl;
+        st.peak = 0.0f;
+      }
+    }
+    s_start[tid] = start;
+    s_head0[tid] = st.head;
+    s_count0[tid] = st.count;
+    s_peak[tid] = 0u;
+    for (uint32_t j = 0; j < dl; ++j) s_hist[tid][j] = st.delay[st.write + j];  // delay[write + i] = the sample pushed i steps ago
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---- phase A: K-weighting, sequential per channel (loudness/processor.rs:153-162), y^2 to the scratch
+    if (lane < C && s_start[lane] < frames) {
+      LoudChannelState& st = a.state[lane];
+      double f[4] = {st.filter[0], st.filter[1], st.filter[2], st.filter[3]};
+      double* vn = a.vnew + (uint64_t)lane * frames;
+      const uint64_t start = s_start[lane];
+      for (uint64_t k = start; k < frames; ++k) {
+        const float yf = (float)kw_step((double)a.block[k * C + lane], f, a.kw);
+        double v = __dmul_rn((double)yf, (double)yf);
+        if (!isfinite(v)) v = 0.0;  // dsp.rs:324-333
+        vn[k - start] = v;
+      }
+      for (int i = 0; i < 4; ++i) st.filter[i] = fabs(f[i]) < 1.0e-30 ? 0.0 : f[i];  // level.rs:14-18
+    }
+  } else if (warp >= 2) {
+    // ---- phase T: TruePeakMeter::process (loudness/processor.rs:123-150) for every (frame, channel) independently;
+    //      each FIR sum in tap order (newest sample first), the block maximum by atomicMax on the bit pattern
+    const uint32_t nt = kStreamThreads - 64;
+    for (uint64_t idx = tid - 64; idx < frames * C; idx += nt) {
+      const uint64_t k = idx / C;
+      const uint32_t c = (uint32_t)(idx - k * C);
+      const uint64_t start = s_start[c];
+      if (k < start) continue;
+      const float s = a.block[k * C + c];
+      float m = fabsf(s);
+      m = m == m ? m : 0.0f;  // f32::max ignores NaN
+      const uint64_t kk = k - start;
+      auto tap = [&](uint32_t i) -> float {  // the sample pushed i steps before sample k
+        return (uint64_t)i <= kk ? a.block[(k - i) * C + c] : s_hist[c][i - kk - 1];
+      };
+      if (dl == 12) {
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+#pragma unroll
+        for (uint32_t i = 0; i < 12; ++i) {
+          const float d = tap(i);
+          o0 = __fadd_rn(o0, __fmul_rn(d, a.fir.fir4[i][0]));
+          o1 = __fadd_rn(o1, __fmul_rn(d, a.fir.fir4[i][1]));
+          o2 = __fadd_rn(o2, __fmul_rn(d, a.fir.fir4[i][2]));
+        }
+        m = fmaxf(fmaxf(fmaxf(m, fabsf(o0)), fabsf(o1)), fabsf(o2));
+      } else if (dl == 24) {
+        float o = 0.0f;
+#pragma unroll
+        for (uint32_t i = 0; i < 24; ++i) o = __fadd_rn(o, __fmul_rn(tap(i), a.fir.fir2[i]));
+        m = fmaxf(m, fabsf(o));
+      }
+      atomicMax(&s_peak[c], __float_as_uint(m));
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: WindowedMeans::push (dsp.rs:334-357) for lane = (channel, window); the old value of step k is the sample
+  //      pushed `cap` steps earlier: this block's own y^2 if k >= cap, else still in the ring
+  if (warp == 1 && lane < C * kLoudWindows) {
+    const uint32_t c = lane / kLoudWindows, w = lane % kLoudWindows;
+    const uint64_t start = s_start[c], n = frames - start;
+    if (n > 0) {
+      LoudChannelState& st = a.state[c];
+      const uint64_t cap = a.caps[w], L = a.ring_len, count0 = s_count0[c];
+      const double* vn = a.vnew + (uint64_t)c * frames;
+      const double* ring = a.ring + (uint64_t)c * L;
+      double s0 = st.sums[w][0], s1 = st.sums[w][1], c0 = st.corr[w][0], c1 = st.corr[w][1];
+      uint64_t refresh = st.refresh[w];
+      uint64_t ri = (s_head0[c] + L - cap) % L;
+      for (uint64_t k = 0; k < n; ++k) {
+        const double v = vn[k];
+        const bool has_old = count0 + k >= cap;
+        const double old = has_old ? (k >= cap ? vn[k - cap] : ring[ri]) : 0.0;
+        ri = ri + 1 == L ? 0 : ri + 1;
+        neumaier_add(s0, c0, v);
+        neumaier_add(s1, c1, v);
+        if (has_old) neumaier_add(s0, c0, -old);
+        if (++refresh == cap) {  // CompensatedPair::refresh
+          s0 = s1;
+          s1 = 0.0;
+          c0 = c1;
+          c1 = 0.0;
+          refresh = 0;
+        }
+      }
+      st.sums[w][0] = s0;
+      st.sums[w][1] = s1;
+      st.corr[w][0] = c0;
+      st.corr[w][1] = c1;
+      st.refresh[w] = refresh;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C: append the block to the ring (only the last ring_len values of a longer block survive), cursors, delay line
+  for (uint32_t c = 0; c < C; ++c) {
+    const uint64_t start = s_start[c], n = frames - start, L = a.ring_len;
+    const double* vn = a.vnew + (uint64_t)c * frames;
+    double* ring = a.ring + (uint64_t)c * L;
+    for (uint64_t k = (n > L ? n - L : 0) + tid; k < n; k += kStreamThreads) ring[(s_head0[c] + k) % L] = vn[k];
+  }
+  if (tid < C && s_start[tid] < frames) {
+    LoudChannelState& st = a.state[tid];
+    const uint64_t start = s_start[tid], n = frames - start, L = a.ring_len;
+    st.head = (s_head0[tid] + n) % L;
+    st.count = s_count0[tid] + n < L ? s_count0[tid] + n : L;
+    st.peak = fmaxf(st.peak, __uint_as_float(s_peak[tid]));
+    if (dl) {
+      // after n decrements-with-wrap the write cursor sits at (write0 - n) mod dl; delay[write + i] (and its copy dl further)
+      // holds the sample pushed i steps ago
+      const uint32_t w0 = st.write % dl;
+      const uint32_t wn = (uint32_t)((w0 + dl - (n % dl)) % dl);
+      for (uint32_t i = 0; i < dl; ++i) {
+        const float val = (uint64_t)i < n ? a.block[(frames - 1 - i) * C + tid] : s_hist[tid][i - n];
+        const uint32_t p = (wn + i) % dl;
+        st.delay[p] = val;
+        st.delay[p + dl] = val;
+      }
+      st.write = wn;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) loud_snapshot(a);
 }
 
 // ---------------------------------------------------------------------------------- batched
@@ -624,7 +830,13 @@ void mat4_mul(const long double* A, const long double* B, long double* C) {
 
 int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s, uint32_t n_streams) {
   if (!n_streams) return OMB_OK;
-  OMB_LAUNCH(k_loudness_stream, dim3(n_streams), dim3(32), 0, s, a);
+  const char* e = getenv("OMB_LOUDNESS_STREAM_SEQ");  // read per launch: the cross-check tests flip it inside one process
+  const bool seq = e && e[0] == '1';
+  if (seq) {
+    OMB_LAUNCH(k_loudness_stream_seq, dim3(n_streams), dim3(32), 0, s, a);
+  } else {
+    OMB_LAUNCH(k_loudness_stream, dim3(n_streams), dim3(kStreamThreads), 0, s, a);
+  }
   OMB_CHECK_LAUNCH();
   return OMB_OK;
 }

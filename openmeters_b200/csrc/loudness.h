@@ -43,6 +43,7 @@ struct LoudStreamArgs {
   double weights[OMB_MAX_CHANNELS];      // channel_weight(position)
   uint8_t positions[OMB_MAX_CHANNELS];
   omb_loudness_snapshot* out;            // [stream]
+  double* vnew;                          // [stream][channels][frames] scratch: this block's squared K-weighted samples
 };
 
 struct LoudnessStreamCore {              // device objects behind omb_loudness (stream_loudness.cu)
@@ -50,6 +51,7 @@ struct LoudnessStreamCore {              // device objects behind omb_loudness (
   DeviceBuffer<double> d_ring;
   DeviceBuffer<float> d_block;
   DeviceBuffer<omb_loudness_snapshot> d_snap;
+  DeviceBuffer<double> d_vnew;           // scratch of the phase-parallel streaming kernel
 };
 int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s, uint32_t n_streams = 1);
 

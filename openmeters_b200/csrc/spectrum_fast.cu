@@ -225,7 +225,7 @@ __device__ __forceinline__ void f_async_copy8(float2* dst_smem, const float* src
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src_gmem));
 #endif
 }
-// Planar ring (experimental, OMB_SPECTRUM_PLANAR=1): the even and odd float2 of every 16-byte quad live in two planes of
+// Planar ring (default since round 2; OMB_SPECTRUM_PLANAR=0 turns it off): the even and odd float2 of every 16-byte quad live in two planes of
 // L / 4 float2 each, so that the group that transforms z[2m + g] reads plane g at unit stride (the interleaved ring is read
 // at a 16-byte stride: a 2-way bank conflict on every 64-bit load, 22 % of the kernel's shared-memory wavefronts).
 __device__ __forceinline__ void f_ring_fetch_planar(float2* plane_e, float2* plane_o, int L, int p0, const float* x, int count) {
@@ -568,9 +568,10 @@ int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lane
   fa.ring_len = (uint32_t)(kN + cfg.hop);
   const unsigned grid = (unsigned)std::min<uint64_t>(n_lanes, (uint64_t)std::max(p.dev.sm_count, 1));
   const size_t fs = fused_smem_bytes(cfg.hop);
-  // OMB_SPECTRUM_PLANAR=1: experimental planar ring (conflict-free frame loads; not yet measured on hardware, off by default)
+  // Planar ring (conflict-free frame loads): measured on B200 in round 2, 2.307e7 -> 2.481e7 lane-hops/s (+7.5 %, cfg4, 128 lanes;
+  // profiles/r02a_cfg4_planar.json), the spectrum GPU tests pass with it: default.  OMB_SPECTRUM_PLANAR=0 restores the interleaved ring.
   const char* planar_env = getenv("OMB_SPECTRUM_PLANAR");
-  const bool planar = planar_env && planar_env[0] == '1' && (cfg.hop % 4) == 0;
+  const bool planar = !(planar_env && planar_env[0] == '0') && (cfg.hop % 4) == 0;
   if (planar) {
     auto kp = k_spectrum_fused_16k<OMB_AVG_PEAK_HOLD, true>;
     auto ke = k_spectrum_fused_16k<OMB_AVG_EXPONENTIAL, true>;

@@ -106,6 +106,8 @@ int LoudnessStream::process_bank(const float* samples, uint64_t stream_stride, s
     a.weights[i] = channel_weight_host(positions[i]);
   }
   a.out = core.d_snap.ptr;
+  OMB_TRY(core.d_vnew.reserve(per * n_streams));
+  a.vnew = core.d_vnew.ptr;
   OMB_TRY(launch_loudness_stream(a, stream, n_streams));
   OMB_CUDA_TRY(cudaMemcpyAsync(out, core.d_snap.ptr, sizeof(omb_loudness_snapshot) * n_streams, cudaMemcpyDeviceToHost, stream));
   OMB_CUDA_TRY(cudaStreamSynchronize(stream));

@@ -47,7 +47,8 @@ EXTRA = {
 
 # header symbols the oracle also implements (same signatures, ombo_ prefix)
 _SHARED = [k for k in capi.HEADER_SYMBOLS if not (
-    k in ("last_error", "device_count", "set_device", "kernel_launch_count", "probe_fp32_tflops") or k.startswith("stft_plan")
+    k in ("last_error", "device_count", "set_device", "kernel_launch_count", "probe_fp32_tflops", "copy_async") or k.startswith("peer_")
+    or k.startswith("stft_plan")
     or k.startswith("stft_execute") or k.startswith("stft_render") or k.startswith("spectrum_plan") or k.startswith("spectrum_execute")
     or k.startswith("loudness_plan") or k.startswith("loudness_execute")
     or k in ("spectrum_default_peak_spec", "spectrum_interpolate_peaks_device")

@@ -214,3 +214,49 @@ def test_spectrum_bank_gpu(product, oracle):
                          secondary_source=capi.CHANNEL_RIGHT, floor_db=-100.0)
     n = run_spectrum_bank_vs_processors(product.api, oracle, cfg, S=8, seconds=0.8, channels=2, block_choices=(512, 1024, 2048), seed=8)
     assert n >= 10
+
+
+# ------------------------------------------------------------------ streaming loudness: phase-parallel kernel vs the sequential port
+def _loudness_stream_sequences_equal(api, monkeypatch, sr, channels, sizes, seed):
+    """k_loudness_stream (IIR / true peak / window sums as separate phases) must give the SAME BYTES as k_loudness_stream_seq
+    (the reference's per-sample loop, OMB_LOUDNESS_STREAM_SEQ=1) snapshot after snapshot: ragged blocks, a channel that
+    starts silent and wakes up mid-block, blocks longer than the shortest windows, non-finite samples."""
+    import ctypes as C
+
+    from openmeters_b200.processors import AudioBlock, LoudnessConfig, LoudnessProcessor
+
+    rng = np.random.default_rng(seed)
+    total = sum(sizes)
+    x = (0.4 * np.sin(np.arange(total)[:, None] * (0.01 + 0.003 * np.arange(channels))[None, :]) +
+         0.05 * rng.uniform(-1, 1, (total, channels))).astype(np.float32)
+    if channels > 1:
+        x[: sizes[0] + sizes[1] // 2, 1] = 0.0          # channel 1 wakes up in the middle of the second block
+    x[total // 2, 0] = np.float32(np.inf)               # y^2 non-finite -> pushed as 0 (dsp.rs:324-333); |s| = inf is a legal peak
+    x[total // 2 + 3, channels - 1] = np.float32(np.nan)
+    snaps = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("OMB_LOUDNESS_STREAM_SEQ", mode)
+        p = LoudnessProcessor(LoudnessConfig(sample_rate=sr), api=api)
+        out, pos = [], 0
+        for n in sizes:
+            s = p.process_block(AudioBlock(x[pos:pos + n].reshape(-1), channels, sr))
+            pos += n
+            out.append((np.float32(s.short_term_loudness), np.float32(s.momentary_loudness), np.array(s.rms_fast_db, np.float32),
+                        np.array(s.rms_slow_db, np.float32), np.array(s.true_peak_db, np.float32)))
+        snaps[mode] = out
+    for a, b in zip(snaps["0"], snaps["1"]):
+        for u, v in zip(a, b):
+            assert np.array_equal(np.asarray(u).view(np.uint32), np.asarray(v).view(np.uint32)), (u, v)
+
+
+@pytest.mark.parametrize("sr,channels,sizes", [(8000.0, 2, [5, 700, 1, 3000, 64, 2500]), (48000.0, 3, [256, 999, 17, 1024]),
+                                               (96000.0, 1, [300, 40, 1000]), (192000.0, 2, [100, 333])])
+def test_loudness_stream_kernels_agree_emulated(emu, monkeypatch, sr, channels, sizes):
+    _loudness_stream_sequences_equal(emu.api, monkeypatch, sr, channels, sizes, 11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sr,channels,sizes", [(8000.0, 2, [5, 700, 1, 30000, 64, 2500]), (48000.0, 8, [256, 9600, 17, 1024, 200000, 3]),
+                                               (44100.0, 6, [1024] * 12), (96000.0, 2, [300, 40, 100000]), (192000.0, 2, [100, 33333])])
+def test_loudness_stream_kernels_agree_gpu(product, monkeypatch, sr, channels, sizes):
+    _loudness_stream_sequences_equal(product.api, monkeypatch, sr, channels, sizes, 12)
