@@ -276,11 +276,22 @@ __global__ void __launch_bounds__(kStreamThreads) k_loudness_stream(LoudStreamAr
       double f[4] = {st.filter[0], st.filter[1], st.filter[2], st.filter[3]};
       double* vn = a.vnew + (uint64_t)lane * frames;
       const uint64_t start = s_start[lane];
-      for (uint64_t k = start; k < frames; ++k) {
-        const float yf = (float)kw_step((double)a.block[k * C + lane], f, a.kw);
-        double v = __dmul_rn((double)yf, (double)yf);
-        if (!isfinite(v)) v = 0.0;  // dsp.rs:324-333
-        vn[k - start] = v;
+      // inputs are fetched kPre at a time ahead of the recurrence: a global load inside the dependent chain would expose its
+      // full latency on every step (measured: 0.5 ms per 1024-frame block before, see profiles/r02_notes.md)
+      constexpr int kPre = 8;
+      for (uint64_t k0 = start; k0 < frames; k0 += kPre) {
+        float xin[kPre];
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) xin[u] = k0 + u < frames ? a.block[(k0 + u) * C + lane] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+          if (k0 + u < frames) {
+            const float yf = (float)kw_step((double)xin[u], f, a.kw);
+            double v = __dmul_rn((double)yf, (double)yf);
+            if (!isfinite(v)) v = 0.0;  // dsp.rs:324-333
+            vn[k0 + u - start] = v;
+          }
+        }
       }
       for (int i = 0; i < 4; ++i) st.filter[i] = fabs(f[i]) < 1.0e-30 ? 0.0 : f[i];  // level.rs:14-18
     }
@@ -334,21 +345,35 @@ __global__ void __launch_bounds__(kStreamThreads) k_loudness_stream(LoudStreamAr
       double s0 = st.sums[w][0], s1 = st.sums[w][1], c0 = st.corr[w][0], c1 = st.corr[w][1];
       uint64_t refresh = st.refresh[w];
       uint64_t ri = (s_head0[c] + L - cap) % L;
-      for (uint64_t k = 0; k < n; ++k) {
-        const double v = vn[k];
-        const bool has_old = count0 + k >= cap;
-        const double old = has_old ? (k >= cap ? vn[k - cap] : ring[ri]) : 0.0;
-        ri = ri + 1 == L ? 0 : ri + 1;
-        neumaier_add(s0, c0, v);
-        neumaier_add(s1, c1, v);
-        if (has_old) neumaier_add(s0, c0, -old);
-        if (++refresh == cap) {  // CompensatedPair::refresh
-          s0 = s1;
-          s1 = 0.0;
-          c0 = c1;
-          c1 = 0.0;
-          refresh = 0;
+      constexpr int kPre = 8;  // new and old values are fetched kPre steps ahead of the compensated-sum chain (see phase A)
+      for (uint64_t k0 = 0; k0 < n; k0 += kPre) {
+        double vin[kPre], oin[kPre];
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+          const uint64_t k = k0 + u;
+          vin[u] = k < n ? vn[k] : 0.0;
+          uint64_t r = ri + u;
+          while (r >= L) r -= L;  // L can be shorter than kPre at toy sample rates
+          oin[u] = (k < n && count0 + k >= cap) ? (k >= cap ? vn[k - cap] : ring[r]) : 0.0;
         }
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+          const uint64_t k = k0 + u;
+          if (k < n) {
+            neumaier_add(s0, c0, vin[u]);
+            neumaier_add(s1, c1, vin[u]);
+            if (count0 + k >= cap) neumaier_add(s0, c0, -oin[u]);
+            if (++refresh == cap) {  // CompensatedPair::refresh
+              s0 = s1;
+              s1 = 0.0;
+              c0 = c1;
+              c1 = 0.0;
+              refresh = 0;
+            }
+          }
+        }
+        ri += kPre;
+        while (ri >= L) ri -= L;
       }
       st.sums[w][0] = s0;
       st.sums[w][1] = s1;

@@ -17,8 +17,8 @@
 //
 // One CTA = one SM walks a run of consecutive frames of one lane; the H = 16384 samples of a frame live in a
 // shared-memory ring of H + hop floats, and the next hop is fetched by 16-byte async copies into the one slot the
-// current frame does not read while the current frame is computed.  Window h, the twiddle rows and Im(c) stay in
-// shared memory (220 KB in total); the derivative window is read through L1/L2 (it does not fit).
+// current frame does not read while the current frame is computed.  The lower halves of the window h and of its derivative
+// dh (the upper halves are their mirror images), the twiddle rows and Im(c) stay in shared memory.
 // Rows a8-a10 of SURVEY.md §8; spectrogram/processor.rs:313-347,439-488,546-567.
 // Packed FP32x2 switches of this translation unit (common.h; measured in profiles/r02b_packed_ab.md): packed complex adds
 // only — packed products cost this FMA-pipe-bound kernel 2-13 %.
@@ -46,7 +46,6 @@ constexpr int kWarps = kT / 32;          // warps per group
 constexpr int kWSize = f16::phys_size(kSub);
 constexpr int kBinGroups = 9;            // a = t + 256 j, j < 8, and a = 2048 (group 0, t = 0, j = 8)
 constexpr int kCntN = kBinGroups * kWarps;
-constexpr int kDhSmem = 2816;            // dh[0 .. kDhSmem) lives in the shared memory left over; the rest stays L1-resident
 
 struct Fast8kArgs {
   StftKernelArgs a;
@@ -60,13 +59,19 @@ struct Smem8k {
   float2 W[2][kWSize];
   float2 tw1[4 * kT];   // rows q = 1, 2, 4, 8 of W_4096^{b q}
   float2 tw2[15 * 16];
-  float h[kN8];
+  // The periodic cosine-sum windows are symmetric about N/2 (h[N - n] = h[n]) and their spectral derivative antisymmetric
+  // (dh[N - n] = -dh[n]), so HALF of each table (n <= N/2) serves the whole window: both fit in shared memory (round 1 kept
+  // all of h and 2816 entries of dh here and read the rest of dh through L1: 16 % long-scoreboard stalls).  The f32 tables of
+  // the reference are symmetric only up to the rounding of cosf (~6e-8 absolute): mirroring changes the upper half of the
+  // window by that much, 1e-9 of a spectral peak — far below the f32 transform's own rounding (checked against float64 in
+  // tests/test_gpu_exact.py).
+  float hh[kSub + 4];   // h[0 .. N/2]
+  float dhh[kSub + 4];  // dh[0 .. N/2]
   float Y[kN8];         // Y[n] = Im c[n]; also the exchange buffer of the inverse radix-2 combine
   unsigned ball[2][kCntN];
   int offs[kCntN + 1];
   float x0_xm[2];
   int pad_[1];
-  float dh_lo[kDhSmem];
   // float ring[ring_len] follows
 };
 static_assert(sizeof(Smem8k) % 16 == 0, "ring must stay 16-byte aligned");
@@ -121,8 +126,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
     sm.tw1[i] = __ldg(&fa.tw1[row * kT + (i & (kT - 1))]);
   }
   for (int i = tid; i < 15 * 16; i += kThreads) sm.tw2[i] = __ldg(&fa.tw2[i]);
-  for (int i = tid; i < kN8; i += kThreads) sm.h[i] = __ldg(&a.win[i]);
-  for (int i = tid; i < kDhSmem; i += kThreads) sm.dh_lo[i] = __ldg(&a.dwin[i]);
+  for (int i = tid; i <= kSub; i += kThreads) {
+    sm.hh[i] = __ldg(&a.win[i]);
+    sm.dhh[i] = __ldg(&a.dwin[i]);
+  }
   Addr ad;
   ad.pA = t + (t >> 4);
   ad.pB = 273 * (t >> 4) + (t & 15);
@@ -139,7 +146,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
   const int pt = g ? (kT - 1 - t) : ((kT - t) & (kT - 1));
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
   const bool wrap_j = (g == 0 && t == 0);  // partner element index (16 - j) & 15 instead of 15 - j
-  const float* dwin = a.dwin + t;
+  const float* hh_lo = sm.hh + t;            // h[t + n]
+  const float* hh_hi = sm.hh + (kSub - t);   // h[t + n + N/2] = h[N/2 - (t + n)] at hh_hi[-n]
+  const float* dh_lo = sm.dhh + t;
+  const float* dh_hi = sm.dhh + (kSub - t);  // dh[t + n + N/2] = -dh[N/2 - (t + n)]
   const int ts2 = kAnyHop ? 2 * t : 0, ts1 = kAnyHop ? t : 0;
   __syncthreads();
 
@@ -264,11 +274,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
           const int n = kT * j;  // + t
           float wa_, wb_;
           if (wsel == 1) {
-            wa_ = (n + kT <= kDhSmem) ? sm.dh_lo[t + n] : __ldg(dwin + n);
-            wb_ = __ldg(dwin + n + kSub);
+            wa_ = dh_lo[n];
+            wb_ = -dh_hi[-n];
           } else {
-            wa_ = sm.h[t + n];
-            wb_ = sm.h[t + n + kSub];
+            wa_ = hh_lo[n];
+            wb_ = hh_hi[-n];
           }
           if (wsel == 2) {  // t*h window, processor.rs:601-608
             wa_ *= ramp0 + (float)n;
