@@ -305,6 +305,9 @@ int omb_loudness_process_block(omb_loudness* h, const float* samples, size_t n_s
 /* the H2D / D2H copies.                                                      */
 /* ------------------------------------------------------------------------ */
 
+/* Plans own their scratch and host-path staging buffers: ONE execute call in flight per plan at a time (calls on different
+ * plans, or on different streams with different plans, are independent).  A plan is bound to the device that was current when
+ * it was created; every execute entry point selects that device itself. */
 typedef struct omb_stft_plan omb_stft_plan;
 
 /* Columns produced for a lane of `samples` samples: processor.rs:294-299. */

@@ -1013,6 +1013,7 @@ int LoudnessPlan::execute_host(const float* h_interleaved, uint32_t n_streams, u
                                uint64_t block_frames, omb_loudness_snapshot* h_out) {
   if (!n_streams || !frames) return OMB_OK;
   if (!h_interleaved || !h_out || block_frames == 0) return fail(OMB_ERR_INVALID, "invalid argument");
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));
   const uint64_t per = frames * channels;
   OMB_TRY(d_in.reserve((size_t)(per * n_streams)));
   for (uint32_t i = 0; i < n_streams; ++i)

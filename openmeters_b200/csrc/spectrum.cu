@@ -368,6 +368,7 @@ static int keys_finish(SpectrumPlan& p, uint64_t n, int32_t* d_peak_bin, cudaStr
 
 int SpectrumPlan::smooth_device(const float* d_power_in, uint32_t n_lanes, uint64_t hops, float* d_state_io, float* d_weighted,
                                 float* d_raw, int32_t* d_peak_bin, bool write_all, cudaStream_t s) {
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));  // plans are bound to the device they were created on
   const uint64_t n = hops * n_lanes;
   if (d_peak_bin) OMB_TRY(keys_begin(*this, n, s));
   OMB_TRY(smooth_launch(*this, d_power_in, n_lanes, hops, d_state_io, d_weighted, d_raw, d_peak_bin ? d_keys.ptr : nullptr, write_all, hops, 0, s));
@@ -380,6 +381,8 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
   const uint64_t hops = cfg.hops_for(samples_per_lane);
   if (!hops || !n_lanes) return OMB_OK;
   if (!d_lanes || !d_weighted || !d_raw) return fail(OMB_ERR_INVALID, "null argument");
+  if (n_lanes > 65535u) return fail(OMB_ERR_UNSUPPORTED, "at most 65535 lanes per spectrum call (got %u): split the batch", n_lanes);
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));  // plans are bound to the device they were created on
   const uint64_t bins = cfg.bins();
   // Enough lanes to fill the GPU with one CTA per lane: the fused kernel (power spectrum never leaves the SM).
   // OMB_SPECTRUM_FUSED=0/1 pins the choice (measurement / cross-checks).
@@ -460,6 +463,7 @@ int SpectrumPlan::execute_host(const float* h_lanes, uint32_t n_lanes, uint64_t 
   const uint64_t hops = cfg.hops_for(samples_per_lane);
   if (!hops || !n_lanes) return OMB_OK;
   if (!h_lanes || !h_weighted || !h_raw) return fail(OMB_ERR_INVALID, "null argument");
+  OMB_CUDA_TRY(cudaSetDevice(dev.device));
   OMB_TRY(d_in.reserve((size_t)(samples_per_lane * n_lanes)));
   for (uint32_t l = 0; l < n_lanes; ++l)
     OMB_CUDA_TRY(cudaMemcpyAsync(d_in.ptr + l * samples_per_lane, h_lanes + l * lane_stride, sizeof(float) * samples_per_lane,

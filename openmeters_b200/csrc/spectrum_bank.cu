@@ -249,6 +249,8 @@ extern "C" {
 
 int omb_spectrum_bank_create(const omb_spectrum_config* cfg, uint32_t n_streams, omb_spectrum_bank** out) {
   if (!cfg || !out || n_streams == 0) return fail(OMB_ERR_INVALID, "invalid argument");
+  // the batched fold-down / smoothing launches address the stream (x trace) through gridDim.y
+  if (n_streams > 32767u) return fail(OMB_ERR_UNSUPPORTED, "spectrum bank: at most 32767 streams per bank (got %u)", n_streams);
   try {
     auto* h = new omb_spectrum_bank();
     h->b.config = SpectrumConfigN::from_c(*cfg);

@@ -219,6 +219,8 @@ extern "C" {
 
 int omb_spectrogram_bank_create(const omb_spectrogram_config* cfg, uint32_t n_streams, omb_spectrogram_bank** out) {
   if (!cfg || !out || n_streams == 0) return fail(OMB_ERR_INVALID, "invalid argument");
+  // the batched fold-down / smoothing launches address the stream (x trace) through gridDim.y
+  if (n_streams > 32767u) return fail(OMB_ERR_UNSUPPORTED, "spectrogram bank: at most 32767 streams per bank (got %u)", n_streams);
   try {
     auto* h = new omb_spectrogram_bank();
     h->b.config = StftConfig::from_c(*cfg);

@@ -71,6 +71,13 @@ void SpectrogramStream::advance_audio(uint64_t count) {  // processor.rs:406-410
 int SpectrogramStream::update_config(const omb_spectrogram_config& c) {  // processor.rs:518-543
   const StftConfig next = StftConfig::from_c(c);
   const StftConfig prev = config;
+  // Deliberate difference from the reference (rustfft is mixed-radix, any size is legal there): transform lengths without a
+  // kernel are refused HERE and the handle keeps its previous, working configuration — instead of accepting the config and
+  // failing every later process_block.
+  if (prepared && (!is_pow2(next.window) || !is_pow2(next.fft_len()) || next.fft_len() > (1ull << 24) || next.hilbert_len() > (1ull << 24)))
+    return fail(OMB_ERR_UNSUPPORTED,
+                "update_config: fft_size %llu x zero_padding %llu has no kernel (power-of-two lengths only, no CPU fallback); previous config kept",
+                (unsigned long long)next.window, (unsigned long long)next.zero_pad);
   config = next;
   const bool rate_changed = prev.sample_rate != next.sample_rate;
   const bool rebuild = prev.window != next.window || prev.zero_pad != next.zero_pad || prev.window_kind != next.window_kind ||

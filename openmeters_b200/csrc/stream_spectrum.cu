@@ -88,7 +88,12 @@ int SpectrumStream::reset_audio() {  // processor.rs:112-118
 
 int SpectrumStream::update_config(const omb_spectrum_config& c) {  // processor.rs:300-322
   const SpectrumConfigN old = config;
-  config = SpectrumConfigN::from_c(c);
+  const SpectrumConfigN next = SpectrumConfigN::from_c(c);
+  // sizes without a kernel are refused and the previous, working configuration is kept (see stream_spectrogram.cu)
+  if (prepared && (!is_pow2(next.fft_size) || next.fft_size > (1ull << 24)))
+    return fail(OMB_ERR_UNSUPPORTED, "update_config: spectrum fft_size %llu has no kernel (power-of-two lengths only, no CPU fallback); previous config kept",
+                (unsigned long long)next.fft_size);
+  config = next;
   if (!prepared) return OMB_OK;
   const bool mode_changed = old.averaging != config.averaging;
   if (old.fft_size != config.fft_size || old.window_kind != config.window_kind) return rebuild_fft();
