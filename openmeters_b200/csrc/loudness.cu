@@ -224,11 +224,28 @@ __device__ __forceinline__ void loud_snapshot(const LoudStreamArgs& a) {  // lou
   *a.out = snap;
 }
 
+// Tile pipeline.  A block is cut into tiles of kTile frames; in iteration i
+//   warps 2-7  stage tile i + 1 of the input and the ring's old values of tile i in shared memory (coalesced, all loads in
+//              flight at once) and then run the true-peak FIR of tile i,
+//   warp 0     runs the K-weighting recurrence over tile i   (inputs from shared memory: no load inside the chain),
+//   warp 1     runs the four compensated window sums of every channel over tile i - 1,
+// one __syncthreads per iteration.  A first version with the three chains merely separated still spent 0.5 ms per 1024-frame
+// block: every step of a chain waited for a global load (the ring of one stream is 9 MB: DRAM latency); measured in
+// profiles/r02_notes.md.
+constexpr int kTile = 128;
+struct LoudTileSmem {
+  float xs[2][kTile][OMB_MAX_CHANNELS];                        // input tile, [frame][channel] (the block's layout)
+  double vs[2][OMB_MAX_CHANNELS][kTile];                       // y^2 of the tile
+  double olds[2][OMB_MAX_CHANNELS * kLoudWindows][kTile];      // the ring value each (channel, window) retires at each step
+};
+
 __global__ void __launch_bounds__(kStreamThreads) k_loudness_stream(LoudStreamArgs a) {
   __shared__ unsigned long long s_start[OMB_MAX_CHANNELS];   // first frame of the block at which the channel is active
   __shared__ unsigned long long s_head0[OMB_MAX_CHANNELS], s_count0[OMB_MAX_CHANNELS];
   __shared__ unsigned s_peak[OMB_MAX_CHANNELS];               // bits of the block's peak (non-negative floats order as integers)
   __shared__ float s_hist[OMB_MAX_CHANNELS][24];              // [j]: the sample pushed j + 1 steps before the block's first active one
+  OMB_DYN_SMEM(unsigned char, smem_raw);
+  LoudTileSmem& sm = *reinterpret_cast<LoudTileSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   a.block += (uint64_t)blockIdx.x * a.block_stride;
   a.state += (uint64_t)blockIdx.x * a.channels;
@@ -236,7 +253,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_loudness_stream(LoudStreamAr
   a.vnew += (uint64_t)blockIdx.x * a.channels * a.frames;
   a.out += blockIdx.x;
   const uint32_t C = a.channels, dl = a.tp_delay_len;
-  const uint64_t frames = a.frames;
+  const uint64_t frames = a.frames, L = a.ring_len;
 
   // ---- phase 0: lazy activation (loudness/processor.rs:264-274) and the constants of this block
   if (tid < C) {
@@ -249,8 +266,8 @@ __global__ void __launch_bounds__(kStreamThreads) k_loudness_stream(LoudStreamAr
       start = f;
       if (f < frames) {
         st.active = 1;
-        st.head = st.silent_frames % a.ring_len;  // WindowedMeans::with_leading_zeros, dsp.rs:359-365
-        st.count = st.silent_frames < a.ring_len ? st.silent_frames : a.ring_len;
+        st.head = st.silent_frames % L;  // WindowedMeans::with_leading_zeros, dsp.rs:359-365
+        st.count = st.silent_frames < L ? st.silent_frames : L;
         for (int w = 0; w < kLoudWindows; ++w) {
           st.refresh[w] = st.silent_frames % a.caps[w];
           st.sums[w][0] = st.sums[w][1] = st.corr[w][0] = st.corr[w][1] = 0.0;
@@ -269,141 +286,167 @@ __global__ void __launch_bounds__(kStreamThreads) k_loudness_stream(LoudStreamAr
   }
   __syncthreads();
 
-  if (warp == 0) {
-    // ---- phase A: K-weighting, sequential per channel (loudness/processor.rs:153-162), y^2 to the scratch
-    if (lane < C && s_start[lane] < frames) {
-      LoudChannelState& st = a.state[lane];
-      double f[4] = {st.filter[0], st.filter[1], st.filter[2], st.filter[3]};
-      double* vn = a.vnew + (uint64_t)lane * frames;
-      const uint64_t start = s_start[lane];
-      // inputs are fetched kPre at a time ahead of the recurrence: a global load inside the dependent chain would expose its
-      // full latency on every step (measured: 0.5 ms per 1024-frame block before, see profiles/r02_notes.md)
-      constexpr int kPre = 8;
-      for (uint64_t k0 = start; k0 < frames; k0 += kPre) {
-        float xin[kPre];
-#pragma unroll
-        for (int u = 0; u < kPre; ++u) xin[u] = k0 + u < frames ? a.block[(k0 + u) * C + lane] : 0.0f;
-#pragma unroll
-        for (int u = 0; u < kPre; ++u) {
-          if (k0 + u < frames) {
-            const float yf = (float)kw_step((double)xin[u], f, a.kw);
-            double v = __dmul_rn((double)yf, (double)yf);
-            if (!isfinite(v)) v = 0.0;  // dsp.rs:324-333
-            vn[k0 + u - start] = v;
-          }
-        }
-      }
-      for (int i = 0; i < 4; ++i) st.filter[i] = fabs(f[i]) < 1.0e-30 ? 0.0 : f[i];  // level.rs:14-18
+  const uint64_t n_tiles = (frames + kTile - 1) / kTile;
+  auto load_x = [&](uint64_t tile, uint32_t first, uint32_t nthr) {  // input tile -> xs[tile & 1]
+    const uint64_t f0 = tile * kTile;
+    for (uint32_t i = first; i < kTile * C; i += nthr) {
+      const uint64_t f = f0 + i / C;
+      sm.xs[tile & 1][i / C][i % C] = f < frames ? a.block[f * C + i % C] : 0.0f;
     }
-  } else if (warp >= 2) {
-    // ---- phase T: TruePeakMeter::process (loudness/processor.rs:123-150) for every (frame, channel) independently;
-    //      each FIR sum in tap order (newest sample first), the block maximum by atomicMax on the bit pattern
-    const uint32_t nt = kStreamThreads - 64;
-    for (uint64_t idx = tid - 64; idx < frames * C; idx += nt) {
-      const uint64_t k = idx / C;
-      const uint32_t c = (uint32_t)(idx - k * C);
-      const uint64_t start = s_start[c];
-      if (k < start) continue;
-      const float s = a.block[k * C + c];
-      float m = fabsf(s);
-      m = m == m ? m : 0.0f;  // f32::max ignores NaN
-      const uint64_t kk = k - start;
-      auto tap = [&](uint32_t i) -> float {  // the sample pushed i steps before sample k
-        return (uint64_t)i <= kk ? a.block[(k - i) * C + c] : s_hist[c][i - kk - 1];
-      };
-      if (dl == 12) {
-        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
-#pragma unroll
-        for (uint32_t i = 0; i < 12; ++i) {
-          const float d = tap(i);
-          o0 = __fadd_rn(o0, __fmul_rn(d, a.fir.fir4[i][0]));
-          o1 = __fadd_rn(o1, __fmul_rn(d, a.fir.fir4[i][1]));
-          o2 = __fadd_rn(o2, __fmul_rn(d, a.fir.fir4[i][2]));
-        }
-        m = fmaxf(fmaxf(fmaxf(m, fabsf(o0)), fabsf(o1)), fabsf(o2));
-      } else if (dl == 24) {
-        float o = 0.0f;
-#pragma unroll
-        for (uint32_t i = 0; i < 24; ++i) o = __fadd_rn(o, __fmul_rn(tap(i), a.fir.fir2[i]));
-        m = fmaxf(m, fabsf(o));
-      }
-      atomicMax(&s_peak[c], __float_as_uint(m));
-    }
+  };
+  load_x(0, tid, kStreamThreads);
+  // per-lane state of the two sequential roles
+  double fz[4] = {0.0, 0.0, 0.0, 0.0};                  // warp 0, lane = channel
+  double s0 = 0.0, s1 = 0.0, c0 = 0.0, c1 = 0.0;        // warp 1, lane = (channel, window)
+  uint64_t refresh = 0;
+  const uint32_t bc = lane / kLoudWindows, bw = lane % kLoudWindows;
+  if (warp == 0 && lane < C) {
+    const LoudChannelState& st = a.state[lane];
+    for (int i = 0; i < 4; ++i) fz[i] = st.filter[i];
+  }
+  if (warp == 1 && lane < C * kLoudWindows) {
+    const LoudChannelState& st = a.state[bc];
+    s0 = st.sums[bw][0];
+    s1 = st.sums[bw][1];
+    c0 = st.corr[bw][0];
+    c1 = st.corr[bw][1];
+    refresh = st.refresh[bw];
   }
   __syncthreads();
 
-  // ---- phase B: WindowedMeans::push (dsp.rs:334-357) for lane = (channel, window); the old value of step k is the sample
-  //      pushed `cap` steps earlier: this block's own y^2 if k >= cap, else still in the ring
-  if (warp == 1 && lane < C * kLoudWindows) {
-    const uint32_t c = lane / kLoudWindows, w = lane % kLoudWindows;
-    const uint64_t start = s_start[c], n = frames - start;
-    if (n > 0) {
-      LoudChannelState& st = a.state[c];
-      const uint64_t cap = a.caps[w], L = a.ring_len, count0 = s_count0[c];
-      const double* vn = a.vnew + (uint64_t)c * frames;
-      const double* ring = a.ring + (uint64_t)c * L;
-      double s0 = st.sums[w][0], s1 = st.sums[w][1], c0 = st.corr[w][0], c1 = st.corr[w][1];
-      uint64_t refresh = st.refresh[w];
-      uint64_t ri = (s_head0[c] + L - cap) % L;
-      constexpr int kPre = 8;  // new and old values are fetched kPre steps ahead of the compensated-sum chain (see phase A)
-      for (uint64_t k0 = 0; k0 < n; k0 += kPre) {
-        double vin[kPre], oin[kPre];
-#pragma unroll
-        for (int u = 0; u < kPre; ++u) {
-          const uint64_t k = k0 + u;
-          vin[u] = k < n ? vn[k] : 0.0;
-          uint64_t r = ri + u;
-          while (r >= L) r -= L;  // L can be shorter than kPre at toy sample rates
-          oin[u] = (k < n && count0 + k >= cap) ? (k >= cap ? vn[k - cap] : ring[r]) : 0.0;
+  for (uint64_t it = 0; it <= n_tiles; ++it) {
+    if (warp >= 2) {
+      const uint32_t lt = tid - 64, nl = kStreamThreads - 64;
+      if (it + 1 < n_tiles) load_x(it + 1, lt, nl);
+      if (it < n_tiles) {
+        // ring values retired during tile `it`: (channel, window) at step kk = k - start reads ring[(head0 + kk + L - cap) % L]
+        // while kk < cap (later steps retire this block's own y^2, read by warp 1 from the scratch)
+        const uint64_t f0 = it * kTile;
+        for (uint32_t i = lt; i < kTile * C * kLoudWindows; i += nl) {
+          const uint32_t row = i / kTile, t = i % kTile;
+          const uint32_t c = row / kLoudWindows, w = row % kLoudWindows;
+          const uint64_t k = f0 + t, start = s_start[c], cap = a.caps[w];
+          double v = 0.0;
+          if (k < frames && k >= start) {
+            const uint64_t kk = k - start;
+            if (s_count0[c] + kk >= cap && kk < cap) v = a.ring[(uint64_t)c * L + (s_head0[c] + kk + L - cap) % L];
+          }
+          sm.olds[it & 1][row][t] = v;
         }
+        // ---- TruePeakMeter::process (loudness/processor.rs:123-150) for every (frame, channel) of the tile independently;
+        //      each FIR sum in tap order (newest sample first), the block maximum by atomicMax on the bit pattern
+        for (uint32_t i = lt; i < kTile * C; i += nl) {
+          const uint64_t k = f0 + i / C;
+          const uint32_t c = i % C;
+          const uint64_t start = s_start[c];
+          if (k >= frames || k < start) continue;
+          const float s = a.block[k * C + c];
+          float m = fabsf(s);
+          m = m == m ? m : 0.0f;  // f32::max ignores NaN
+          const uint64_t kk = k - start;
+          auto tap = [&](uint32_t j) -> float {  // the sample pushed j steps before sample k
+            return (uint64_t)j <= kk ? a.block[(k - j) * C + c] : s_hist[c][j - kk - 1];
+          };
+          if (dl == 12) {
+            float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
 #pragma unroll
-        for (int u = 0; u < kPre; ++u) {
-          const uint64_t k = k0 + u;
-          if (k < n) {
-            neumaier_add(s0, c0, vin[u]);
-            neumaier_add(s1, c1, vin[u]);
-            if (count0 + k >= cap) neumaier_add(s0, c0, -oin[u]);
-            if (++refresh == cap) {  // CompensatedPair::refresh
-              s0 = s1;
-              s1 = 0.0;
-              c0 = c1;
-              c1 = 0.0;
-              refresh = 0;
+            for (uint32_t j = 0; j < 12; ++j) {
+              const float d = tap(j);
+              o0 = __fadd_rn(o0, __fmul_rn(d, a.fir.fir4[j][0]));
+              o1 = __fadd_rn(o1, __fmul_rn(d, a.fir.fir4[j][1]));
+              o2 = __fadd_rn(o2, __fmul_rn(d, a.fir.fir4[j][2]));
             }
+            m = fmaxf(fmaxf(fmaxf(m, fabsf(o0)), fabsf(o1)), fabsf(o2));
+          } else if (dl == 24) {
+            float o = 0.0f;
+#pragma unroll
+            for (uint32_t j = 0; j < 24; ++j) o = __fadd_rn(o, __fmul_rn(tap(j), a.fir.fir2[j]));
+            m = fmaxf(m, fabsf(o));
+          }
+          atomicMax(&s_peak[c], __float_as_uint(m));
+        }
+      }
+    } else if (warp == 0) {
+      // ---- K-weighting over tile `it`, sequential per channel (loudness/processor.rs:153-162)
+      if (it < n_tiles && lane < C) {
+        const uint64_t f0 = it * kTile, start = s_start[lane];
+        double* vn = a.vnew + (uint64_t)lane * frames;
+#pragma unroll 4
+        for (uint32_t t = 0; t < kTile; ++t) {
+          const uint64_t k = f0 + t;
+          if (k < frames && k >= start) {
+            const float yf = (float)kw_step((double)sm.xs[it & 1][t][lane], fz, a.kw);
+            double v = __dmul_rn((double)yf, (double)yf);
+            if (!isfinite(v)) v = 0.0;  // dsp.rs:324-333
+            sm.vs[it & 1][lane][t] = v;
+            vn[k - start] = v;
           }
         }
-        ri += kPre;
-        while (ri >= L) ri -= L;
       }
-      st.sums[w][0] = s0;
-      st.sums[w][1] = s1;
-      st.corr[w][0] = c0;
-      st.corr[w][1] = c1;
-      st.refresh[w] = refresh;
+    } else if (it > 0 && lane < C * kLoudWindows) {
+      // ---- WindowedMeans::push (dsp.rs:334-357) over tile `it - 1`, lane = (channel, window)
+      const uint64_t tile = it - 1, f0 = tile * kTile, start = s_start[bc], cap = a.caps[bw], count0 = s_count0[bc];
+      const double* vn = a.vnew + (uint64_t)bc * frames;
+      const double* vsr = sm.vs[tile & 1][bc];
+      const double* oldr = sm.olds[tile & 1][lane];
+#pragma unroll 4
+      for (uint32_t t = 0; t < kTile; ++t) {
+        const uint64_t k = f0 + t;
+        if (k < frames && k >= start) {
+          const uint64_t kk = k - start;
+          const double v = vsr[t];
+          const bool has_old = count0 + kk >= cap;
+          neumaier_add(s0, c0, v);
+          neumaier_add(s1, c1, v);
+          if (has_old) neumaier_add(s0, c0, -(kk >= cap ? vn[kk - cap] : oldr[t]));
+          if (++refresh == cap) {  // CompensatedPair::refresh
+            s0 = s1;
+            s1 = 0.0;
+            c0 = c1;
+            c1 = 0.0;
+            refresh = 0;
+          }
+        }
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
+
+  // ---- write-back of the sequential roles' state
+  if (warp == 0 && lane < C && s_start[lane] < frames) {
+    LoudChannelState& st = a.state[lane];
+    for (int i = 0; i < 4; ++i) st.filter[i] = fabs(fz[i]) < 1.0e-30 ? 0.0 : fz[i];  // level.rs:14-18
+  }
+  if (warp == 1 && lane < C * kLoudWindows && s_start[bc] < frames) {
+    LoudChannelState& st = a.state[bc];
+    st.sums[bw][0] = s0;
+    st.sums[bw][1] = s1;
+    st.corr[bw][0] = c0;
+    st.corr[bw][1] = c1;
+    st.refresh[bw] = refresh;
+  }
 
   // ---- phase C: append the block to the ring (only the last ring_len values of a longer block survive), cursors, delay line
   for (uint32_t c = 0; c < C; ++c) {
-    const uint64_t start = s_start[c], n = frames - start, L = a.ring_len;
+    const uint64_t start = s_start[c], n = frames - start;
     const double* vn = a.vnew + (uint64_t)c * frames;
     double* ring = a.ring + (uint64_t)c * L;
     for (uint64_t k = (n > L ? n - L : 0) + tid; k < n; k += kStreamThreads) ring[(s_head0[c] + k) % L] = vn[k];
   }
-  if (tid < C && s_start[tid] < frames) {
-    LoudChannelState& st = a.state[tid];
-    const uint64_t start = s_start[tid], n = frames - start, L = a.ring_len;
-    st.head = (s_head0[tid] + n) % L;
-    st.count = s_count0[tid] + n < L ? s_count0[tid] + n : L;
-    st.peak = fmaxf(st.peak, __uint_as_float(s_peak[tid]));
+  if (tid >= 64 && tid < 64 + C && s_start[tid - 64] < frames) {
+    const uint32_t c = tid - 64;
+    LoudChannelState& st = a.state[c];
+    const uint64_t start = s_start[c], n = frames - start;
+    st.head = (s_head0[c] + n) % L;
+    st.count = s_count0[c] + n < L ? s_count0[c] + n : L;
+    st.peak = fmaxf(st.peak, __uint_as_float(s_peak[c]));
     if (dl) {
       // after n decrements-with-wrap the write cursor sits at (write0 - n) mod dl; delay[write + i] (and its copy dl further)
       // holds the sample pushed i steps ago
       const uint32_t w0 = st.write % dl;
       const uint32_t wn = (uint32_t)((w0 + dl - (n % dl)) % dl);
       for (uint32_t i = 0; i < dl; ++i) {
-        const float val = (uint64_t)i < n ? a.block[(frames - 1 - i) * C + tid] : s_hist[tid][i - n];
+        const float val = (uint64_t)i < n ? a.block[(frames - 1 - i) * C + c] : s_hist[c][i - n];
         const uint32_t p = (wn + i) % dl;
         st.delay[p] = val;
         st.delay[p + dl] = val;
@@ -860,7 +903,11 @@ int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s, uint32_t n_s
   if (seq) {
     OMB_LAUNCH(k_loudness_stream_seq, dim3(n_streams), dim3(32), 0, s, a);
   } else {
-    OMB_LAUNCH(k_loudness_stream, dim3(n_streams), dim3(kStreamThreads), 0, s, a);
+    static const bool attr = [] {
+      return cudaFuncSetAttribute(k_loudness_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoudTileSmem)) == cudaSuccess;
+    }();
+    if (!attr) return fail(OMB_ERR_CUDA, "cudaFuncSetAttribute(k_loudness_stream) failed");
+    OMB_LAUNCH(k_loudness_stream, dim3(n_streams), dim3(kStreamThreads), sizeof(LoudTileSmem), s, a);
   }
   OMB_CHECK_LAUNCH();
   return OMB_OK;

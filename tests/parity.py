@@ -54,7 +54,10 @@ def compare_reassigned_column(a: np.ndarray, b: np.ndarray, *, sr: float, fft_le
         return abs(pa[2] - pb[2]) <= rel * max(abs(pb[2]), peak * 1e-3)
 
     def on_threshold(p):
-        return p[2] <= power_floor * (1 + 1e-3) or p[1] <= 4 * tol_f or sr / 2 - p[1] <= 4 * tol_f
+        # a point sits on a decision threshold if its power is at the 1e-14 floor or its frequency is within its own
+        # uncertainty (the frequency tolerance at ITS level) of 0 or sr/2 — a -100 dB bin next to DC can land on either side
+        ft = 4 * tol_f * scale(p[2])
+        return p[2] <= power_floor * (1 + 1e-3) or p[1] <= ft or sr / 2 - p[1] <= ft
 
     i = j = 0
     while i < len(a) and j < len(b):
