@@ -39,7 +39,8 @@ __device__ __forceinline__ void ring_fetch_pow2(float* ring, int ring_mask, cons
 //   global -> shared : `bulk_g2s`, completion counted in bytes on an mbarrier (`mbar_expect_tx` + `mbar_wait`)
 //   shared -> global : `bulk_s2g` + `bulk_commit` + `bulk_wait_read` (the source may be overwritten afterwards)
 // Addresses and sizes are multiples of 16 bytes.  Under the CPU emulator the copies are synchronous memcpys and the
-// barrier operations are no-ops (the emulator's __syncthreads orders them).
+// mbarrier is modelled in its own 64 bits (pending bytes | armed flag | phase counter), so a thread that reaches
+// `mbar_wait` before the elected thread has issued the copy yields until the phase completes, as on the device.
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, unsigned arrivals) {
 #ifndef OMB_EMU
@@ -47,15 +48,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, unsigned arrivals) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(arrivals));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #else
-  (void)mbar; (void)arrivals;
+  (void)arrivals;  // every use has one arriving thread (the one that issues the copies)
+  *mbar = 0;
 #endif
 }
+#ifdef OMB_EMU
+// emulated mbarrier word: bits 0..31 phase counter, bit 32 armed (the arrival happened), bits 33..63 pending bytes
+__device__ __forceinline__ void mbar_emu_settle(uint64_t* mbar) {
+  if (((*mbar >> 32) & 1u) && (*mbar >> 33) == 0) *mbar = (uint32_t)(*mbar) + 1u;  // armed and nothing pending: next phase
+}
+#endif
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, unsigned bytes) {  // one arrival + `bytes` pending
 #ifndef OMB_EMU
   const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 #else
-  (void)mbar; (void)bytes;
+  *mbar += ((uint64_t)bytes << 33) | (1ull << 32);
+  mbar_emu_settle(mbar);
 #endif
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, unsigned parity) {
@@ -71,13 +80,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, unsigned parity) {
       "OMB_MBAR_DONE:\n"
       "}\n" ::"r"(a), "r"(parity) : "memory");
 #else
-  (void)mbar; (void)parity;
+  while (((uint32_t)(*mbar) & 1u) == parity) omb_emu::yield();
 #endif
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* mbar) {
 #ifdef OMB_EMU
   memcpy(dst_smem, src_gmem, bytes);
-  (void)mbar;
+  *mbar -= (uint64_t)bytes << 33;
+  mbar_emu_settle(mbar);
 #else
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), m = (unsigned)__cvta_generic_to_shared(mbar);
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src_gmem),

@@ -57,13 +57,16 @@ struct StftPlan {
   DeviceInfo dev;
   int kernel_choice = OMB_KERNEL_AUTO;
   bool fast = false;
-  int fast_kind = 0;  // 0 generic, 1 = stft_fast.cu, 2 = stft_fast2.cu, 3 = stft_classic_fast.cu, 4 = stft_fast8k.cu, 5 = stft_fast2k.cu, 6 = stft_fast1k.cu
+  int fast_kind = 0;  // 0 generic, 1 = stft_fast.cu, 2 = stft_fast2.cu, 3 = stft_classic_fast.cu, 4 = stft_fast8k.cu, 5 = stft_fast2k.cu, 6 = stft_fast1k.cu, 7 = stft_r64.cu
   bool smem_kernel = false;  // stft_smem.cu (used when no specialised kernel applies and OMB_KERNEL_GENERIC was not forced)
   float power_scale = 1.0f;
   std::vector<float> h_win, h_dwin, h_twin, h_norm;
   DeviceBuffer<float> d_win, d_dwin, d_twin, d_norm;
   DeviceBuffer<float2> d_tw_fft, d_tw_hil, d_scratch;
   DeviceBuffer<float2> d_fast_tables;  // specialised-kernel twiddle tables
+  DeviceBuffer<float2> d_r64_tables;   // stft_r64.cu: W_4096^{t q} rows
+  DeviceBuffer<float> d_r64_scratch;   // stft_r64.cu: global register park (only with OMB_R64_PARK=global)
+  bool r64 = false;                    // stft_r64.cu prepared (N = 4096 reassigned, any hop % 4 == 0)
   // host-path staging
   DeviceBuffer<float> d_in;
   DeviceBuffer<omb_spectrogram_point> d_points;
@@ -94,6 +97,10 @@ int launch_stft_fast(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
 bool stft_fast2_supported(const StftConfig& cfg, const DeviceInfo& dev);
 int stft_fast2_prepare(StftPlan& plan);
 int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
+// stft_r64.cu: reassigned N = 4096, two-pass radix-64 transforms, one 64-thread team per frame (third generation)
+bool stft_r64_supported(const StftConfig& cfg, const DeviceInfo& dev);
+int stft_r64_prepare(StftPlan& plan);
+int launch_stft_r64(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
 // stft_fast2k.cu: reassigned N = 2048 (two interleaved frames per 4096-point transform)
 bool stft_fast2k_supported(const StftConfig& cfg, const DeviceInfo& dev);
 int stft_fast2k_prepare(StftPlan& plan);

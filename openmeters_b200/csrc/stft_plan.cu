@@ -69,11 +69,16 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
 
   fast = false;
   fast_kind = 0;
-  // OMB_FAST_KERNEL=1|2 pins the specialised kernel generation (measurement / cross-checks); default: newest that fits
+  // OMB_FAST_KERNEL=1|2|3 pins the specialised kernel generation (measurement / cross-checks); default: newest that fits
   const char* pin = getenv("OMB_FAST_KERNEL");
-  const int want = pin ? atoi(pin) : 2;
+  const int want = pin ? atoi(pin) : 3;
   const bool gen1 = stft_fast_supported(cfg, dev), gen2 = want >= 2 && stft_fast2_supported(cfg, dev);
-  if (choice != OMB_KERNEL_GENERIC && (gen1 || gen2)) {
+  const bool gen3 = want >= 3 && stft_r64_supported(cfg, dev);
+  if (choice != OMB_KERNEL_GENERIC && gen3) {  // N = 4096, any hop % 4 == 0: two-pass radix-64 teams (stft_r64.cu)
+    OMB_TRY(stft_r64_prepare(*this));
+    fast = true;
+    fast_kind = 7;
+  } else if (choice != OMB_KERNEL_GENERIC && (gen1 || gen2)) {
     OMB_TRY(stft_fast_prepare(*this));  // uploads the twiddle tables both generations use
     fast = true;
     fast_kind = 1;
@@ -158,6 +163,7 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   const bool aligned16 = (reinterpret_cast<uintptr_t>(d_lanes) & 15u) == 0 && (lane_stride % 4) == 0;
   const bool aligned8 = (reinterpret_cast<uintptr_t>(d_lanes) & 7u) == 0 && (lane_stride % 2) == 0;
   if (fast_kind == 3 && aligned8) return launch_stft_classic_fast(*this, a, s);
+  if (fast_kind == 7 && aligned16) return launch_stft_r64(*this, a, s);
   if (fast_kind == 4 && aligned16) return launch_stft_fast8k(*this, a, s);
   if (fast_kind == 5 && aligned16) return launch_stft_fast2k(*this, a, s);
   if (fast_kind == 6 && aligned16) return launch_stft_fast1k(*this, a, s);

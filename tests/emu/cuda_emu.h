@@ -96,6 +96,7 @@ struct BlockState {
   Fiber* cur = nullptr;
   const std::function<void()>* body = nullptr;
   std::vector<char> dyn_smem;
+  std::vector<uint32_t> tmem;  // tensor memory of the CTA: [128 lanes][512 columns] (tmem_park.cuh), allocated on first use
 };
 
 inline BlockState*& tls_block() {
@@ -251,6 +252,13 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
   std::vector<std::thread> pool;
   for (unsigned t = 0; t < workers; ++t) pool.emplace_back(worker);
   for (auto& t : pool) t.join();
+}
+
+// Tensor memory (tcgen05.ld / tcgen05.st in tmem_park.cuh): a plain per-CTA array, [lane][column].
+inline uint32_t* tmem() {
+  auto& v = blk().tmem;
+  if (v.empty()) v.assign(128 * 512, 0u);
+  return v.data();
 }
 
 inline void* dyn_smem() {

@@ -50,9 +50,9 @@ def test_loudness_batch_two_streams_stereo(emu):
     cases.loudness_parity(emu.api, LoudnessConfig(), 2, None, np.stack([a, b]), 500)
 
 
-@pytest.mark.parametrize("gen", ["1", "2"])
+@pytest.mark.parametrize("gen", ["1", "2", "3"])
 def test_specialised_reassigned_kernels(emu, gen, monkeypatch):
-    """Both generations of the specialised N=4096 kernel (stft_fast.cu / stft_fast2.cu) under the emulator:
+    """All three generations of the specialised N=4096 kernel (stft_fast.cu / stft_fast2.cu / stft_r64.cu) under the emulator:
     multi-run work split, odd frame counts (one idle group in the last pair), 3 lanes."""
     monkeypatch.setenv("OMB_FAST_KERNEL", gen)
     cfg = SpectrogramConfig(fft_size=4096, hop_size=1024, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
