@@ -67,6 +67,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, unsigned bytes) {
   mbar_emu_settle(mbar);
 #endif
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {  // one arrival, no bytes (release semantics at CTA scope)
+#ifndef OMB_EMU
+  const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+#else
+  *mbar += 1ull << 32;
+  mbar_emu_settle(mbar);
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, unsigned parity) {
 #ifndef OMB_EMU
   const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
@@ -80,6 +89,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, unsigned parity) {
       "OMB_MBAR_DONE:\n"
       "}\n" ::"r"(a), "r"(parity) : "memory");
 #else
+  while (((uint32_t)(*mbar) & 1u) == parity) omb_emu::yield();
+#endif
+}
+// Same, for a thread that expects to wait long (a consumer warp polling a producer): sleeps between polls so the spin does not
+// take issue slots from the warps it is waiting for.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* mbar, unsigned parity, unsigned sleep_ns) {
+#ifndef OMB_EMU
+  const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+  unsigned done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(sleep_ns);
+  }
+#else
+  (void)sleep_ns;
   while (((uint32_t)(*mbar) & 1u) == parity) omb_emu::yield();
 #endif
 }

@@ -16,15 +16,21 @@
 //   * Everything a thread must carry across a transform lives in TENSOR MEMORY (tmem_park.cuh): the centre samples
 //     x[2048 + t + 64 j] (read once from the landed frame, used by the three windowed transforms), the spectrum S of
 //     the h-windowed transform and the cross term nd — all of them come back to the thread that parked them, which is
-//     what tcgen05.st / tcgen05.ld .32x32b do.  TMEM is otherwise idle in this kernel (no MMA), and shared memory is
-//     full: 4 x (33 KB exchange + 16 KB Im c) + 16 KB half windows + 7 KB twiddles = 218 KB.
+//     what tcgen05.st / tcgen05.ld .32x32b do.  TMEM is otherwise idle in this kernel (no MMA).  Im c, which the inverse
+//     transform leaves in the wrong threads, crosses shared memory once (through the idle exchange buffer) and is then
+//     parked as the complex analysis input c[n] — 128 columns that each windowed transform reloads with ONE tcgen05.ld.
+//     Shared memory: 4 x 33 KB exchange + 32 KB windows + 7 KB twiddles = 172 KB.
 //   * The inverse transform is the forward one on conjugated data, so ONE copy of the transform code serves all five
 //     transforms of a frame (loop over the transform index; keeps the loop body inside the instruction cache).
-//   * Windows: the lower halves of h and dh serve the whole window (periodic cosine-sum windows are symmetric about N/2,
-//     their spectral derivative antisymmetric; stft_fast8k.cu explains the 6e-8 this moves the upper half by).
 // Any hop that is a multiple of 4 (16-byte aligned bulk copies); there is no ring and hence no hop-specific variant.
 #ifndef OMB_F32X2_CMUL
 #define OMB_F32X2_CMUL 0
+#endif
+#ifndef OMB_R64_PC
+#define OMB_R64_PC 8      // partner values of the pair step in flight per chunk (A/B: profiles/r02_notes.md)
+#endif
+#ifndef OMB_R64_PRUNE
+#define OMB_R64_PRUNE 0   // 1: last radix-4 step of pass B pruned to the outputs used (three code copies; measured slower)
 #endif
 #include <cstdlib>
 
@@ -44,12 +50,15 @@ constexpr int kOff = (kH - kM) / 2;      // first centre sample
 constexpr int kTeam = 64;                // threads per team
 constexpr int kTeams = 4;
 constexpr int kThreads = kTeam * kTeams;
-constexpr int kRS = 65;                  // row stride of the exchange buffer (float2): both access patterns conflict-free
-constexpr int kHalf = kM / 2;            // 2048
+constexpr int kRS = 66;                  // row stride of the exchange buffer (float2): column writes (64-bit) and row reads (128-bit) conflict-free
 constexpr int kGroups = 33;              // bins t + 64 j, j < 32, and bin 2048 (t = 0, j = 32)
 constexpr unsigned kFrameBytes = kH * sizeof(float);
 // TMEM / scratch columns of one warp (a warp owns 256 of the 512 columns of its lane quadrant)
-constexpr int kColX = 0, kColS = 64, kColNd = 128, kColSn = 160, kColNdn = 164, kColsPerWarp = 256;
+constexpr int kColC = 0;      // 64 centre samples x[off + n], later 64 complex c[n] (128 columns), n = t + 64 j
+constexpr int kColS = 128;    // S[t + 64 j], j < 32 (64 columns)
+constexpr int kColNd = 192;   // nd, j < 32
+constexpr int kColSn = 224;   // S[2048] (2 columns), then nd[2048] at kColSn + 2
+constexpr int kColsPerWarp = 256;
 
 struct R64Args {
   StftKernelArgs a;
@@ -59,8 +68,7 @@ struct R64Args {
 };
 
 struct TeamSmem {
-  alignas(16) float2 W[kTeam * kRS];  // landing zone of the frame (8192 floats, linear) / exchange buffer [row][65]
-  float Y[kM];                        // Im c[n]
+  alignas(16) float2 W[kTeam * kRS];  // landing zone of the frame (8192 floats, linear) / exchange buffer [row][66] / Im c staging
   int2 cnt[kGroups + 1];              // kept points of (warp 0, warp 1) per bin group
   float x0_xm[2];
   alignas(8) uint64_t mbar;
@@ -68,8 +76,8 @@ struct TeamSmem {
 
 struct Smem {
   TeamSmem team[kTeams];
-  float hh[kHalf + 4];    // h[0 .. N/2]
-  float dhh[kHalf + 4];   // dh[0 .. N/2]
+  float h[kM];
+  float dh[kM];
   float2 tw[14 * kTeam];
   uint32_t tmem_base;
   uint32_t pad_[3];
@@ -82,6 +90,11 @@ __device__ __forceinline__ void team_sync(int team) {
   omb_emu::named_sync(1 + team, kTeam);
 #else
   asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kTeam) : "memory");
+#endif
+}
+__device__ __forceinline__ void sched_fence() {  // keeps ptxas from hoisting the next chunk's loads above this point (register pressure)
+#ifndef OMB_EMU
+  asm volatile("" ::: "memory");
 #endif
 }
 
@@ -104,8 +117,10 @@ __device__ __forceinline__ void twiddle63(float2 (&v)[64], const float2* tab) {
 }
 
 // One 4096-point forward transform of the team: thread t enters with elements t + 64 j and leaves with bins t + 64 k.
-// The barrier before the stores orders them after every thread's previous reads of W (frame samples, partner rows,
-// the previous exchange).
+// Pass A is decimation in frequency (its last step is four independent 16-point transforms whose outputs can leave as
+// they complete), pass B decimation in time (its first step is four 16-point transforms that can start as their inputs
+// arrive): measured +1.7 % over DIF / DIF on the transform alone.  The barrier before the stores orders them after every
+// thread's previous reads of W (frame samples, partner rows, the previous exchange).
 __device__ __forceinline__ void transform(float2 (&v)[64], float2* W, const float2* twt, int t, int team) {
   f64pt::dft64<false>(v);
   twiddle63(v, twt);
@@ -114,10 +129,14 @@ __device__ __forceinline__ void transform(float2 (&v)[64], float2* W, const floa
 #pragma unroll
   for (int q = 0; q < 64; ++q) wr[q * kRS] = v[q];
   team_sync(team);
-  const float2* rd = W + t * kRS;
+  const float4* rd = reinterpret_cast<const float4*>(W + t * kRS);
 #pragma unroll
-  for (int s = 0; s < 64; ++s) v[s] = rd[s];
-  f64pt::dft64<false>(v);
+  for (int s = 0; s < 32; ++s) {
+    const float4 p = rd[s];
+    v[2 * s] = make_float2(p.x, p.y);
+    v[2 * s + 1] = make_float2(p.z, p.w);
+  }
+  f64pt::dit_front<false>(v);  // the caller finishes with dit_final<kPrune>: the last radix-4 step, pruned to the outputs it uses
 }
 
 template <bool kTmem, int N>
@@ -133,8 +152,7 @@ __device__ __forceinline__ void park_st(uint32_t tcol, float* scratch, int col, 
 template <bool kTmem, int N>
 __device__ __forceinline__ void park_ld(uint32_t tcol, const float* scratch, int col, float (&r)[N]) {
   if (kTmem) {
-    tmem_ld<N>(tcol + col, r);
-    tmem_wait_ld();
+    tmem_ld<N>(tcol + col, r);  // includes tcgen05.wait::ld
   } else {
 #pragma unroll
     for (int i = 0; i < N; ++i) r[i] = scratch[(size_t)(col + i) * kThreads];
@@ -143,6 +161,7 @@ __device__ __forceinline__ void park_ld(uint32_t tcol, const float* scratch, int
 
 template <bool kTmem>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_r64(R64Args ra) {
+  constexpr int kCtaThreads = kThreads;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const StftKernelArgs& a = ra.a;
@@ -153,11 +172,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_r64(R64Args ra) {
   const ReassignConsts rc{a.bin_hz, a.max_hz, a.inv_2pi, a.inv_hop, a.latency_hops};
 
   // ---- one-off: tables, TMEM, barriers
-  for (int i = tid; i <= kHalf; i += kThreads) {
-    sm.hh[i] = __ldg(&a.win[i]);
-    sm.dhh[i] = __ldg(&a.dwin[i]);
+  for (int i = tid; i < kM; i += kCtaThreads) {
+    sm.h[i] = __ldg(&a.win[i]);
+    sm.dh[i] = __ldg(&a.dwin[i]);
   }
-  for (int i = tid; i < 14 * kTeam; i += kThreads) sm.tw[i] = __ldg(&ra.tw[i]);
+  for (int i = tid; i < 14 * kTeam; i += kCtaThreads) sm.tw[i] = __ldg(&ra.tw[i]);
   if (kTmem && tid < 32) tmem_alloc(&sm.tmem_base);
   if (t == 0) mbar_init(&ts.mbar, 1);
   if (kTmem) tmem_fence_before_sync();
@@ -197,26 +216,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_r64(R64Args ra) {
     float2 v[64];
     {
       const float* wf = reinterpret_cast<const float*>(ts.W);
-      // centre samples of this thread's analysis points n = t + 64 j -> park
+      // centre samples of this thread's analysis points n = t + 64 j -> park (they become Re c after the forward transform)
       float xc[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) xc[j] = wf[kOff + t + kTeam * j];
-      park_st<kTmem, 64>(tcol, scratch, kColX, xc);
+      park_st<kTmem, 64>(tcol, scratch, kColC, xc);
       // F input: z[n] = x[2n] + j x[2n+1], n = t + 64 j
       const float2* wz = ts.W + t;
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] = wz[kTeam * j];
     }
-    float bias = 0.0f;
 #pragma unroll 1
     for (int tr = 0; tr < 5; ++tr) {
       if (tr == 1) {
         // ---- X: Q[k] = cos(th_k) conj(Z[M-k]) + j sin(th_k) Z[k], k = t + 64 j, th_k = th_t + 2 pi j / 128; the inverse
         //      transform runs as conj(forward(conj Q)), so conj(Q) is what enters the transform
         team_sync(team);
-        float2* row = ts.W + t * kRS;
+        float4* row = reinterpret_cast<float4*>(ts.W + t * kRS);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) row[j] = v[j];
+        for (int j = 0; j < 32; ++j) row[j] = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
         if (t == 0) {
           ts.x0_xm[0] = v[0].x + v[0].y;
           ts.x0_xm[1] = v[0].x - v[0].y;
@@ -224,51 +242,75 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_r64(R64Args ra) {
         team_sync(team);
         // partner of k = t + 64 j: row 64 - t, column 63 - j; for t = 0 row 0, column 64 - j (j = 0 reads a don't-care: DC is zeroed)
         const float2* prow = t == 0 ? ts.W + 1 : ts.W + pt * kRS;
+        constexpr int kPc = OMB_R64_PC;  // partner values in flight: two chunks of 8 (register budget: v holds 128)
+        float2 zp[2][kPc];
 #pragma unroll
-        for (int j0 = 0; j0 < 64; j0 += 16) {
+        for (int i = 0; i < kPc; ++i) zp[0][i] = prow[63 - i];
 #pragma unroll
-          for (int j = j0; j < j0 + 16; ++j) {
-            const float2 zp = prow[63 - j];
+        for (int c = 0; c < 64 / kPc; ++c) {
+          if (c + 1 < 64 / kPc) {
+#pragma unroll
+            for (int i = 0; i < kPc; ++i) zp[(c + 1) & 1][i] = prow[63 - kPc * (c + 1) - i];
+          }
+#pragma unroll
+          for (int i = 0; i < kPc; ++i) {
+            const int j = kPc * c + i;
             const float cj = f64pt::kCos128[j], sj = f64pt::kSin128[j];
             const float ck = cos_t * cj - sin_t * sj;
             const float sk = sin_t * cj + cos_t * sj;
-            const float2 z = v[j];
-            v[j] = make_float2(ck * zp.x - sk * z.y, ck * zp.y - sk * z.x);
+            const float2 z = v[j], p = zp[c & 1][i];
+            v[j] = make_float2(ck * p.x - sk * z.y, ck * p.y - sk * z.x);
           }
-#ifndef OMB_EMU
-          asm volatile("" ::: "memory");  // keeps the partner loads of the next 16 bins behind this chunk's arithmetic (registers)
-#endif
+          sched_fence();
         }
         if (t == 0) v[0] = make_float2(0.0f, 0.0f);
-        bias = sign * 0.5f * ts.x0_xm[1] - 0.5f * ts.x0_xm[0];
       } else if (tr >= 2) {
-        // ---- G input: c[n] w[n], c[n] = (M x[off + n] + bias) + j Im c[n], w = h, dh, t*h
-        const int wsel = tr - 2;
-        const float* tab = wsel == 1 ? sm.dhh : sm.hh;
-        const float* lo = tab + t;                 // n = t + 64 j <= 2047
-        const float* up = tab + (kM - t);          // mirrored: index 4096 - n = (4096 - t) - 64 j
-        // multiplier of the table value: 1 | +-1 (dh is antisymmetric) | n - (N-1)/2 (t*h window, processor.rs:601-608)
-        const float a1 = wsel == 2 ? 1.0f : 0.0f;
-        const float a0 = wsel == 2 ? ramp0 : 1.0f;
-        const float b0 = wsel == 2 ? ramp0 : (wsel == 1 ? -1.0f : 1.0f);
-        float xc[64];
-        park_ld<kTmem, 64>(tcol, scratch, kColX, xc);
-        const float* y = ts.Y + t;
+        // ---- G input: c[n] w[n], w = h, dh, t*h (processor.rs:601-608: (n - (N-1)/2) * h[n], formed on the fly, bit-identical)
+        float c[128];
+        park_ld<kTmem, 128>(tcol, scratch, kColC, c);
+        if (tr == 4) {
+          const float* tab = sm.h + t;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const float hv = j < 32 ? lo[kTeam * j] : up[-kTeam * j];
-          const float wv = hv * fmaf(a1, (float)(kTeam * j), j < 32 ? a0 : b0);
-          const float cx = fmaf((float)kM, xc[j], bias);
-          v[j] = f16::cscale2(make_float2(cx, y[kTeam * j]), wv);
+          for (int j = 0; j < 64; ++j) {
+            const float wv = (ramp0 + (float)(kTeam * j)) * tab[kTeam * j];
+            v[j] = f16::cscale2(make_float2(c[2 * j], c[2 * j + 1]), wv);
+          }
+        } else {
+          const float* tab = (tr == 3 ? sm.dh : sm.h) + t;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = f16::cscale2(make_float2(c[2 * j], c[2 * j + 1]), tab[kTeam * j]);
         }
       }
       transform(v, ts.W, twt, t, team);
+      if (tr == 0 || !OMB_R64_PRUNE) {
+        f64pt::dit_final<false, f16::kAll>(v);
+      } else if (tr == 1) {
+        f64pt::dit_final<false, f16::kMid8>(v);    // only the centre half, outputs 16..47
+      } else {
+        f64pt::dit_final<false, f16::kFirst9>(v);  // only bins <= Nyquist, outputs 0..32
+      }
       if (tr == 1) {
-        // ---- centre half of the inverse: y[m] = conj(v), m = t + 64 n1, n1 = 16..47 -> Y as float2[m - 1024]
-        float2* y2 = reinterpret_cast<float2*>(ts.Y) + t;
+        // ---- centre half of the inverse: y[m] = conj(v), m = t + 64 n1, n1 = 16..47, carries Im c[2(m - 1024)], Im c[2(m - 1024) + 1]:
+        //      redistributed through W (free between two exchanges) to the threads that own n = t + 64 j, combined with the parked
+        //      centre samples into c[n] = (M x[off + n] + bias) + j Im c[n], and parked for the three windowed transforms
+        team_sync(team);
+        float2* y2 = ts.W + t;
 #pragma unroll
         for (int q = 16; q < 48; ++q) y2[kTeam * (q - 16)] = make_float2(v[q].x, -v[q].y);
         team_sync(team);
+        const float bias = sign * 0.5f * ts.x0_xm[1] - 0.5f * ts.x0_xm[0];
+        const float* yf = reinterpret_cast<const float*>(ts.W) + t;
+        float c[128];
+        {
+          float xc[64];
+          park_ld<kTmem, 64>(tcol, scratch, kColC, xc);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            c[2 * j] = fmaf((float)kM, xc[j], bias);
+            c[2 * j + 1] = yf[kTeam * j];
+          }
+        }
+        park_st<kTmem, 128>(tcol, scratch, kColC, c);
       } else if (tr == 2) {
         float s[64];
 #pragma unroll
@@ -280,14 +322,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_r64(R64Args ra) {
         const float sn[2] = {v[32].x, v[32].y};
         park_st<kTmem, 2>(tcol, scratch, kColSn, sn);
       } else if (tr == 3) {
-        float s[64], sn[2], nd[32], ndn[1];
+        float s[64], sn[4], nd[32], ndn[1];
         park_ld<kTmem, 64>(tcol, scratch, kColS, s);
-        park_ld<kTmem, 2>(tcol, scratch, kColSn, sn);
+        park_ld<kTmem, 4>(tcol, scratch, kColSn, sn);
 #pragma unroll
         for (int j = 0; j < 32; ++j) nd[j] = v[j].y * s[2 * j] - v[j].x * s[2 * j + 1];
         ndn[0] = v[32].y * sn[0] - v[32].x * sn[1];
         park_st<kTmem, 32>(tcol, scratch, kColNd, nd);
-        park_st<kTmem, 1>(tcol, scratch, kColNdn, ndn);
+        park_st<kTmem, 1>(tcol, scratch, kColSn + 2, ndn);
       }
     }
     // ---- every thread has read its row of the last exchange: the next frame may land
@@ -300,33 +342,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_r64(R64Args ra) {
     // ---- R: reassignment + ordered compaction (order: bin group j, then thread t)
     omb_spectrogram_point pts[kGroups];
     unsigned keep_lo = 0, keep_hi = 0;
-    // (S and nd come back from the park eight bin groups at a time: T, the points and one chunk are live, never all of S)
+    {
+      float nd[32], sn[4];
+      park_ld<kTmem, 32>(tcol, scratch, kColNd, nd);
+      park_ld<kTmem, 4>(tcol, scratch, kColSn, sn);
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-      float s[16], nd[8];
-      if (c < 4) {
-        park_ld<kTmem, 16>(tcol, scratch, kColS + 16 * c, s);
-        park_ld<kTmem, 8>(tcol, scratch, kColNd + 8 * c, nd);
-      } else {
-        float sn[2], ndn[1];
-        park_ld<kTmem, 2>(tcol, scratch, kColSn, sn);
-        park_ld<kTmem, 1>(tcol, scratch, kColNdn, ndn);
-        s[0] = sn[0];
-        s[1] = sn[1];
-        nd[0] = ndn[0];
-      }
-#pragma unroll
-      for (int i = 0; i < (c < 4 ? 8 : 1); ++i) {
-        const int j = 8 * c + i;
-        const int bin = t + kTeam * j;
-        const float norm = (bin == 0 || j == 32) ? ra.norm_dc : ra.norm_ac;
-        const bool k = reassign_bin_nd(make_float2(s[2 * i], s[2 * i + 1]), nd[i], v[j], norm, bin, rc, &pts[j]) & (j < 32 || t == 0);
-        const unsigned m = __ballot_sync(0xffffffffu, k);
-        if (lane_id == 0) {
-          if (wt == 0) ts.cnt[j].x = __popc(m); else ts.cnt[j].y = __popc(m);
+      for (int c = 0; c < 3; ++c) {
+        float s[32];
+        if (c < 2) {
+          park_ld<kTmem, 32>(tcol, scratch, kColS + 32 * c, s);
+        } else {
+          s[0] = sn[0];
+          s[1] = sn[1];
         }
-        if (k) {
-          if (j < 32) keep_lo |= 1u << j; else keep_hi = 1u;
+#pragma unroll
+        for (int i = 0; i < (c < 2 ? 16 : 1); ++i) {
+          const int j = 16 * c + i;
+          const int bin = t + kTeam * j;
+          const float norm = (bin == 0 || j == 32) ? ra.norm_dc : ra.norm_ac;
+          const float ndj = j < 32 ? nd[j & 31] : sn[2];
+          const bool k = reassign_bin_nd(make_float2(s[2 * i], s[2 * i + 1]), ndj, v[j], norm, bin, rc, &pts[j]) & (j < 32 || t == 0);
+          const unsigned m = __ballot_sync(0xffffffffu, k);
+          if (lane_id == 0) {
+            if (wt == 0) ts.cnt[j].x = __popc(m); else ts.cnt[j].y = __popc(m);
+          }
+          if (k) {
+            if (j < 32) keep_lo |= 1u << j; else keep_hi = 1u;
+          }
         }
       }
     }
