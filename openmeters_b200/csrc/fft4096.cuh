@@ -5,6 +5,7 @@
 #pragma once
 #include "device_math.cuh"
 #include "fft16.cuh"
+#include "tmem_park.cuh"
 
 namespace omb {
 namespace f4k {
@@ -77,6 +78,42 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[16], float2* W, const fl
   f16::dft16p<false, kPrune>(v);
 }
 
+
+// ---- twiddles from tensor memory.  The 15 + 15 twiddles a thread uses in passes 1 and 2 depend only on its index, never on the
+// data: parked once per kernel in the thread's own TMEM columns (tmem_park.cuh) they cost one tcgen05.ld per pass instead of 4 + 15
+// shared-memory loads and the 11 complex products that rebuild the pass-1 set (twiddle15<kTw = 1>) — shared-memory wavefronts are
+// the first co-limiter of the radix-16 kernels (profiles/r02f_ncu_full_fast2.json).
+struct TwTmem {
+  uint32_t t1, t2;  // TMEM addresses: 30 columns each (15 float2, q = 1..15), padded to 32
+};
+template <bool INV>
+__device__ __forceinline__ void twiddle15_tmem(float2 (&v)[16], uint32_t taddr) {
+  float w[32];
+  tmem_ld<32>(taddr, w);
+#pragma unroll
+  for (int q = 1; q < 16; ++q) v[q] = f16::mul_tw<INV>(v[q], make_float2(w[2 * (q - 1)], w[2 * (q - 1) + 1]));
+}
+template <int kPrune, bool kLocal3 = false>
+__device__ __forceinline__ void fft_forward_tmem(float2 (&v)[16], float2* W, const TwTmem& tw, const Addr& ad, int g) {
+  f16::dft16<false>(v);
+  twiddle15_tmem<false>(v, tw.t1);
+  float2* wa = W + ad.pA;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wa[273 * q] = v[q];
+  group_sync(g);
+  float2* wb = W + ad.pB;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
+  f16::dft16<false>(v);
+  twiddle15_tmem<false>(v, tw.t2);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
+  group_sync(g);
+  const float2* wc = W + ad.pC;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = wc[j];
+  f16::dft16p<false, kPrune>(v);
+}
 
 }  // namespace f4k
 }  // namespace omb

@@ -67,6 +67,8 @@ struct Smem2 {
   float dh[kM];
   GroupSmem g[kGroupsPerCta];
   alignas(16) uint64_t mbar[2];          // [0]: completion barrier of the ring's bulk copies (kBulkIn)
+  uint32_t tmem_base;                    // kTmemTab
+  uint32_t pad_[3];
   // float ring[ring_len] follows
 };
 static_assert(sizeof(Smem2) % 16 == 0 && sizeof(GroupSmem) % 16 == 0, "bulk copies need 16-byte aligned shared addresses");
@@ -91,6 +93,9 @@ __device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const flo
 // copy (cp.async.bulk.global.shared) instead of 27 predicated scalar STG per thread; the staging offset reproduces the slot's
 // misalignment (slots are 12-byte multiples) so the 16-byte aligned body is one copy and <= 3 head / tail floats are stored
 // by three threads each.
+// kVariant bit 5 (kTmemTab): everything a thread reads from a TABLE — its 15 + 15 twiddles and its 16 + 16 window values — sits in the
+// thread's own tensor-memory columns (tcgen05.st once, one tcgen05.ld per pass / window): 95 shared-memory loads, 48 window loads
+// and 220 twiddle-product instructions per thread-frame become 13 TMEM loads.
 template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
   constexpr int kTw2 = kVariant & 1;
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   constexpr bool kAnyHop = (kVariant & 4) != 0;
   constexpr bool kBulkIn = (kVariant & 8) != 0;
   constexpr bool kBulkOut = (kVariant & 16) != 0;
+  constexpr bool kTmemTab = (kVariant & 32) != 0;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
   float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
@@ -140,7 +146,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
   if (kBulkIn && tid == 0) mbar_init(&sm.mbar[0], 1);
   unsigned ring_phase = 0;  // parity of the mbarrier phase the next wait is for
+  if (kTmemTab && tid < 32) tmem_alloc(&sm.tmem_base);
+  if (kTmemTab) tmem_fence_before_sync();
   __syncthreads();
+  TwTmem twm{0u, 0u};
+  uint32_t tm_h = 0u, tm_dh = 0u;
+  if (kTmemTab) {
+    tmem_fence_after_sync();
+    // a warp owns 128 columns of its lane quadrant: [0,32) pass-1 twiddles, [32,64) pass-2 twiddles, [64,80) h, [80,96) dh
+    const uint32_t tb = tmem_addr(sm.tmem_base, (uint32_t)(tid >> 7) * 128u);
+    twm.t1 = tb;
+    twm.t2 = tb + 32u;
+    tm_h = tb + 64u;
+    tm_dh = tb + 80u;
+    float w1[32], w2[32], hv[16], dv[16];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) {
+      const float2 a1 = __ldg(&fa.tw1[(q - 1) * kT + t]);
+      const float2 a2 = __ldg(&fa.tw2[(q - 1) * 16 + (t & 15)]);
+      w1[2 * (q - 1)] = a1.x;
+      w1[2 * (q - 1) + 1] = a1.y;
+      w2[2 * (q - 1)] = a2.x;
+      w2[2 * (q - 1) + 1] = a2.y;
+    }
+    w1[30] = w1[31] = w2[30] = w2[31] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      hv[j] = __ldg(&a.win[t + kT * j]);
+      dv[j] = __ldg(&a.dwin[t + kT * j]);
+    }
+    tmem_st<32>(twm.t1, w1);
+    tmem_st<32>(twm.t2, w2);
+    tmem_st<16>(tm_h, hv);
+    tmem_st<16>(tm_dh, dv);
+    tmem_wait_st();
+  }
 
   for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
     const uint64_t lane = run / fa.runs_per_lane;
@@ -194,7 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         for (int j = 0; j < 16; ++j)
           v[j] = kAnyHop ? *reinterpret_cast<const float2*>(ring + ((r0 + 2 * kT * j + 2 * t) & ring_mask))
                          : *reinterpret_cast<const float2*>(ring + ((r0 + 2 * kT * j) & ring_mask) + 2 * t);
-        fft_forward<f16::kAll, kTw2, kLocal>(v, gs.W, tw1t, tw2o, adf, g);
+        if (kTmemTab) fft_forward_tmem<f16::kAll, kLocal>(v, gs.W, twm, adf, g);
+        else fft_forward<f16::kAll, kTw2, kLocal>(v, gs.W, tw1t, tw2o, adf, g);
 #pragma unroll
         for (int q = 0; q < 16; ++q) gs.W[adf.pC + q] = v[q];
         if (t == 0) {
@@ -235,7 +276,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           float2* wb = gs.W + ad.pB;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wb[17 * j];
-          twiddle15<true, kTw2, false>(v, tw2o, 16);
+          if (kTmemTab) twiddle15_tmem<true>(v, twm.t2);
+          else twiddle15<true, kTw2, false>(v, tw2o, 16);
           f16::dft16<true>(v);
 #pragma unroll
           for (int q = 0; q < 16; ++q) wb[17 * q] = v[q];
@@ -243,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           const float2* wa = gs.W + ad.pA;
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = wa[273 * j];
-          twiddle15<true, 1, true>(v, tw1t, kT);
+          if (kTmemTab) twiddle15_tmem<true>(v, twm.t1);
+          else twiddle15<true, 1, true>(v, tw1t, kT);
           f16::dft16p<true, f16::kMid8>(v);
           // q[m], m = t + 256 m2, m2 = 4..11 -> Y as float2[m - 1024]
           float2* y2 = reinterpret_cast<float2*>(gs.Y) + t;
@@ -258,15 +301,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
 #pragma unroll 1
         for (int wsel = 0; wsel < 3; ++wsel) {
           const float* win = (wsel == 1 ? sm.dh : sm.h) + t;
+          float wreg[16];
+          if (kTmemTab) tmem_ld<16>(wsel == 1 ? tm_dh : tm_h, wreg);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float wv = win[kT * j];
+            float wv = kTmemTab ? wreg[j] : win[kT * j];
             if (wsel == 2) wv *= ramp0 + (float)(kT * j);       // t*h window, processor.rs:601-608
             const float xs = kAnyHop ? ring[(r0 + off + kT * j + t) & ring_mask] : ring[((r0 + off + kT * j) & ring_mask) + t];
             const float cx = fmaf((float)kM, xs, bias);
             v[j] = f16::cscale2(make_float2(cx, gs.Y[t + kT * j]), wv);
           }
-          fft_forward<f16::kFirst9, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
+          if (kTmemTab) fft_forward_tmem<f16::kFirst9>(v, gs.W, twm, ad, g);
+          else fft_forward<f16::kFirst9, kTw2>(v, gs.W, tw1t, tw2o, ad, g);
           if (wsel == 0) {
 #pragma unroll
             for (int j = 0; j < kBinGroups; ++j) S[j] = v[j];
@@ -353,6 +399,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
     __syncthreads();
   }
   if (kBulkOut && t == 0) bulk_wait_read();  // shared memory must outlive the copies that read it
+  if (kTmemTab) {
+    __syncthreads();
+    if (tid < 32) tmem_free(sm.tmem_base);
+  }
 }
 
 uint32_t ring_len_for(uint64_t hop) { return (uint32_t)next_pow2(2 * (uint64_t)kM + 3 * hop); }
@@ -377,6 +427,8 @@ int stft_fast2_prepare(StftPlan& plan) {
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<58>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<62>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
 }
 
@@ -402,7 +454,7 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
   // OMB_FAST2_BULK: 0 = per-thread LDGSTS ring + scalar column stores (round 1), 1 = bulk ring fill, 3 = bulk ring fill and bulk
   // column store (default: kDefaultBulk)
-  static const int bulk = [] { const char* e = getenv("OMB_FAST2_BULK"); return e ? atoi(e) & 3 : kDefaultBulk; }();
+  static const int bulk = [] { const char* e = getenv("OMB_FAST2_BULK"); return e ? atoi(e) & 7 : kDefaultBulk; }();
   const size_t smem = smem_bytes(a.hop);
   const bool any_hop = (a.hop % 512) != 0;
 #define OMB_FAST2_LAUNCH(V) OMB_LAUNCH(k_reassigned_fast2<V>, dim3(grid), dim3(kThreads), smem, s, fa)
@@ -410,6 +462,8 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
     if (any_hop) OMB_FAST2_LAUNCH(6); else OMB_FAST2_LAUNCH(2);
   } else if (bulk == 1) {
     if (any_hop) OMB_FAST2_LAUNCH(14); else OMB_FAST2_LAUNCH(10);
+  } else if (bulk == 7) {  // + tables in tensor memory
+    if (any_hop) OMB_FAST2_LAUNCH(62); else OMB_FAST2_LAUNCH(58);
   } else {
     if (any_hop) OMB_FAST2_LAUNCH(30); else OMB_FAST2_LAUNCH(26);
   }

@@ -73,7 +73,10 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
   const char* pin = getenv("OMB_FAST_KERNEL");
   const int want = pin ? atoi(pin) : 3;
   const bool gen1 = stft_fast_supported(cfg, dev), gen2 = want >= 2 && stft_fast2_supported(cfg, dev);
-  const bool gen3 = want >= 3 && stft_r64_supported(cfg, dev);
+  // Generation 3 (stft_r64.cu) has no staging ring, so its rate does not depend on the hop; generation 2 is 2 % faster at the hops
+  // its ring handles with warp-uniform rows (multiples of 512) and slower at the others (profiles/r02_notes.md).  Unpinned: each
+  // hop goes to the faster kernel.
+  const bool gen3 = want >= 3 && stft_r64_supported(cfg, dev) && (pin != nullptr || !gen2 || (cfg.hop % 512) != 0);
   if (choice != OMB_KERNEL_GENERIC && gen3) {  // N = 4096, any hop % 4 == 0: two-pass radix-64 teams (stft_r64.cu)
     OMB_TRY(stft_r64_prepare(*this));
     fast = true;

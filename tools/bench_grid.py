@@ -17,7 +17,7 @@ from openmeters_b200._lib import api as lib_api  # noqa: E402
 from openmeters_b200.processors import SpectrogramConfig  # noqa: E402
 from tests.cases import settings_grid  # noqa: E402
 
-TIER = {1: "stft_fast.cu", 2: "stft_fast2.cu", 3: "stft_classic_fast.cu", 4: "stft_fast8k.cu", 5: "stft_fast2k.cu", 6: "stft_fast1k.cu"}
+TIER = {1: "stft_fast.cu", 2: "stft_fast2.cu", 3: "stft_classic_fast.cu", 4: "stft_fast8k.cu", 5: "stft_fast2k.cu", 6: "stft_fast1k.cu", 7: "stft_r64.cu"}
 
 
 def timed(fn, iters=5, warm=2):
