@@ -57,7 +57,7 @@ struct StftPlan {
   DeviceInfo dev;
   int kernel_choice = OMB_KERNEL_AUTO;
   bool fast = false;
-  int fast_kind = 0;  // 0 generic, 1 = stft_fast.cu, 2 = stft_fast2.cu, 3 = stft_classic_fast.cu, 4 = stft_fast8k.cu, 5 = stft_fast2k.cu, 6 = stft_fast1k.cu, 7 = stft_r64.cu
+  int fast_kind = 0;  // 0 generic, 1 = stft_fast.cu, 2 = stft_fast2.cu, 3 = stft_classic_fast.cu, 4 = stft_fast8k.cu, 5 = stft_fast2k.cu, 6 = stft_fast1k.cu, 7 = stft_r64.cu, 8 = stft_r64x.cu
   bool smem_kernel = false;  // stft_smem.cu (used when no specialised kernel applies and OMB_KERNEL_GENERIC was not forced)
   float power_scale = 1.0f;
   std::vector<float> h_win, h_dwin, h_twin, h_norm;
@@ -101,6 +101,10 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
 bool stft_r64_supported(const StftConfig& cfg, const DeviceInfo& dev);
 int stft_r64_prepare(StftPlan& plan);
 int launch_stft_r64(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
+// stft_r64x.cu: reassigned N = 16384 on chip (one 256-thread CTA per frame, 64 x 64 x 4 transforms, TMEM park)
+bool stft_r64x_supported(const StftConfig& cfg, const DeviceInfo& dev);
+int stft_r64x_prepare(StftPlan& plan);
+int launch_stft_r64x(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s);
 // stft_fast2k.cu: reassigned N = 2048 (two interleaved frames per 4096-point transform)
 bool stft_fast2k_supported(const StftConfig& cfg, const DeviceInfo& dev);
 int stft_fast2k_prepare(StftPlan& plan);

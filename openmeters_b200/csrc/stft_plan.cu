@@ -89,6 +89,10 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
       OMB_TRY(stft_fast2_prepare(*this));
       fast_kind = 2;
     }
+  } else if (choice != OMB_KERNEL_GENERIC && stft_r64x_supported(cfg, dev) && !getenv("OMB_NO_R64X")) {
+    OMB_TRY(stft_r64x_prepare(*this));
+    fast = true;
+    fast_kind = 8;
   } else if (choice != OMB_KERNEL_GENERIC && stft_fast8k_supported(cfg, dev) && !getenv("OMB_NO_FAST8K")) {
     OMB_TRY(stft_fast8k_prepare(*this));
     fast = true;
@@ -167,6 +171,7 @@ int StftPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_t sa
   const bool aligned8 = (reinterpret_cast<uintptr_t>(d_lanes) & 7u) == 0 && (lane_stride % 2) == 0;
   if (fast_kind == 3 && aligned8) return launch_stft_classic_fast(*this, a, s);
   if (fast_kind == 7 && aligned16) return launch_stft_r64(*this, a, s);
+  if (fast_kind == 8 && aligned16) return launch_stft_r64x(*this, a, s);
   if (fast_kind == 4 && aligned16) return launch_stft_fast8k(*this, a, s);
   if (fast_kind == 5 && aligned16) return launch_stft_fast2k(*this, a, s);
   if (fast_kind == 6 && aligned16) return launch_stft_fast1k(*this, a, s);

@@ -240,3 +240,13 @@ def test_settings_grid_emulated(emu, n, hop, zp, window, reassign):
     """the (size, hop, zero padding, window, mode) grid the settings UI can reach, through whichever kernel
     tier the plan picks — caught a 341-thread launch (partial warp under full-mask collectives) for F = 4096."""
     cases.settings_grid_case(emu.api, n, hop, zp, window, reassign)
+
+@pytest.mark.parametrize("hop,frames,window", [(4096, 5, capi.WINDOW_BLACKMAN_HARRIS), (256, 7, capi.WINDOW_HANN), (1000, 3, capi.WINDOW_HAMMING)])
+def test_16k_kernel_on_chip(emu, hop, frames, window):
+    """stft_r64x.cu (N = 16384 reassigned: one CTA per frame, 64 x 64 x 4 transforms, TMEM park, bin-staged ordered column) vs the
+    oracle: more frames than emulated SMs (a CTA walks several frames: TMA phase bookkeeping), two lanes, hops off every grid."""
+    cfg = SpectrogramConfig(fft_size=16384, hop_size=hop, window=window, use_reassignment=True)
+    n = 32768 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(2, (n + 64) / 48000.0)[:, :n]
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 2 * frames and st["checked"] > 10000

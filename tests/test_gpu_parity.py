@@ -215,6 +215,34 @@ def test_cfg5_reassigned_batch(product, kernel):
     assert st["cols"] == 4 * ((96000 * 2 - 16384) // 2048 + 1)
 
 
+# ---------------------------------------------------------------- N = 16384 reassigned, the UI's largest size, on chip (stft_r64x.cu)
+@pytest.mark.gpu
+@pytest.mark.parametrize("hop,window", [(4096, capi.WINDOW_BLACKMAN_HARRIS), (256, capi.WINDOW_HANN), (2732, capi.WINDOW_BLACKMAN)])
+def test_size_16384_reassigned(product, hop, window):
+    """One CTA per frame, 64 x 64 x 4 transforms with the analysis input / S / nd parked in tensor memory; 300+ frames over 148 SMs so
+    every CTA walks several frames; vs the oracle, and the specialised kernel must be the one that ran."""
+    cfg = SpectrogramConfig(fft_size=16384, hop_size=hop, window=window, use_reassignment=True)
+    frames = 101
+    n = 32768 + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(3, (n + 64) / 48000.0)[:, :n]
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=product.api)
+    assert plan.kernel_generation == 8
+    st = cases.stft_parity(product.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 3 * frames and st["checked"] > 100000
+
+
+@pytest.mark.gpu
+def test_size_16384_specialised_and_generic_agree(product, monkeypatch):
+    """The on-chip kernel against the global-scratch generic tier on the GPU (pairwise metric)."""
+    cfg = SpectrogramConfig(fft_size=16384, hop_size=2048, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    n = 32768 + 20 * 2048
+    lanes = synth.cfg2_lanes(2, (n + 64) / 48000.0)[:, :n]
+    pa, ca = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=product.api).execute_host(lanes)
+    pb, cb = batch.StftPlan(cfg, kernel=capi.KERNEL_GENERIC, api=product.api).execute_host(lanes)
+    st = parity.compare_reassigned(pa, ca, pb, cb, sr=48000.0, fft_len=16384, window=16384, hop=2048)
+    assert st["cols"] == 42 and st["checked"] > 100000
+
+
 # ---------------------------------------------------------------- N = 4096 at the UI's small hops (N/16 ... N/128)
 @pytest.mark.parametrize("hop", [256, 64, 32])
 def test_cfg2_small_hops(product, hop):

@@ -17,7 +17,7 @@ from openmeters_b200._lib import api as lib_api  # noqa: E402
 from openmeters_b200.processors import SpectrogramConfig  # noqa: E402
 from tests.cases import settings_grid  # noqa: E402
 
-TIER = {1: "stft_fast.cu", 2: "stft_fast2.cu", 3: "stft_classic_fast.cu", 4: "stft_fast8k.cu", 5: "stft_fast2k.cu", 6: "stft_fast1k.cu", 7: "stft_r64.cu"}
+TIER = {1: "stft_fast.cu", 2: "stft_fast2.cu", 3: "stft_classic_fast.cu", 4: "stft_fast8k.cu", 5: "stft_fast2k.cu", 6: "stft_fast1k.cu", 7: "stft_r64.cu", 8: "stft_r64x.cu"}
 
 
 def timed(fn, iters=5, warm=2):
@@ -45,7 +45,8 @@ def main():
             (4096, 256, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 128, 1, capi.WINDOW_BLACKMAN_HARRIS, True),
             (4096, 64, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (4096, 32, 1, capi.WINDOW_BLACKMAN_HARRIS, True),
             (1024, 256, 1, capi.WINDOW_HANN, True), (1024, 32, 1, capi.WINDOW_HANN, True),
-            (8192, 2048, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (8192, 256, 1, capi.WINDOW_BLACKMAN_HARRIS, True)] + settings_grid()
+            (8192, 2048, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (8192, 256, 1, capi.WINDOW_BLACKMAN_HARRIS, True),
+            (16384, 4096, 1, capi.WINDOW_BLACKMAN_HARRIS, True), (16384, 256, 1, capi.WINDOW_HANN, True)] + settings_grid()
     if "--first" in sys.argv:  # e.g. --first 1: only the product default (short enough to run under ncu)
         grid = grid[:int(sys.argv[sys.argv.index("--first") + 1])]
     base = synth.cfg2_lanes(8, 4.0)
