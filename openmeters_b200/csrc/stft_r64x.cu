@@ -21,6 +21,10 @@
 // Same mathematics as the other reassigned kernels: packed real forward transform, fused Hilbert pair step, one
 // inverse (run as the forward transform on conjugated data), three windowed transforms, Auger-Flandrin offsets
 // (spectrogram/processor.rs:439-608).  Any hop that is a multiple of 4.
+//
+// The kernel is a template on the team size kT: kT = 256 is the above (N = 16384 = 64 x 64 x 4, one team per CTA); kT = 128 is
+// N = 8192 = 64 x 64 x 2 (pass C = radix-2 across a PAIR of threads), two independent 128-thread teams per CTA on two frames, the
+// window tables in shared memory — the cfg5 size, next to stft_fast8k.cu (OMB_R64X_8K=0|1 picks; profiles/r02_notes.md).
 #ifndef OMB_F32X2_CMUL
 #define OMB_F32X2_CMUL 0
 #endif
@@ -36,38 +40,59 @@ namespace omb {
 
 namespace {
 
-constexpr int kM = 16384;                // complex points per transform = window length N
-constexpr int kH = 2 * kM;               // samples per frame (Hilbert block)
-constexpr int kOff = (kH - kM) / 2;      // first centre sample
-constexpr int kT = 256;                  // threads
-constexpr int kRS = 260;                 // row stride of exchange 1 (float2): [k1][t], read back at stride 4
-constexpr int kRSb = 65;                 // exchange 2: [k1][a][k2] at k1 * 260 + a * 65 + k2;  pair rows: tau * 65 + j + 4 (tau >> 6)
-constexpr int kWSize = 64 * kRS + 16;    // float2 elements (pair rows reach 65 * 255 + 63 + 12)
-constexpr int kGroups = 33;              // bins tau + 256 j, j < 32, and bin 8192 (tau = 0, j = 32)
-constexpr int kWarps = kT / 32;
-constexpr unsigned kFrameBytes = kH * sizeof(float);
+template <int kT>
+struct Geo {
+  static constexpr int kM = 64 * kT;             // complex points per transform = window length N
+  static constexpr int kH = 2 * kM;              // samples per frame (Hilbert block)
+  static constexpr int kOff = (kH - kM) / 2;     // first centre sample
+  static constexpr int kA = kT / 64;             // radix of pass C = threads per sub-problem (4 or 2)
+  static constexpr int kD = 64 / kA;             // pass-C butterflies per thread
+  static constexpr int kTeams = 256 / kT;        // teams (frames in flight) per CTA
+  static constexpr int kRS = kT + kA;            // row stride of exchange 1 (float2): [k1][t], read back at stride kA — conflict-free
+  static constexpr int kSkew = 16 / kA;          // pair rows: tau * 65 + j + kSkew (tau >> 6): rows tau, tau + 64 on different banks
+  static constexpr int kWSize = 64 * kRS + 16;   // float2 elements of a team's buffer
+  static constexpr int kWarps = kT / 32;
+  static constexpr unsigned kFrameBytes = kH * sizeof(float);
+  static constexpr bool kWinSmem = kT == 128;    // window tables in shared memory (2 x 32 KB) / global memory (2 x 64 KB)
+};
+constexpr int kRSb = 65;                 // exchange 2: [k1][a][k2] at k1 * kRS + a * 65 + k2
+constexpr int kGroups = 33;              // bins tau + kT j, j < 32, and the Nyquist bin (tau = 0, j = 32)
 constexpr int kColC = 0, kColS = 128, kColNd = 192, kColSn = 224, kColsPerWarp = 256;  // as in stft_r64.cu
 
 struct R64xArgs {
   StftKernelArgs a;
-  const float2* tw1;    // global: [14][256]: rows 0..6 = W_16384^{t q}, q = 1..7; rows 7..13 = W_16384^{8 t q}
-  const float2* tw2;    // global: [14][4]:   the same rows of W_256^{a q}, a < 4
+  const float2* tw1;    // global: [14][kT]: rows 0..6 = W_M^{t q}, q = 1..7; rows 7..13 = W_M^{8 t q}
+  const float2* tw2;    // global: [14][kA]: the same rows of W_kT^{a q}, a < kA
   float norm_ac, norm_dc;
 };
 
-struct Smem {
-  alignas(16) float2 W[kWSize];
-  float2 tw1[14 * kT];
-  float2 tw2[14 * 4];
-  int cnt[(kGroups + 1) * kWarps];
-  int offs[(kGroups + 1) * kWarps + 1];
+template <int kT>
+struct TeamSmem {
+  alignas(16) float2 W[Geo<kT>::kWSize];
+  int cnt[(kGroups + 1) * Geo<kT>::kWarps];
+  int offs[(kGroups + 1) * Geo<kT>::kWarps + 2];
   float x0_xm[2];
   alignas(8) uint64_t mbar;
-  uint32_t tmem_base;
-  uint32_t pad_[1];
+  uint64_t pad_;
 };
-static_assert(sizeof(float2) * kWSize >= kFrameBytes, "the exchange buffer must hold a whole frame");
-static_assert(sizeof(float2) * kWSize >= 12 * (kM / 2 + 1), "the exchange buffer must hold a whole staged column");
+template <int kT>
+struct Smem {
+  TeamSmem<kT> team[Geo<kT>::kTeams];
+  float2 tw1[14 * kT];
+  float2 tw2[14 * 4];
+  uint32_t tmem_base;
+  uint32_t pad_[3];
+  // kWinSmem: float h[kM], dh[kM] follow
+};
+
+template <int kT>
+__device__ __forceinline__ void team_sync(int team) {
+#ifdef OMB_EMU
+  omb_emu::named_sync(1 + team, kT);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(kT) : "memory");
+#endif
+}
 
 __device__ __forceinline__ float2 cmul_s(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
@@ -87,37 +112,58 @@ __device__ __forceinline__ void twiddle63(float2 (&v)[64], const float2* tab, in
   }
 }
 
-// Passes A and B of the forward transform and the loads of pass C.  On entry the thread holds elements ta + 256 j (ta: the residue
-// class it owns, any bijection thread -> class); on return v[d + 16 a] holds the pass-C input (a < 4, d < 16) of the radix-4
-// butterfly whose outputs k3 = 0..3 are the bins tau + 256 (d + 16 k3), tau = (tid >> 2) + 64 (tid & 3).
-__device__ __forceinline__ void transform_ab(float2 (&v)[64], Smem& sm, int ta, int tid) {
+// Passes A and B of the forward transform and the loads of pass C.  On entry the thread holds elements ta + kT j (ta: the residue
+// class it owns, any bijection thread -> class); on return v[d + kD a] holds the pass-C input (a < kA, d < kD) of the radix-kA
+// butterfly whose outputs k3 are the bins tau + kT (d + kD k3), tau = (t / kA) + 64 (t % kA).
+template <int kT>
+__device__ __forceinline__ void transform_ab(float2 (&v)[64], float2* W, const float2* tw1, const float2* tw2, int ta, int t, int team) {
+  using G = Geo<kT>;
   f64pt::dft64<false>(v);
-  twiddle63(v, sm.tw1 + ta, kT);
-  __syncthreads();  // every earlier read of W (frame samples, partner rows, staging, the previous transform) is done
-  float2* wr = sm.W + ta;
+  twiddle63(v, tw1 + ta, kT);
+  team_sync<kT>(team);  // every earlier read of W (frame samples, partner rows, staging, the previous transform) is done
+  float2* wr = W + ta;
 #pragma unroll
-  for (int q = 0; q < 64; ++q) wr[q * kRS] = v[q];
-  __syncthreads();
-  const int k1 = tid >> 2, a = tid & 3;
-  const float2* rd = sm.W + k1 * kRS + a;
+  for (int q = 0; q < 64; ++q) wr[q * G::kRS] = v[q];
+  team_sync<kT>(team);
+  const int k1 = t / G::kA, a = t % G::kA;
+  const float2* rd = W + k1 * G::kRS + a;
 #pragma unroll
-  for (int b = 0; b < 64; ++b) v[b] = rd[4 * b];
+  for (int b = 0; b < 64; ++b) v[b] = rd[G::kA * b];
   f64pt::dft64<false>(v);
-  twiddle63(v, sm.tw2 + a, 4);
-  __syncthreads();  // all of exchange 1 has been read: exchange 2 reuses the buffer
-  float2* wq = sm.W + k1 * kRS + a * kRSb;
+  twiddle63(v, tw2 + a, 4);
+  team_sync<kT>(team);  // all of exchange 1 has been read: exchange 2 reuses the buffer
+  float2* wq = W + k1 * G::kRS + a * kRSb;
 #pragma unroll
   for (int k2 = 0; k2 < 64; ++k2) wq[k2] = v[k2];
-  __syncwarp();  // exchange 2 stays inside the quad (k1, 0..3) of one warp
-  const float2* rq = sm.W + k1 * kRS + a;  // this thread's c = a
+  __syncwarp();  // exchange 2 stays inside the kA threads (k1, 0..kA-1) of one warp
+  const float2* rq = W + k1 * G::kRS + a;  // this thread's c = a
 #pragma unroll
-  for (int d = 0; d < 16; ++d)
+  for (int d = 0; d < G::kD; ++d)
 #pragma unroll
-    for (int s = 0; s < 4; ++s) v[d + 16 * s] = rq[s * kRSb + 4 * d];
+    for (int s2 = 0; s2 < G::kA; ++s2) v[d + G::kD * s2] = rq[s2 * kRSb + G::kA * d];
 }
-template <int kPrune>
+// Pass C: radix-kA butterflies over (v[d], v[d + kD], ...); kPrune = kFirst9: only outputs j <= 32 (bins <= Nyquist), kMid8: only
+// 16 <= j < 48 (the centre half of the inverse), kAll.
+template <int kT, int kPrune>
 __device__ __forceinline__ void transform_c(float2 (&v)[64]) {
-  f64pt::dit_final<false, kPrune>(v);  // sixteen radix-4 butterflies over (v[d], v[d + 16], v[d + 32], v[d + 48]); pruned like stft_r64.cu
+  if (Geo<kT>::kA == 4) {
+    f64pt::dit_final<false, kPrune>(v);
+  } else {
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+      const float2 a0 = v[d], a1 = v[d + 32];
+      if (kPrune == f16::kAll) {
+        v[d] = f16::cadd2(a0, a1);
+        v[d + 32] = f16::csub2(a0, a1);
+      } else if (kPrune == f16::kFirst9) {
+        v[d] = f16::cadd2(a0, a1);
+        if (d == 0) v[32] = f16::csub2(a0, a1);
+      } else {  // kMid8: j = d (k3 = 0) for d >= 16, j = d + 32 (k3 = 1) for d < 16
+        if (d >= 16) v[d] = f16::cadd2(a0, a1);
+        else v[d + 32] = f16::csub2(a0, a1);
+      }
+    }
+  }
 }
 
 template <int N>
@@ -130,75 +176,90 @@ __device__ __forceinline__ void park_ld(uint32_t tcol, int col, float (&r)[N]) {
   tmem_ld<N>(tcol + col, r);
 }
 
-__global__ void __launch_bounds__(kT, 1) k_reassigned_r64x(R64xArgs ra) {
+template <int kT>
+__global__ void __launch_bounds__(256, 1) k_reassigned_r64x(R64xArgs ra) {
+  using G = Geo<kT>;
+  constexpr int kM = G::kM;
   OMB_DYN_SMEM(unsigned char, smem_raw);
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  Smem<kT>& sm = *reinterpret_cast<Smem<kT>*>(smem_raw);
+  float* sm_h = reinterpret_cast<float*>(smem_raw + sizeof(Smem<kT>));  // kWinSmem only
+  float* sm_dh = sm_h + kM;
   const StftKernelArgs& a = ra.a;
-  const int tid = threadIdx.x, lane_id = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, t = tid % kT, lane_id = tid & 31, warp = t >> 5;
+  const int team = __shfl_sync(0xffffffffu, tid / kT, 0);  // warp-uniform by construction; tells the compiler so
+  TeamSmem<kT>& ts = sm.team[team];
+  float2* W = ts.W;
   const ReassignConsts rc{a.bin_hz, a.max_hz, a.inv_2pi, a.inv_hop, a.latency_hops};
 
-  for (int i = tid; i < 14 * kT; i += kT) sm.tw1[i] = __ldg(&ra.tw1[i]);
+  for (int i = tid; i < 14 * kT; i += 256) sm.tw1[i] = __ldg(&ra.tw1[i]);
   if (tid < 14 * 4) sm.tw2[tid] = __ldg(&ra.tw2[tid]);
+  if (G::kWinSmem) {
+    for (int i = tid; i < kM; i += 256) {
+      sm_h[i] = __ldg(&a.win[i]);
+      sm_dh[i] = __ldg(&a.dwin[i]);
+    }
+  }
   if (tid < 32) tmem_alloc(&sm.tmem_base);
-  if (tid == 0) mbar_init(&sm.mbar, 1);
+  if (t == 0) mbar_init(&ts.mbar, 1);
   tmem_fence_before_sync();
   __syncthreads();
   tmem_fence_after_sync();
   const uint32_t tcol = tmem_addr(sm.tmem_base, (uint32_t)(tid >> 7) * kColsPerWarp);
 
   // per-thread constants
-  const int tau = (tid >> 2) + 64 * (tid & 3);  // bins tau + 256 j after a transform
-  float cos_t, sin_t;                            // th_tau = 2 pi tau / H
+  const int tau = (t / G::kA) + 64 * (t % G::kA);  // bins tau + kT j after a transform
+  float cos_t, sin_t;                              // th_tau = 2 pi tau / H
   sincospif((float)tau / (float)kM, &sin_t, &cos_t);
-  const float sign = (tid & 1) ? -1.0f : 1.0f;   // (-1)^n of the analysis point n = tid + 256 j
-  const float ramp0 = (float)tid - (float)(kM - 1) * 0.5f;
-  const int ptau = (kT - tau) & (kT - 1);        // owner class of the mirror bins M - k
-  auto row_of = [](int r) { return r * kRSb + 4 * (r >> 6); };  // pair rows: skewed so that rows r and r + 64 use different banks
+  const float sign = (t & 1) ? -1.0f : 1.0f;       // (-1)^n of the analysis point n = t + kT j
+  const float ramp0 = (float)t - (float)(kM - 1) * 0.5f;
+  const int ptau = (kT - tau) & (kT - 1);          // owner class of the mirror bins M - k
+  auto row_of = [](int r) { return r * kRSb + G::kSkew * (r >> 6); };
 
   const uint64_t per_lane = a.frames_per_lane - a.first_frame;
   const uint64_t total = per_lane * a.n_lanes;
+  const uint64_t stride = (uint64_t)gridDim.x * G::kTeams;
   auto frame_src = [&](uint64_t gi) {
     const uint64_t l = gi / per_lane, f = a.first_frame + gi % per_lane;
     return a.lanes + l * a.lane_stride + f * (uint64_t)a.hop;
   };
-  uint64_t g = blockIdx.x;
+  uint64_t g = (uint64_t)blockIdx.x * G::kTeams + team;
   unsigned phase = 0;
-  if (g < total && tid == 0) {
-    mbar_expect_tx(&sm.mbar, kFrameBytes);
-    bulk_g2s(sm.W, frame_src(g), kFrameBytes, &sm.mbar);
+  if (g < total && t == 0) {
+    mbar_expect_tx(&ts.mbar, G::kFrameBytes);
+    bulk_g2s(W, frame_src(g), G::kFrameBytes, &ts.mbar);
   }
 
-  for (; g < total; g += gridDim.x) {
+  for (; g < total; g += stride) {
     const uint64_t lane = g / per_lane, f = a.first_frame + g % per_lane;
-    mbar_wait(&sm.mbar, phase);
+    mbar_wait(&ts.mbar, phase);
     phase ^= 1u;
     float2 v[64];
     {
-      const float* wf = reinterpret_cast<const float*>(sm.W);
+      const float* wf = reinterpret_cast<const float*>(W);
       float xc[64];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) xc[j] = wf[kOff + tid + kT * j];
+      for (int j = 0; j < 64; ++j) xc[j] = wf[G::kOff + t + kT * j];
       park_st<64>(tcol, kColC, xc);
-      const float2* wz = sm.W + tid;  // F input: z[n] = x[2n] + j x[2n+1], n = tid + 256 j
+      const float2* wz = W + t;  // F input: z[n] = x[2n] + j x[2n+1], n = t + kT j
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] = wz[kT * j];
     }
 #pragma unroll 1
     for (int tr = 0; tr < 5; ++tr) {
-      int ta = tid;
+      int ta = t;
       if (tr == 1) {
-        // ---- X: conj(Q[k]), Q[k] = cos(th_k) conj(Z[M-k]) + j sin(th_k) Z[k], k = tau + 256 j, th_k = th_tau + 2 pi j / 128
-        __syncthreads();
-        float2* row = sm.W + row_of(tau);
+        // ---- X: conj(Q[k]), Q[k] = cos(th_k) conj(Z[M-k]) + j sin(th_k) Z[k], k = tau + kT j, th_k = th_tau + 2 pi j / 128
+        team_sync<kT>(team);
+        float2* row = W + row_of(tau);
 #pragma unroll
         for (int j = 0; j < 64; ++j) row[j] = v[j];
         if (tau == 0) {
-          sm.x0_xm[0] = v[0].x + v[0].y;
-          sm.x0_xm[1] = v[0].x - v[0].y;
+          ts.x0_xm[0] = v[0].x + v[0].y;
+          ts.x0_xm[1] = v[0].x - v[0].y;
         }
-        __syncthreads();
-        // partner of k = tau + 256 j: row 256 - tau, column 63 - j; for tau = 0 row 0, column 64 - j (j = 0: don't-care, DC is zeroed)
-        const float2* prow = tau == 0 ? sm.W + 1 : sm.W + row_of(ptau);
+        team_sync<kT>(team);
+        // partner of k = tau + kT j: row kT - tau, column 63 - j; for tau = 0 row 0, column 64 - j (j = 0: don't-care, DC is zeroed)
+        const float2* prow = tau == 0 ? W + 1 : W + row_of(ptau);
         constexpr int kPc = 8;
         float2 zp[2][kPc];
 #pragma unroll
@@ -222,35 +283,35 @@ __global__ void __launch_bounds__(kT, 1) k_reassigned_r64x(R64xArgs ra) {
         if (tau == 0) v[0] = make_float2(0.0f, 0.0f);
         ta = tau;
       } else if (tr >= 2) {
-        // ---- G input: c[n] w[n], n = tid + 256 j, w = h, dh, t*h (processor.rs:601-608, formed on the fly, bit-identical)
+        // ---- G input: c[n] w[n], n = t + kT j, w = h, dh, t*h (processor.rs:601-608, formed on the fly, bit-identical)
         float c[128];
         park_ld<128>(tcol, kColC, c);
-        const float* tab = (tr == 3 ? a.dwin : a.win) + tid;
+        const float* tab = (G::kWinSmem ? (tr == 3 ? sm_dh : sm_h) : (tr == 3 ? a.dwin : a.win)) + t;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
-          float wv = __ldg(&tab[kT * j]);
+          float wv = G::kWinSmem ? tab[kT * j] : __ldg(&tab[kT * j]);
           if (tr == 4) wv *= ramp0 + (float)(kT * j);
           v[j] = f16::cscale2(make_float2(c[2 * j], c[2 * j + 1]), wv);
         }
       }
-      transform_ab(v, sm, ta, tid);
+      transform_ab<kT>(v, W, sm.tw1, sm.tw2, ta, t, team);
       if (tr == 0) {
-        transform_c<f16::kAll>(v);
+        transform_c<kT, f16::kAll>(v);
       } else if (tr == 1) {
-        transform_c<f16::kMid8>(v);    // outputs 16..47: the centre half
+        transform_c<kT, f16::kMid8>(v);    // outputs 16..47: the centre half
       } else {
-        transform_c<f16::kFirst9>(v);  // outputs 0..32: bins <= Nyquist
+        transform_c<kT, f16::kFirst9>(v);  // outputs 0..32: bins <= Nyquist
       }
       if (tr == 1) {
-        // ---- centre half of the inverse: y[m] = conj(v), m = tau + 256 j, j = 16..47 -> staging as float2[m - 4096]; then every
-        //      thread collects Im c of its analysis points n = tid + 256 j and parks c[n] = (M x[off + n] + bias) + j Im c[n]
-        __syncthreads();
-        float2* y2 = sm.W + tau;
+        // ---- centre half of the inverse: y[m] = conj(v), m = tau + kT j, j = 16..47 -> staging as float2[m - M/4]; then every
+        //      thread collects Im c of its analysis points n = t + kT j and parks c[n] = (M x[off + n] + bias) + j Im c[n]
+        team_sync<kT>(team);
+        float2* y2 = W + tau;
 #pragma unroll
         for (int q = 16; q < 48; ++q) y2[kT * (q - 16)] = make_float2(v[q].x, -v[q].y);
-        __syncthreads();
-        const float bias = sign * 0.5f * sm.x0_xm[1] - 0.5f * sm.x0_xm[0];
-        const float* yf = reinterpret_cast<const float*>(sm.W) + tid;
+        team_sync<kT>(team);
+        const float bias = sign * 0.5f * ts.x0_xm[1] - 0.5f * ts.x0_xm[0];
+        const float* yf = reinterpret_cast<const float*>(W) + t;
         float c[128];
         {
           float xc[64];
@@ -284,9 +345,9 @@ __global__ void __launch_bounds__(kT, 1) k_reassigned_r64x(R64xArgs ra) {
       }
     }
     // ---- R: reassigned points of this thread's bins, staged by bin in W (power < 0 marks a dropped bin)
-    __syncthreads();  // every quad has finished reading exchange 2
+    team_sync<kT>(team);  // every thread group has finished reading exchange 2
     {
-      float* stage = reinterpret_cast<float*>(sm.W);
+      float* stage = reinterpret_cast<float*>(W);
       float nd[32], sn[4];
       park_ld<32>(tcol, kColNd, nd);
       park_ld<4>(tcol, kColSn, sn);
@@ -316,29 +377,29 @@ __global__ void __launch_bounds__(kT, 1) k_reassigned_r64x(R64xArgs ra) {
         }
       }
     }
-    __syncthreads();
-    // ---- ordered compaction in natural order: thread tid, group q -> bin tid + 256 q (thread 0 also bin 8192)
+    team_sync<kT>(team);
+    // ---- ordered compaction in natural order: thread t, group q -> bin t + kT q (thread 0 also the Nyquist bin)
     {
-      const float* stage = reinterpret_cast<const float*>(sm.W);
+      const float* stage = reinterpret_cast<const float*>(W);
       unsigned keep_lo = 0, keep_hi = 0;
 #pragma unroll
       for (int q = 0; q < kGroups; ++q) {
-        const int bin = tid + kT * q;
-        const bool k = (q < 32 || tid == 0) && stage[3 * (q < 32 ? bin : kM / 2) + 2] >= 0.0f;
+        const int bin = t + kT * q;
+        const bool k = (q < 32 || t == 0) && stage[3 * (q < 32 ? bin : kM / 2) + 2] >= 0.0f;
         const unsigned m = __ballot_sync(0xffffffffu, k);
-        if (lane_id == 0) sm.cnt[q * kWarps + warp] = __popc(m);
+        if (lane_id == 0) ts.cnt[q * G::kWarps + warp] = __popc(m);
         if (k) {
           if (q < 32) keep_lo |= 1u << q; else keep_hi = 1u;
         }
       }
-      __syncthreads();
-      if (warp == 0) {  // exclusive scan of the 33 x 8 warp counts (order: group, warp), 9 entries per lane
-        constexpr int kN = kGroups * kWarps, kPer = (kN + 31) / 32;
+      team_sync<kT>(team);
+      if (warp == 0) {  // exclusive scan of the 33 x kWarps warp counts (order: group, warp)
+        constexpr int kN = kGroups * G::kWarps, kPer = (kN + 31) / 32;
         int c[kPer], tot = 0;
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
           const int idx = lane_id * kPer + i;
-          c[i] = idx < kN ? sm.cnt[idx] : 0;
+          c[i] = idx < kN ? ts.cnt[idx] : 0;
           tot += c[i];
         }
         int incl = tot;
@@ -351,12 +412,12 @@ __global__ void __launch_bounds__(kT, 1) k_reassigned_r64x(R64xArgs ra) {
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
           const int idx = lane_id * kPer + i;
-          if (idx < kN) sm.offs[idx] = run;
+          if (idx < kN) ts.offs[idx] = run;
           run += c[i];
         }
-        if (lane_id == 31) sm.offs[kN] = incl;
+        if (lane_id == 31) ts.offs[kN] = incl;
       }
-      __syncthreads();
+      team_sync<kT>(team);
       const uint64_t slot = lane * a.frames_per_lane + f;
       float* out = reinterpret_cast<float*>(a.out_points + slot * a.point_stride);
       const unsigned lt_mask = (1u << lane_id) - 1u;
@@ -365,54 +426,68 @@ __global__ void __launch_bounds__(kT, 1) k_reassigned_r64x(R64xArgs ra) {
         const bool k = q < 32 ? ((keep_lo >> q) & 1u) != 0 : keep_hi != 0;
         const unsigned m = __ballot_sync(0xffffffffu, k);
         if (k) {
-          const float* src = stage + 3 * (q < 32 ? tid + kT * q : kM / 2);
-          float* o = out + 3 * (sm.offs[q * kWarps + warp] + __popc(m & lt_mask));
+          const float* src = stage + 3 * (q < 32 ? t + kT * q : kM / 2);
+          float* o = out + 3 * (ts.offs[q * G::kWarps + warp] + __popc(m & lt_mask));
           o[0] = src[0];
           o[1] = src[1];
           o[2] = src[2];
         }
       }
-      if (tid == 0) a.out_counts[slot] = (uint32_t)sm.offs[kGroups * kWarps];
+      if (t == 0) a.out_counts[slot] = (uint32_t)ts.offs[kGroups * G::kWarps];
     }
     // ---- the staged column has been read: the next frame may land
-    __syncthreads();
-    if (tid == 0 && g + gridDim.x < total) {
+    team_sync<kT>(team);
+    if (t == 0 && g + stride < total) {
       fence_async_smem();
-      mbar_expect_tx(&sm.mbar, kFrameBytes);
-      bulk_g2s(sm.W, frame_src(g + gridDim.x), kFrameBytes, &sm.mbar);
+      mbar_expect_tx(&ts.mbar, G::kFrameBytes);
+      bulk_g2s(W, frame_src(g + stride), G::kFrameBytes, &ts.mbar);
     }
   }
   __syncthreads();
   if (tid < 32) tmem_free(sm.tmem_base);
 }
 
-size_t smem_bytes() { return sizeof(Smem); }
+template <int kT>
+size_t smem_bytes() { return sizeof(Smem<kT>) + (Geo<kT>::kWinSmem ? 2 * sizeof(float) * Geo<kT>::kM : 0); }
+
+// N = 8192: OMB_R64X_8K=1 / 0 pins this kernel / stft_fast8k.cu; unpinned, stft_fast8k.cu keeps the hops its ring handles with
+// warp-uniform rows (multiples of 512 up to 2048: the two are within 2 % of each other there, profiles/r02_notes.md) and this
+// kernel takes every other multiple of 4.
+bool r64x_for_8k(uint64_t hop) {
+  static const int v = [] { const char* e = getenv("OMB_R64X_8K"); return e ? atoi(e) : -1; }();
+  if (v >= 0) return v != 0;
+  return (hop % 512) != 0 || hop > 2048;
+}
 
 }  // namespace
 
 bool stft_r64x_supported(const StftConfig& cfg, const DeviceInfo& dev) {
-  if (!cfg.reassign || cfg.window != (uint64_t)kM || cfg.zero_pad != 1) return false;
+  if (!cfg.reassign || cfg.zero_pad != 1) return false;
+  if (cfg.window != 16384u && !(cfg.window == 8192u && r64x_for_8k(cfg.hop))) return false;
   if (cfg.hop < 4 || (cfg.hop % 4) != 0) return false;  // bulk copies start at f * hop floats: 16-byte aligned
   if (dev.cc_major != 0 && dev.cc_major < 10) return false;  // tcgen05 / TMEM
-  return dev.max_smem_optin == 0 || smem_bytes() <= (size_t)dev.max_smem_optin;
+  const size_t need = cfg.window == 16384u ? smem_bytes<256>() : smem_bytes<128>();
+  return dev.max_smem_optin == 0 || need <= (size_t)dev.max_smem_optin;
 }
 
 int stft_r64x_prepare(StftPlan& plan) {
+  const int kT = (int)(plan.cfg.window / 64), kA = kT / 64, M = 64 * kT;
   std::vector<float2> tab(14 * kT + 14 * 4);
   const double tau = 6.28318530717958647692;
   for (int i = 0; i < 14; ++i) {
     const int q = i < 7 ? i + 1 : 8 * (i - 6);
     for (int t = 0; t < kT; ++t) {
-      const double ang = -tau * (double)((t * q) % kM) / (double)kM;
+      const double ang = -tau * (double)((t * q) % M) / (double)M;
       tab[i * kT + t] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
     for (int a = 0; a < 4; ++a) {
-      const double ang = -tau * (double)((a * q) % 256) / 256.0;
+      const double ang = a < kA ? -tau * (double)((a * q) % kT) / (double)kT : 0.0;
       tab[14 * kT + i * 4 + a] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
   }
   OMB_TRY(plan.d_r64_tables.upload(tab, plan.stream));
-  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_r64x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_r64x<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<256>()));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_r64x<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128>()));
   return OMB_OK;
 }
 
@@ -421,6 +496,7 @@ int launch_stft_r64x(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   if (per_lane == 0 || a.n_lanes == 0) return OMB_OK;
   if ((reinterpret_cast<uintptr_t>(a.lanes) & 15u) != 0 || (a.lane_stride % 4) != 0)
     return fail(OMB_ERR_INVALID, "specialised STFT kernel needs 16-byte aligned lanes (pointer and lane_stride % 4 == 0)");
+  const int kT = (int)(a.window / 64);
   R64xArgs ra{};
   ra.a = a;
   ra.tw1 = plan.d_r64_tables.ptr;
@@ -428,8 +504,13 @@ int launch_stft_r64x(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   ra.norm_ac = plan.h_norm.size() > 1 ? plan.h_norm[1] : plan.h_norm[0];
   ra.norm_dc = plan.h_norm[0];
   const uint64_t total = per_lane * a.n_lanes;
-  const unsigned grid = (unsigned)std::min<uint64_t>(total, (uint64_t)std::max(plan.dev.sm_count, 1));
-  OMB_LAUNCH(k_reassigned_r64x, dim3(grid), dim3(kT), smem_bytes(), s, ra);
+  const uint64_t teams = kT == 256 ? 1 : 2;
+  const unsigned grid = (unsigned)std::min<uint64_t>((total + teams - 1) / teams, (uint64_t)std::max(plan.dev.sm_count, 1));
+  if (kT == 256) {
+    OMB_LAUNCH(k_reassigned_r64x<256>, dim3(grid), dim3(256), smem_bytes<256>(), s, ra);
+  } else {
+    OMB_LAUNCH(k_reassigned_r64x<128>, dim3(grid), dim3(256), smem_bytes<128>(), s, ra);
+  }
   OMB_CHECK_LAUNCH();
   return OMB_OK;
 }

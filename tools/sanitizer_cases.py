@@ -35,7 +35,7 @@ def main():
         cases.append((4096, 1000, 7))
     cases.append((16384, 4096, 8))  # stft_r64x.cu
     if not only_new:
-        cases += [(8192, 2048, 4), (8192, 256, 4), (2048, 64, 5), (2048, 512, 5), (1024, 32, 6), (1024, 256, 6)]
+        cases += [(8192, 2048, 4), (8192, 256, 8), (2048, 64, 5), (2048, 512, 5), (1024, 32, 6), (1024, 256, 6)]
     for n, hop, gen in cases:
         cfg = SpectrogramConfig(fft_size=n, hop_size=hop, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
         frames = 11
