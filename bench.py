@@ -291,7 +291,7 @@ class StftWorkload(Workload):
             self.out = torch.empty((k * F, self.bins), dtype=torch.int16, device=dev)
             self.cnt = None
         tiers = {0: "k_reassigned_smem / generic", 1: "k_reassigned_fast", 2: "k_reassigned_fast2", 3: "k_classic_1024", 4: "k_reassigned_8k",
-                 5: "k_reassigned_fast2k", 6: "k_reassigned_fast1k"}
+                 5: "k_reassigned_fast2k", 6: "k_reassigned_fast1k", 7: "k_reassigned_r64", 8: "k_reassigned_r64x"}
         self.kernel = tiers.get(self.plan.kernel_generation, "?")
         self.out_bytes = self.out.numel() * self.out.element_size()
 
@@ -416,6 +416,16 @@ def make_workload(name, args, world):
         return StftWorkload("cfg1", cfg, 256 * world, 1 << 18, "weak", "STFT frames/s (1024-pt Hann, hop 512, classic u16 dB columns)",
                             "cfg1: 1024-pt Hann classic STFT hop 512, 48 kHz mono (Mid) lanes (BASELINE configs[0])",
                             lambda S_: synth.cfg2_lanes(8, S_ / 48000.0)[:, :S_], None, 256)
+    if name == "n16384":  # the settings UI's largest size (ui/settings.rs:146-147): on chip since round 2 (stft_r64x.cu)
+        cfg = SpectrogramConfig(fft_size=16384, hop_size=4096, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+        return StftWorkload("n16384", cfg, 32, 32768 + 339 * 4096, "strong", "STFT frames/s (16384-pt, hop 4096, Blackman-Harris, time-frequency reassigned)",
+                            "16384-pt BH reassigned STFT hop 4096, 48 kHz mono lanes (largest size of the settings UI)",
+                            lambda S_: synth.cfg2_lanes(8, S_ / 48000.0)[:, :S_], 5 * 5 * 16384 * 14 + 16384 * 30 + 8193 * 40)
+    if name == "n2048":   # the product's default spectrogram configuration (spectrogram/processor.rs:47-59)
+        cfg = SpectrogramConfig(fft_size=2048, hop_size=64, window=capi.WINDOW_HANN, use_reassignment=True)
+        return StftWorkload("n2048", cfg, 64, 4096 + 1023 * 64, "strong", "STFT frames/s (2048-pt, hop 64, Hann, time-frequency reassigned)",
+                            "2048-pt Hann reassigned STFT hop 64, 48 kHz mono lanes (the product's default configuration)",
+                            lambda S_: synth.cfg2_lanes(8, S_ / 48000.0)[:, :S_], 5 * 5 * 2048 * 11 + 2048 * 30 + 1025 * 40)
     if name == "cfg4":
         return SpectrumWorkload(128, args.cfg4_seconds * 48000)
     if name == "cfg3":
@@ -753,7 +763,7 @@ def run_e2e_image(args, wl, api, torch, dev, pin_in, k, units_job, allmax, barri
 def run_secondary(args, api, torch, dev, stream, peak_gbs):
     """A few milliseconds each: the other BASELINE configs, device-resident, CUDA events (SURVEY §8d's secondary metrics)."""
     out = {}
-    for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
+    for name in ("cfg1", "cfg3", "cfg4", "cfg5", "n2048", "n16384"):
         sub = argparse.Namespace(**vars(args))
         sub.cfg5_lanes, sub.cfg5_frames, sub.cfg4_seconds = 32, 505, 10
         wl = make_workload(name, sub, 1)
