@@ -46,6 +46,22 @@ def test_emulated_kernel_reassigned_against_float64(emu):
                             exact.flat_tolerances(n=4096, hop=1024, sr=48000.0), "emulated cfg2 kernel")
 
 
+@pytest.mark.parametrize("n,hop,kind,sr", [(4096, 1000, capi.WINDOW_BLACKMAN_HARRIS, 48000.0),    # stft_r64.cu (radix-64 teams, TMEM park)
+                                          (16384, 4096, capi.WINDOW_BLACKMAN_HARRIS, 48000.0),  # stft_r64x.cu<256> (64 x 64 x 4)
+                                          (8192, 1000, capi.WINDOW_HANN, 96000.0)])             # stft_r64x.cu<128> (64 x 64 x 2)
+def test_emulated_team_kernels_against_float64(emu, n, hop, kind, sr):
+    """The round-2 team kernels under the emulator against exact math, with the oracle measured beside them (rule of tests/exact.py)."""
+    lanes = synth.cfg2_lanes(2, (2 * n + 6 * hop + 16) / 48000.0)[:, :2 * n + 6 * hop]
+    cfg = SpectrogramConfig(sample_rate=sr, fft_size=n, hop_size=hop, window=kind, use_reassignment=True)
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=emu.api)
+    assert plan.kernel_generation in (7, 8)
+    pa, ca = plan.execute_host(lanes)
+    pb, cb = oracle_py.stft_batch(cfg, lanes)
+    kw = dict(n=n, hop=hop, kind=kind, sr=sr)
+    exact.assert_reassigned(exact.reassigned_table(pa, ca, lanes, **kw), exact.reassigned_table(pb, cb, lanes, **kw),
+                            exact.flat_tolerances(n=n, hop=hop, sr=sr), f"emulated team kernel N={n}")
+
+
 @pytest.mark.parametrize("n,hop,kind,zp", [(1024, 512, capi.WINDOW_HANN, 1), (2048, 256, capi.WINDOW_BLACKMAN, 2)])
 def test_oracle_classic_against_float64(n, hop, kind, zp):
     st2 = synth.cfg1_stereo(4.0).reshape(-1, 2)

@@ -40,8 +40,22 @@ def test_cfg5_reassigned_against_float64(product):
     _reassigned_case(product.api, lanes, 8192, 2048, capi.WINDOW_BLACKMAN_HARRIS, 96000.0)
 
 
+def test_size_16384_reassigned_against_float64(product):
+    """stft_r64x.cu (64 x 64 x 4 transforms) against exact math; the scaling of the flat rule with the transform length is the one of
+    tests/cases.py::settings_grid_case (an f32 transform of 2^14 points is where the SURVEY's 1e-5 is stated)."""
+    lanes = synth.cfg2_lanes(2, (32768 + 40 * 4096) / 48000.0)
+    ti, to = _reassigned_case(product.api, lanes, 16384, 4096, capi.WINDOW_BLACKMAN_HARRIS, 48000.0, capi.KERNEL_FAST)
+    assert ti.unaligned == 0
+
+
+def test_size_8192_team_kernel_against_float64(product):
+    """N = 8192 at a hop off the 512 grid: stft_r64x.cu<128> (64 x 64 x 2 transforms, two teams per CTA)."""
+    lanes = synth.cfg5_lanes(2, 16384 + 60 * 1000)
+    _reassigned_case(product.api, lanes, 8192, 1000, capi.WINDOW_BLACKMAN_HARRIS, 96000.0, capi.KERNEL_FAST)
+
+
 @pytest.mark.parametrize("n,hop,kind", [(2048, 64, capi.WINDOW_HANN), (1024, 32, capi.WINDOW_HANN), (4096, 256, capi.WINDOW_HAMMING),
-                                        (2048, 512, capi.WINDOW_RECTANGULAR)])
+                                        (4096, 1000, capi.WINDOW_BLACKMAN), (2048, 512, capi.WINDOW_RECTANGULAR)])
 def test_other_sizes_reassigned_against_float64(product, n, hop, kind):
     lanes = synth.cfg2_lanes(2, (2 * n + 150 * hop) / 48000.0)
     _reassigned_case(product.api, lanes, n, hop, kind, 48000.0)
