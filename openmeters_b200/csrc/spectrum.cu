@@ -398,6 +398,14 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
   const uint64_t budget_floats = (64ull << 20) / 4;
   uint64_t chunk = std::max<uint64_t>(1, budget_floats / std::max<uint64_t>(1, (uint64_t)n_lanes * bins));
   chunk = std::min(chunk, hops);
+  // Power stage: with at least a few hops per lane, the front half of the fused kernel (staging ring, one pass over the PCM, hop
+  // segments as work items; OMB_SPECTRUM_RING_POWER=0 keeps the frame-per-CTA kernel, which re-reads every sample N / hop times)
+  const char* rp_env = getenv("OMB_SPECTRUM_RING_POWER");
+  const bool ring_power_env = !(rp_env && rp_env[0] == '0');
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(d_lanes) & 15u) == 0 && (lane_stride % 4) == 0 && (cfg.hop % 4) == 0;
+  const bool ring_power = fast16k && fused16k && aligned16 && ring_power_env && hops >= 4;
+  // (Running the power stage of chunk i + 1 on a side stream under the smoothing stage of chunk i was measured: nothing — the
+  // power kernel's CTAs take every SM's registers, the two stages cannot co-reside; profiles/r02_notes.md.)
   OMB_TRY(d_power.reserve((size_t)((uint64_t)n_lanes * chunk * bins)));
   float* state = nullptr;
   if (cfg.averaging != OMB_AVG_NONE) {
@@ -406,7 +414,9 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
     state = d_state.ptr;
   }
   if (d_peak_bin) OMB_TRY(keys_begin(*this, hops * n_lanes, s));
-  if (fast16k) {  // hop-block sums for DC removal: once for the whole batch, chunks index into them
+  if (ring_power) {
+    OMB_TRY(spectrum_fast_frame_means(*this, d_lanes, lane_stride, n_lanes, hops, s));
+  } else if (fast16k) {  // hop-block sums for DC removal: once for the whole batch, chunks index into them
     OMB_TRY(spectrum_fast_block_sums(*this, d_lanes, lane_stride, n_lanes, hops, s));
     ext_bsum_blocks = hops - 1 + cfg.fft_size / cfg.hop;
   }
@@ -414,7 +424,8 @@ int SpectrumPlan::execute_device(const float* d_lanes, uint32_t n_lanes, uint64_
   for (uint64_t h0 = 0; h0 < hops && rc >= 0; h0 += chunk) {
     const uint64_t n = std::min(chunk, hops - h0);
     ext_block_off = h0;
-    rc = power_device(d_lanes + h0 * cfg.hop, n_lanes, n, lane_stride, d_power.ptr, s);
+    if (ring_power) rc = launch_spectrum_fused_power(*this, d_lanes + h0 * cfg.hop, n_lanes, n, lane_stride, d_power.ptr, h0, hops, s);
+    else rc = power_device(d_lanes + h0 * cfg.hop, n_lanes, n, lane_stride, d_power.ptr, s);
     if (rc >= 0) rc = smooth_launch(*this, d_power.ptr, n_lanes, n, state, d_weighted, d_raw, d_peak_bin ? d_keys.ptr : nullptr, true, hops, h0, s);
   }
   ext_bsum_blocks = 0;

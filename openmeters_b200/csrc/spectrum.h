@@ -99,6 +99,9 @@ int spectrum_fast_prepare(SpectrumPlan& p);
 int launch_spectrum_power_fast(SpectrumPlan& p, SpectrumPowerArgs& a, cudaStream_t s);
 int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lanes, uint64_t hops, uint64_t lane_stride, float* d_weighted,
                           float* d_raw, int32_t* d_peak_bin, cudaStream_t s);
+int launch_spectrum_fused_power(SpectrumPlan& p, const float* d_lanes, uint32_t n_lanes, uint64_t hops, uint64_t lane_stride, float* d_power,
+                                uint64_t h0, uint64_t hops_total, cudaStream_t s);
+int spectrum_fast_frame_means(SpectrumPlan& p, const float* d_lanes, uint64_t lane_stride, uint32_t n_lanes, uint64_t hops, cudaStream_t s);
 int spectrum_fast_block_sums(SpectrumPlan& p, const float* d_lanes, uint64_t lane_stride, uint32_t n_lanes, uint64_t hops, cudaStream_t s);
 
 }  // namespace omb

@@ -179,7 +179,13 @@ struct SpecFusedArgs {
   float alpha, decay, state_floor, floor_db;
   float norm_ac, norm_dc;
   uint32_t ring_len;
+  // work items: (lane, hop segment).  The smoothing modes walk whole lanes (segs = 1: their state lives in registers across hops);
+  // kPowerOnly splits every lane into `segs` segments of `seg_len` hops — the power spectrum has no state.
+  uint32_t segs;
+  uint64_t seg_len;
+  uint64_t means_stride;                       // hops of the whole batch (the means of lane l start at l * means_stride)
 };
+constexpr int kPowerOnly = 3;                  // kMode beyond OMB_AVG_*: store the normalised power spectrum (two-kernel path)
 
 struct SmemF {
   float2 W[2][kWSize];
@@ -268,6 +274,10 @@ struct FusedConsts {  // kernel arguments the epilogue reads, copied to register
 template <int kMode>
 __device__ __forceinline__ void fused_bin(const FusedConsts& c, float p, float& st, unsigned bin, float aw, float* ow, float* orw, bool cand,
                                           unsigned long long& best) {
+  if (kMode == kPowerOnly) {  // the smoothing kernel (spectrum.cu) takes it from here
+    *ow = p;
+    return;
+  }
   float v;
   if (kMode == OMB_AVG_EXPONENTIAL) {  // spectrum/processor.rs:366-377
     st = st <= 0.0f ? p : __fadd_rn(__fmul_rn(st, c.alpha), __fmul_rn(p, c.one_minus_alpha));
@@ -359,9 +369,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
   const float norm_ac = 0.25f * fa.norm_ac, norm_dc = 0.25f * fa.norm_dc;
   __syncthreads();
 
-  for (uint32_t lane = blockIdx.x; lane < a.n_lanes; lane += gridDim.x) {
-    const float* x = a.lanes + (uint64_t)lane * a.lane_stride;
-    const float* means = fa.means + (uint64_t)lane * a.hops;
+  for (uint64_t item = blockIdx.x; item < (uint64_t)a.n_lanes * fa.segs; item += gridDim.x) {
+    const uint32_t lane = (uint32_t)(item / fa.segs);
+    const uint64_t h_begin = (item % fa.segs) * fa.seg_len;
+    const uint64_t h_end = h_begin + fa.seg_len < a.hops ? h_begin + fa.seg_len : a.hops;
+    if (h_begin >= h_end) continue;
+    const float* x = a.lanes + (uint64_t)lane * a.lane_stride + h_begin * (uint64_t)hop;
+    const float* means = fa.means + (uint64_t)lane * fa.means_stride;
     float st[kSlots][4];
     float st_mid[2] = {0.0f, 0.0f};  // bins 2048 and 6144 (aa = 2048), thread 0 only
 #pragma unroll
@@ -374,25 +388,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
     if (kPlanar) f_ring_fetch_planar(plane_e, plane_o, L, 0, x, kN);
     else f_ring_fetch(ring, L, 0, x, kN);
     f_async_commit_wait(false);
-    float mean_next = __ldg(&means[0]);
-    for (uint64_t h = 0; h < a.hops; ++h) {
+    float mean_next = __ldg(&means[h_begin]);
+    for (uint64_t h = h_begin; h < h_end; ++h) {
       f_async_commit_wait(true);
       __syncthreads();  // ring holds frame h; everybody is done with frame h - 1 (ring, W, wkey[(h - 1) & 1] complete)
-      if (h + 1 < a.hops) {
+      if (h + 1 < h_end) {
         int p0 = r0 + kN;
         p0 -= (p0 >= L) ? L : 0;
-        if (kPlanar) f_ring_fetch_planar(plane_e, plane_o, L, p0, x + h * (uint64_t)hop + kN, hop);
-        else f_ring_fetch(ring, L, p0, x + h * (uint64_t)hop + kN, hop);
+        if (kPlanar) f_ring_fetch_planar(plane_e, plane_o, L, p0, x + (h - h_begin) * (uint64_t)hop + kN, hop);
+        else f_ring_fetch(ring, L, p0, x + (h - h_begin) * (uint64_t)hop + kN, hop);
       }
       f_async_commit_wait(false);
-      if (fa.peak_bin && h > 0 && tid == 0) {  // finish the previous hop's arg-max
+      if (fa.peak_bin && h > h_begin && tid == 0) {  // finish the previous hop's arg-max
         unsigned long long best = 0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) best = sm.wkey[(h - 1) & 1][w] > best ? sm.wkey[(h - 1) & 1][w] : best;
         fa.peak_bin[(uint64_t)lane * a.hops + h - 1] = best ? (int32_t)(best & 0xffffffffu) : -1;
       }
       const float mean = mean_next;
-      if (h + 1 < a.hops) mean_next = __ldg(&means[h + 1]);
+      if (h + 1 < h_end) mean_next = __ldg(&means[h + 1]);
       const float* lo = ring + r0;
       const float* hi = lo - L;
       const int split = L - r0;  // multiple of 4 (hop % 4 == 0): a float2 at an even offset never straddles the wrap
@@ -481,10 +495,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
       r0 -= (r0 >= L) ? L : 0;
     }
     __syncthreads();
-    if (fa.peak_bin && a.hops > 0 && tid == 0) {
+    if (fa.peak_bin && tid == 0) {
       unsigned long long best = 0;
-      for (int w = 0; w < kThreads / 32; ++w) best = sm.wkey[(a.hops - 1) & 1][w] > best ? sm.wkey[(a.hops - 1) & 1][w] : best;
-      fa.peak_bin[(uint64_t)lane * a.hops + a.hops - 1] = best ? (int32_t)(best & 0xffffffffu) : -1;
+      for (int w = 0; w < kThreads / 32; ++w) best = sm.wkey[(h_end - 1) & 1][w] > best ? sm.wkey[(h_end - 1) & 1][w] : best;
+      fa.peak_bin[(uint64_t)lane * a.hops + h_end - 1] = best ? (int32_t)(best & 0xffffffffu) : -1;
     }
     __syncthreads();
   }
@@ -566,6 +580,9 @@ int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lane
   fa.norm_ac = p.h_norm.size() > 1 ? p.h_norm[1] : p.h_norm[0];
   fa.norm_dc = p.h_norm[0];
   fa.ring_len = (uint32_t)(kN + cfg.hop);
+  fa.segs = 1;
+  fa.seg_len = hops;
+  fa.means_stride = hops;
   const unsigned grid = (unsigned)std::min<uint64_t>(n_lanes, (uint64_t)std::max(p.dev.sm_count, 1));
   const size_t fs = fused_smem_bytes(cfg.hop);
   // Planar ring (conflict-free frame loads): measured on B200 in round 2, 2.307e7 -> 2.481e7 lane-hops/s (+7.5 %, cfg4, 128 lanes;
@@ -586,6 +603,69 @@ int launch_spectrum_fused(SpectrumPlan& p, const float* d_lanes, uint32_t n_lane
   } else {
     OMB_LAUNCH(k_spectrum_fused_16k<OMB_AVG_NONE>, dim3(grid), dim3(kThreads), fs, s, fa);
   }
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+// The front half of the fused kernel as the power stage of the two-kernel path (few lanes, streaming): hop-overlapped staging ring,
+// one pass over the PCM, (lane, hop segment) work items that fill the GPU whatever the lane count.  `d_lanes` points at hop h0 of the
+// batch, `hops` is the chunk length; the frame means of the WHOLE batch were computed once (spectrum_fast_frame_means) and the
+// chunk starts at hop `h0` of them.
+int launch_spectrum_fused_power(SpectrumPlan& p, const float* d_lanes, uint32_t n_lanes, uint64_t hops, uint64_t lane_stride, float* d_power,
+                                uint64_t h0, uint64_t hops_total, cudaStream_t s) {
+  if (!hops || !n_lanes) return OMB_OK;
+  const SpectrumConfigN& cfg = p.cfg;
+  SpecFusedArgs fa{};
+  fa.a.lanes = d_lanes;
+  fa.a.lane_stride = lane_stride;
+  fa.a.n_lanes = n_lanes;
+  fa.a.hops = hops;
+  fa.a.hop = (uint32_t)cfg.hop;
+  fa.a.win = p.d_win.ptr;
+  fa.tw1 = p.d_fast_tables.ptr;
+  fa.tw2 = fa.tw1 + 15 * kT;
+  fa.means = p.d_means.ptr + h0;
+  fa.means_stride = hops_total;
+  fa.a_db = p.d_adb.ptr;
+  fa.out_weighted = d_power;
+  fa.out_raw = d_power;
+  fa.peak_bin = nullptr;
+  fa.mode = kPowerOnly;
+  fa.state_floor = p.state_floor;
+  fa.floor_db = cfg.floor_db;
+  fa.norm_ac = p.h_norm.size() > 1 ? p.h_norm[1] : p.h_norm[0];
+  fa.norm_dc = p.h_norm[0];
+  fa.ring_len = (uint32_t)(kN + cfg.hop);
+  // segments: about two work items per SM, at least 8 hops each (a segment primes its ring with a whole frame)
+  const uint64_t sms = (uint64_t)std::max(p.dev.sm_count, 1);
+  uint64_t segs = std::max<uint64_t>(1, (2 * sms + n_lanes - 1) / n_lanes);
+  uint64_t seg_len = std::max<uint64_t>(std::min<uint64_t>(8, hops), (hops + segs - 1) / segs);
+  segs = (hops + seg_len - 1) / seg_len;
+  fa.segs = (uint32_t)segs;
+  fa.seg_len = seg_len;
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)n_lanes * segs, sms);
+  const size_t fs = fused_smem_bytes(cfg.hop);
+  const bool planar = (cfg.hop % 4) == 0;
+  if (planar) {
+    auto k = k_spectrum_fused_16k<kPowerOnly, true>;
+    OMB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+    OMB_LAUNCH(k, dim3(grid), dim3(kThreads), fs, s, fa);
+  } else {
+    auto k = k_spectrum_fused_16k<kPowerOnly, false>;
+    OMB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+    OMB_LAUNCH(k, dim3(grid), dim3(kThreads), fs, s, fa);
+  }
+  OMB_CHECK_LAUNCH();
+  return OMB_OK;
+}
+
+// Frame means of a whole batch (f64 block sums -> f32), once; the fused kernels index them by absolute hop.
+int spectrum_fast_frame_means(SpectrumPlan& p, const float* d_lanes, uint64_t lane_stride, uint32_t n_lanes, uint64_t hops, cudaStream_t s) {
+  OMB_TRY(spectrum_fast_block_sums(p, d_lanes, lane_stride, n_lanes, hops, s));
+  const uint64_t n_blocks = hops - 1 + (uint64_t)kN / p.cfg.hop;
+  OMB_TRY(p.d_means.reserve((size_t)(hops * n_lanes)));
+  OMB_LAUNCH(k_frame_means, dim3((unsigned)((hops * n_lanes + 255) / 256)), dim3(256), 0, s, p.d_bsum.ptr, n_blocks, hops, n_lanes,
+             (uint32_t)(kN / p.cfg.hop), p.d_means.ptr);
   OMB_CHECK_LAUNCH();
   return OMB_OK;
 }

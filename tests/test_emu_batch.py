@@ -218,6 +218,23 @@ def test_spectrum_fused_16k(emu, mode, param, monkeypatch):
     assert st is not None
 
 
+@pytest.mark.parametrize("mode,param,hop,lanes", [(capi.AVG_PEAK_HOLD, 12.0, 1024, 2), (capi.AVG_EXPONENTIAL, 0.6, 2048, 3), (capi.AVG_NONE, 0.0, 512, 1)])
+def test_spectrum_two_kernel_path_ring_power(emu, mode, param, hop, lanes, monkeypatch):
+    """The two-kernel path (few lanes: OMB_SPECTRUM_FUSED=0) with the front half of the fused kernel as its power stage: (lane, hop
+    segment) work items, each priming its own ring — 23 hops split into segments of 8, so segments start mid-lane — against the
+    oracle, and bit-for-bit against the same kernel run as ONE segment per lane is not observable from here, so: against the
+    frame-per-CTA power kernel (OMB_SPECTRUM_RING_POWER=0) within the parity metric."""
+    monkeypatch.setenv("OMB_SPECTRUM_FUSED", "0")
+    cfg = SpectrumConfig(fft_size=16384, hop_size=hop, window=capi.WINDOW_HANN, averaging=mode, averaging_param=param, floor_db=-100.0)
+    x = synth.cfg4_streams(2, (16384 + 22 * hop) / 48000.0).reshape(4, -1)[:lanes]
+    monkeypatch.setenv("OMB_SPECTRUM_RING_POWER", "1")
+    cases.spectrum_parity(emu.api, cfg, x)
+    wa, ra, pka = batch.SpectrumPlan(cfg, api=emu.api).execute_host(x)
+    monkeypatch.setenv("OMB_SPECTRUM_RING_POWER", "0")
+    wb, rb, pkb = batch.SpectrumPlan(cfg, api=emu.api).execute_host(x)
+    assert wa.shape == wb.shape and np.max(np.abs(wa - wb)) < 2e-3 and np.max(np.abs(ra - rb)) < 2e-3  # dB; both within 1e-5 of the oracle in power
+
+
 @pytest.mark.parametrize("mode,param,hop", [(capi.AVG_PEAK_HOLD, 12.0, 1024), (capi.AVG_EXPONENTIAL, 0.6, 2048), (capi.AVG_NONE, 0.0, 512)])
 def test_spectrum_fused_16k_planar_ring(emu, mode, param, hop, monkeypatch):
     """The experimental planar staging ring of the fused kernel (OMB_SPECTRUM_PLANAR=1, off by default): even / odd float2 of

@@ -206,6 +206,21 @@ def test_cfg4_streaming_two_sources(product, oracle):
             parity.compare_db(a.traces[t][w][None], o.traces[t][w][None], -100.0)
 
 
+def test_cfg4_two_kernel_path_ring_power(product, monkeypatch):
+    """Few lanes -> two-kernel path with the front half of the fused kernel as its power stage ((lane, hop segment) work items, each
+    priming its own ring): same results as the frame-per-CTA power kernel within the parity metric; peak-hold state carries across
+    the chunk boundaries (4 chunks here)."""
+    monkeypatch.setenv("OMB_SPECTRUM_FUSED", "0")
+    cfg = SpectrumConfig(fft_size=16384, hop_size=1024, window=capi.WINDOW_HANN, averaging=capi.AVG_PEAK_HOLD, averaging_param=12.0, floor_db=-100.0)
+    lanes = synth.cfg4_streams(8, 22.0).reshape(16, -1)
+    monkeypatch.setenv("OMB_SPECTRUM_RING_POWER", "1")
+    a = batch.SpectrumPlan(cfg, api=product.api).execute_host(lanes)
+    monkeypatch.setenv("OMB_SPECTRUM_RING_POWER", "0")
+    b = batch.SpectrumPlan(cfg, api=product.api).execute_host(lanes)
+    assert np.max(np.abs(a[0] - b[0])) < 5e-3 and np.max(np.abs(a[1] - b[1])) < 5e-3  # dB, two f32 transforms
+    assert np.mean(a[2] == b[2]) > 0.999                                              # peak bins, up to near-ties
+
+
 # ---------------------------------------------------------------- cfg5: 8192-pt reassigned at 96 kHz
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_cfg5_reassigned_batch(product, kernel):
