@@ -322,7 +322,8 @@ void omb_stft_plan_destroy(omb_stft_plan* p);
 /* bins = fft_size*zp/2+1 */
 uint32_t omb_stft_plan_bins(const omb_stft_plan* p);
 /* 0: generic kernel; > 0: generation of the specialised sm_100a kernel the plan resolved to
- * (1 = stft_fast.cu, 2 = stft_fast2.cu: reassigned N = 4096; 3 = stft_classic_fast.cu: classic N = 1024). */
+ * (1 = stft_fast.cu, 2 = stft_fast2.cu, 7 = stft_r64.cu: reassigned N = 4096; 3 = stft_classic_fast.cu: classic N = 1024;
+ * 4 = stft_fast8k.cu: N = 8192; 5 = stft_fast2k.cu: N = 2048; 6 = stft_fast1k.cu: N = 1024; 8 = stft_r64x.cu: N = 16384 / 8192). */
 int omb_stft_plan_is_fast(const omb_stft_plan* p);
 float omb_stft_plan_power_scale(const omb_stft_plan* p);
 

@@ -21,7 +21,7 @@ class StftPlan:
         self._h = C.c_void_p()
         _check(self._api, self._api.stft_plan_create(C.byref(self._c), kernel, C.byref(self._h)), "stft_plan_create")
         self.bins = int(self._api.stft_plan_bins(self._h))
-        self.kernel_generation = int(self._api.stft_plan_is_fast(self._h))  # 0 generic / shared-memory tier, 1..5 specialised (stft.h: fast_kind)
+        self.kernel_generation = int(self._api.stft_plan_is_fast(self._h))  # 0 generic / shared-memory tier, 1..8 specialised (stft.h: fast_kind)
         self.is_fast = self.kernel_generation > 0
         self.power_scale = float(self._api.stft_plan_power_scale(self._h))
 
