@@ -49,6 +49,8 @@ struct Fast2Args {
   const float2* tw1;   // global: [15][256] W_4096^{b q}
   const float2* tw2;   // global: [15][16]  W_256^{o q}
   uint32_t frames_per_run, runs_per_lane, ring_len;
+  uint64_t chunk;      // > 0: every CTA walks ONE contiguous range of `chunk` frames of the linearised (lane, frame) sequence (the ring is
+                       // primed once per lane it touches) instead of runs dealt round-robin (a prime per run)
   float norm_ac, norm_dc;  // bin_norm[k] for 0 < k < N/2 and for k in {0, N/2} (window.rs:100-108)
 };
 
@@ -182,10 +184,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
     tmem_wait_st();
   }
 
-  for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
-    const uint64_t lane = run / fa.runs_per_lane;
-    const uint64_t f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
-    const uint64_t f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  uint64_t gpos = (uint64_t)blockIdx.x * fa.chunk;
+  const uint64_t g_end = gpos + fa.chunk < per_lane * a.n_lanes ? gpos + fa.chunk : per_lane * a.n_lanes;
+  for (uint64_t run = blockIdx.x; fa.chunk ? gpos < g_end : run < total_runs; run += gridDim.x) {
+    uint64_t lane, f_begin, f_end;
+    if (fa.chunk) {
+      lane = gpos / per_lane;
+      const uint64_t fb = gpos % per_lane;
+      const uint64_t n = per_lane - fb < g_end - gpos ? per_lane - fb : g_end - gpos;
+      f_begin = a.first_frame + fb;
+      f_end = f_begin + n;
+      gpos += n;
+    } else {
+      lane = run / fa.runs_per_lane;
+      f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
+      f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+    }
     const float* x = a.lanes + lane * a.lane_stride;
     const uint64_t s_end = (f_end - 1) * (uint64_t)hop + (uint64_t)H;  // one past the last sample this run reads
     // prime: everything frames f_begin and f_begin+1 read
@@ -451,7 +466,16 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.frames_per_run = (uint32_t)std::min<uint64_t>(run, per_lane);
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
-  const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  // Large batches: one contiguous range of frames per CTA (even length: the two groups work on frame pairs), balanced to a pair and
+  // primed once per lane touched; OMB_FAST2_CONTIG=0 keeps the round-robin runs (measured: profiles/r02_notes.md)
+  static const bool contig_env = [] { const char* e = getenv("OMB_FAST2_CONTIG"); return !(e && e[0] == '0'); }();
+  const uint64_t total_frames = per_lane * a.n_lanes;
+  fa.chunk = 0;
+  if (contig_env && total_frames >= ctas * 96) {
+    fa.chunk = ((total_frames + ctas - 1) / ctas + 1) & ~1ull;
+    grid = (unsigned)((total_frames + fa.chunk - 1) / fa.chunk);
+  }
   // OMB_FAST2_BULK: 0 = per-thread LDGSTS ring + scalar column stores (round 1), 1 = bulk ring fill, 3 = bulk ring fill and bulk
   // column store (default: kDefaultBulk)
   static const int bulk = [] { const char* e = getenv("OMB_FAST2_BULK"); return e ? atoi(e) & 7 : kDefaultBulk; }();

@@ -16,6 +16,8 @@
 #ifndef OMB_F32X2_CMUL
 #define OMB_F32X2_CMUL 0
 #endif
+#include <cstdlib>
+
 #include "async_copy.cuh"
 #include "device_math.cuh"
 #include "fft16.cuh"
@@ -43,6 +45,7 @@ struct Fast2kArgs {
   const float2* tw1;   // global: [15][256] W_4096^{b q}
   const float2* tw2;   // global: [15][16]  W_256^{o q}
   uint32_t frames_per_run, runs_per_lane, ring_len;
+  uint64_t chunk;      // > 0: one contiguous range of `chunk` frames of the linearised (lane, frame) sequence per CTA (stft_fast2.cu)
   float norm_ac, norm_dc;  // bin_norm / 4 (the separated spectra are doubled)
 };
 
@@ -119,10 +122,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2k(Fast2kArgs fa
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
   __syncthreads();
 
-  for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
-    const uint64_t lane = run / fa.runs_per_lane;
-    const uint64_t f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
-    const uint64_t f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  uint64_t gpos = (uint64_t)blockIdx.x * fa.chunk;
+  const uint64_t g_end = gpos + fa.chunk < per_lane * a.n_lanes ? gpos + fa.chunk : per_lane * a.n_lanes;
+  for (uint64_t run = blockIdx.x; fa.chunk ? gpos < g_end : run < total_runs; run += gridDim.x) {
+    uint64_t lane, f_begin, f_end;
+    if (fa.chunk) {
+      lane = gpos / per_lane;
+      const uint64_t fb = gpos % per_lane;
+      const uint64_t n = per_lane - fb < g_end - gpos ? per_lane - fb : g_end - gpos;
+      f_begin = a.first_frame + fb;
+      f_end = f_begin + n;
+      gpos += n;
+    } else {
+      lane = run / fa.runs_per_lane;
+      f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
+      f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+    }
     const float* x = a.lanes + lane * a.lane_stride;
     const uint64_t s_end = (f_end - 1) * (uint64_t)hop + (uint64_t)H;  // one past the last sample this run reads
     {  // prime: everything the first four frames read
@@ -364,7 +380,15 @@ int launch_stft_fast2k(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) 
   fa.frames_per_run = (uint32_t)std::min<uint64_t>(run, per_lane);
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
-  const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  // Large batches: one contiguous range of frames per CTA, primed once per lane touched (stft_fast2.cu; OMB_FAST2K_CONTIG=0: round-robin runs)
+  static const bool contig_env = [] { const char* e = getenv("OMB_FAST2K_CONTIG"); return !(e && e[0] == '0'); }();
+  const uint64_t total_frames = per_lane * a.n_lanes;
+  fa.chunk = 0;
+  if (contig_env && total_frames >= ctas * 192) {
+    fa.chunk = ((total_frames + ctas - 1) / ctas + 3) / 4 * 4;
+    grid = (unsigned)((total_frames + fa.chunk - 1) / fa.chunk);
+  }
   OMB_LAUNCH(k_reassigned_fast2k, dim3(grid), dim3(kThreads), smem_bytes(a.hop), s, fa);
   OMB_CHECK_LAUNCH();
   return OMB_OK;

@@ -28,6 +28,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "device_math.cuh"
 #include "fft16.cuh"
 #include "fft4096.cuh"
@@ -52,6 +54,7 @@ struct Fast8kArgs {
   const float2* tw1;   // global: [15][256] W_4096^{b q}
   const float2* tw2;   // global: [15][16]  W_256^{o q}
   uint32_t frames_per_run, runs_per_lane, ring_len;
+  uint64_t chunk;      // > 0: one contiguous range of `chunk` frames of the linearised (lane, frame) sequence per CTA (stft_fast2.cu)
   float norm_ac, norm_dc;  // bin_norm[k] for 0 < k < N/2 and for k in {0, N/2} (window.rs:100-108)
 };
 
@@ -153,10 +156,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_8k(Fast8kArgs fa) {
   const int ts2 = kAnyHop ? 2 * t : 0, ts1 = kAnyHop ? t : 0;
   __syncthreads();
 
-  for (uint64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
-    const uint64_t lane = run / fa.runs_per_lane;
-    const uint64_t f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
-    const uint64_t f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+  const uint64_t per_lane = a.frames_per_lane - a.first_frame;
+  uint64_t gpos = (uint64_t)blockIdx.x * fa.chunk;
+  const uint64_t g_end = gpos + fa.chunk < per_lane * a.n_lanes ? gpos + fa.chunk : per_lane * a.n_lanes;
+  for (uint64_t run = blockIdx.x; fa.chunk ? gpos < g_end : run < total_runs; run += gridDim.x) {
+    uint64_t lane, f_begin, f_end;
+    if (fa.chunk) {
+      lane = gpos / per_lane;
+      const uint64_t fb = gpos % per_lane;
+      const uint64_t n = per_lane - fb < g_end - gpos ? per_lane - fb : g_end - gpos;
+      f_begin = a.first_frame + fb;
+      f_end = f_begin + n;
+      gpos += n;
+    } else {
+      lane = run / fa.runs_per_lane;
+      f_begin = a.first_frame + (run % fa.runs_per_lane) * (uint64_t)fa.frames_per_run;
+      f_end = (f_begin + fa.frames_per_run < a.frames_per_lane) ? f_begin + fa.frames_per_run : a.frames_per_lane;
+    }
     const float* x = a.lanes + lane * a.lane_stride;
     int r0 = 0;  // ring position of the current frame's first sample
     ring_fetch(ring, L, 0, x + f_begin * (uint64_t)hop, H);
@@ -424,7 +440,15 @@ int launch_stft_fast8k(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) 
   fa.frames_per_run = (uint32_t)std::min<uint64_t>(run, per_lane);
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
-  const unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  // Large batches: one contiguous range of frames per CTA, primed once per lane touched (stft_fast2.cu; OMB_FAST8K_CONTIG=0: round-robin runs)
+  static const bool contig_env = [] { const char* e = getenv("OMB_FAST8K_CONTIG"); return !(e && e[0] == '0'); }();
+  const uint64_t total_frames = per_lane * a.n_lanes;
+  fa.chunk = 0;
+  if (contig_env && total_frames >= ctas * 48) {
+    fa.chunk = ((total_frames + ctas - 1) / ctas + 0) / 1 * 1;
+    grid = (unsigned)((total_frames + fa.chunk - 1) / fa.chunk);
+  }
   auto k_aligned = k_reassigned_8k<0, false>;
   auto k_any = k_reassigned_8k<0, true>;
   if ((a.hop % 512) == 0) {

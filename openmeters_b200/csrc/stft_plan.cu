@@ -73,10 +73,10 @@ int StftPlan::init(const omb_spectrogram_config& c, int choice) {
   const char* pin = getenv("OMB_FAST_KERNEL");
   const int want = pin ? atoi(pin) : 3;
   const bool gen1 = stft_fast_supported(cfg, dev), gen2 = want >= 2 && stft_fast2_supported(cfg, dev);
-  // Generation 3 (stft_r64.cu) has no staging ring, so its rate does not depend on the hop; generation 2 is 2 % faster at the hops
-  // its ring handles with warp-uniform rows (multiples of 512) and slower at the others (profiles/r02_notes.md).  Unpinned: each
-  // hop goes to the faster kernel.
-  const bool gen3 = want >= 3 && stft_r64_supported(cfg, dev) && (pin != nullptr || !gen2 || (cfg.hop % 512) != 0);
+  // Generation 3 (stft_r64.cu) has no staging ring: any hop that is a multiple of 4.  Generation 2 with its contiguous work
+  // assignment is 3-4 % faster at every hop its ring handles (multiples of 512 up to 2048, multiples of 4 below 512;
+  // profiles/r02_notes.md), so unpinned generation 3 serves the hops generation 2 cannot.
+  const bool gen3 = want >= 3 && stft_r64_supported(cfg, dev) && ((pin != nullptr && atoi(pin) >= 3) || !gen2);
   if (choice != OMB_KERNEL_GENERIC && gen3) {  // N = 4096, any hop % 4 == 0: two-pass radix-64 teams (stft_r64.cu)
     OMB_TRY(stft_r64_prepare(*this));
     fast = true;

@@ -6,6 +6,7 @@ import pytest
 from openmeters_b200 import _capi as capi
 from openmeters_b200 import batch, synth
 from openmeters_b200.processors import LoudnessConfig, SpectrogramConfig, SpectrumConfig
+from oracle import oracle_py
 from tests import cases, parity
 
 
@@ -59,6 +60,31 @@ def test_specialised_reassigned_kernels(emu, gen, monkeypatch):
     lanes = synth.cfg2_lanes(3, (8192 + 40 * 1024) / 48000.0)  # 41 frames per lane
     st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
     assert st["cols"] == 3 * 41 and st["unmatched"] <= 4
+
+
+def test_specialised_kernel_contiguous_ranges(emu, monkeypatch):
+    """Generation 2 at a batch large enough for the contiguous work assignment (>= 96 frames per SM; the emulator has 4): every CTA
+    walks one range of the linearised (lane, frame) sequence; the ranges cut lanes at odd frames and span a lane boundary (three
+    lanes of 131 frames over 4 CTAs of 100).  Must equal the round-robin runs bit for bit, and match the oracle."""
+    monkeypatch.setenv("OMB_FAST_KERNEL", "2")
+    cfg = SpectrogramConfig(fft_size=4096, hop_size=512, window=capi.WINDOW_BLACKMAN_HARRIS, use_reassignment=True)
+    n = 8192 + 130 * 512
+    lanes = synth.cfg2_lanes(3, (n + 64) / 48000.0)[:, :n]
+    pa, ca = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=emu.api).execute_host(lanes)
+    pb, cb = oracle_py.stft_batch(cfg, lanes)
+    st = parity.compare_reassigned(pa, ca, pb, cb, sr=48000.0, fft_len=4096, window=4096, hop=512)
+    assert st["cols"] == 3 * 131
+
+
+@pytest.mark.parametrize("n,hop,frames,sr", [(8192, 512, 101, 96000.0), (2048, 64, 403, 48000.0), (1024, 32, 805, 48000.0)])
+def test_ring_kernels_contiguous_ranges(emu, n, hop, frames, sr):
+    """stft_fast8k.cu / stft_fast2k.cu / stft_fast1k.cu at batches large enough for the contiguous work assignment (the emulator has 4
+    SMs): ranges that cut lanes at frames that are not multiples of the kernels' frames-per-iteration and span the lane boundary."""
+    cfg = SpectrogramConfig(sample_rate=sr, fft_size=n, hop_size=hop, window=capi.WINDOW_HANN, use_reassignment=True)
+    S = 2 * n + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(2, (S + 64) / 48000.0)[:, :S]
+    st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+    assert st["cols"] == 2 * frames
 
 
 def test_specialised_kernel_other_hops_and_windows(emu):

@@ -30,7 +30,7 @@ def main():
     only_new = "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "new"
     pin = os.environ.get("OMB_FAST_KERNEL")
     kind = {None: None, "1": 1, "2": 2, "3": 7}[pin]  # fast_kind of the pinned generation (stft.h)
-    cases = [(4096, 1024, kind or 2), (4096, 64, kind or 7)]
+    cases = [(4096, 1024, kind or 2), (4096, 64, kind or 2)]
     if pin != "2":
         cases.append((4096, 1000, 7))
     cases.append((16384, 4096, 8))  # stft_r64x.cu
