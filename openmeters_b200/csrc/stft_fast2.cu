@@ -49,6 +49,7 @@ struct Fast2Args {
   const float2* tw1;   // global: [15][256] W_4096^{b q}
   const float2* tw2;   // global: [15][16]  W_256^{o q}
   uint32_t frames_per_run, runs_per_lane, ring_len;
+  uint32_t pairs;      // frame pairs per loop iteration (one CTA barrier and one ring prefetch per iteration): as many as the ring holds
   uint64_t chunk;      // > 0: every CTA walks ONE contiguous range of `chunk` frames of the linearised (lane, frame) sequence (the ring is
                        // primed once per lane it touches) instead of runs dealt round-robin (a prime per run)
   float norm_ac, norm_dc;  // bin_norm[k] for 0 < k < N/2 and for k in {0, N/2} (window.rs:100-108)
@@ -203,10 +204,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
     }
     const float* x = a.lanes + lane * a.lane_stride;
     const uint64_t s_end = (f_end - 1) * (uint64_t)hop + (uint64_t)H;  // one past the last sample this run reads
-    // prime: everything frames f_begin and f_begin+1 read
+    // prime: everything the frames of the first iteration read (2 * pairs frames)
+    const uint64_t iter_frames = 2ull * fa.pairs, iter_span = (iter_frames - 1) * (uint64_t)hop;
     {
       const uint64_t s0 = f_begin * (uint64_t)hop;
-      const uint64_t s1 = s0 + (uint64_t)H + (uint64_t)hop < s_end ? s0 + (uint64_t)H + (uint64_t)hop : s_end;
+      const uint64_t s1 = s0 + (uint64_t)H + iter_span < s_end ? s0 + (uint64_t)H + iter_span : s_end;
       if (kBulkIn) {
         if (tid == 0) {
           mbar_expect_tx(&sm.mbar[0], ring_bytes(s0, s1));
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         async_commit();
       }
     }
-    for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kGroupsPerCta) {
+    for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += iter_frames) {
       if (kBulkIn) {
         mbar_wait(&sm.mbar[0], ring_phase);
         ring_phase ^= 1u;
@@ -225,10 +227,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         async_wait_all();
       }
       if (kBulkOut && t == 0) bulk_wait_read();  // the previous column has left the transform buffer
-      __syncthreads();  // ring holds frames fa0, fa0+1; both groups are done with the previous pair
-      {                 // prefetch what the next pair adds: two hops
-        const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)hop;
-        const uint64_t s1 = s0 + 2ull * hop < s_end ? s0 + 2ull * hop : s_end;
+      __syncthreads();  // ring holds the frames of this iteration; both groups are done with the previous one
+      {                 // prefetch what the next iteration adds: 2 * pairs hops
+        const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + iter_span;
+        const uint64_t s1 = s0 + iter_frames * hop < s_end ? s0 + iter_frames * hop : s_end;
         if (kBulkIn) {
           if (tid == 0) {  // every phase is armed (with 0 bytes at the end of a run) so the parity bookkeeping stays uniform
             mbar_expect_tx(&sm.mbar[0], ring_bytes(s0, s1));
@@ -239,7 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           async_commit();
         }
       }
-      const uint64_t f = fa0 + g;
+#pragma unroll 1
+      for (uint32_t sp = 0; sp < fa.pairs; ++sp) {
+      const uint64_t f = fa0 + 2ull * sp + g;
+      if (kBulkOut && sp > 0) {  // the previous column of this group must have left the transform buffer (bulk store) before it is reused
+        if (t == 0) bulk_wait_read();
+        group_sync(g);
+      }
       if (f < f_end) {
         const int r0 = (int)(f * (uint64_t)hop) & ring_mask;  // multiple of 512 unless kAnyHop (then of 4)
         float2 v[16];
@@ -404,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
           }
         }
       }
+      }  // sp
     }
     if (kBulkIn) {
       mbar_wait(&sm.mbar[0], ring_phase);  // the last (empty) phase armed inside the loop
@@ -467,6 +476,12 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  // frame pairs per iteration: as many as fit the ring next to the prefetch of the following iteration, H + (4 pairs - 1) hop <= ring
+  // (hop 1024: 2, hop <= 512: 4, hop 2048: 1); OMB_FAST2_PAIRS pins it (1 = one CTA barrier per pair, round 1)
+  static const int pairs_env = [] { const char* e = getenv("OMB_FAST2_PAIRS"); return e ? atoi(e) : 0; }();
+  uint32_t pairs = (uint32_t)std::min<uint64_t>(4, ((uint64_t)fa.ring_len - 2 * kM + a.hop) / (4 * (uint64_t)a.hop));
+  if (pairs_env > 0) pairs = std::min<uint32_t>(pairs, (uint32_t)pairs_env);
+  fa.pairs = std::max<uint32_t>(1, pairs);
   // Large batches: one contiguous range of frames per CTA (even length: the two groups work on frame pairs), balanced to a pair and
   // primed once per lane touched; OMB_FAST2_CONTIG=0 keeps the round-robin runs (measured: profiles/r02_notes.md)
   static const bool contig_env = [] { const char* e = getenv("OMB_FAST2_CONTIG"); return !(e && e[0] == '0'); }();
