@@ -369,13 +369,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_spectrum_fused_16k(SpecFusedArg
   const float norm_ac = 0.25f * fa.norm_ac, norm_dc = 0.25f * fa.norm_dc;
   __syncthreads();
 
-  for (uint64_t item = blockIdx.x; item < (uint64_t)a.n_lanes * fa.segs; item += gridDim.x) {
-    const uint32_t lane = (uint32_t)(item / fa.segs);
-    const uint64_t h_begin = (item % fa.segs) * fa.seg_len;
-    const uint64_t h_end = h_begin + fa.seg_len < a.hops ? h_begin + fa.seg_len : a.hops;
-    if (h_begin >= h_end) continue;
+  // (the smoothing modes see compile-time segs = 1, h_begin = 0: their code is the whole-lane loop of round 1)
+  const uint64_t n_items = kMode == kPowerOnly ? (uint64_t)a.n_lanes * fa.segs : (uint64_t)a.n_lanes;
+  for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t lane = kMode == kPowerOnly ? (uint32_t)(item / fa.segs) : (uint32_t)item;
+    const uint64_t h_begin = kMode == kPowerOnly ? (item % fa.segs) * fa.seg_len : 0;
+    const uint64_t h_end = kMode == kPowerOnly ? (h_begin + fa.seg_len < a.hops ? h_begin + fa.seg_len : a.hops) : a.hops;
+    if (kMode == kPowerOnly && h_begin >= h_end) continue;
     const float* x = a.lanes + (uint64_t)lane * a.lane_stride + h_begin * (uint64_t)hop;
-    const float* means = fa.means + (uint64_t)lane * fa.means_stride;
+    const float* means = fa.means + (uint64_t)lane * (kMode == kPowerOnly ? fa.means_stride : a.hops);
     float st[kSlots][4];
     float st_mid[2] = {0.0f, 0.0f};  // bins 2048 and 6144 (aa = 2048), thread 0 only
 #pragma unroll
