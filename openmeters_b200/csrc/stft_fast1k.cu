@@ -43,6 +43,7 @@ struct Fast1kArgs {
   const float2* tw1;   // global: [15][256] W_4096^{b q}
   const float2* tw2;   // global: [15][16]  W_256^{o q}
   uint32_t frames_per_run, runs_per_lane, ring_len;
+  uint32_t reps;       // loop iterations' worth of frames per CTA barrier / ring prefetch (stft_fast2.cu: `pairs`): as many as the ring holds
   uint64_t chunk;      // > 0: one contiguous range of `chunk` frames of the linearised (lane, frame) sequence per CTA (stft_fast2.cu)
   float norm_ac, norm_dc;  // bin_norm / 16 (the separated spectra are scaled by 4)
 };
@@ -141,23 +142,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
     }
     const float* x = a.lanes + lane * a.lane_stride;
     const uint64_t s_end = (f_end - 1) * (uint64_t)hop + (uint64_t)H;  // one past the last sample this run reads
+    const uint64_t iter_frames = (uint64_t)kFramesPerIter * fa.reps;
     {  // prime: everything the first eight frames read
       const uint64_t s0 = f_begin * (uint64_t)hop;
-      const uint64_t want = s0 + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
+      const uint64_t want = s0 + (uint64_t)H + (iter_frames - 1) * hop;
       k1_ring_fetch(ring, ring_mask, x, s0, want < s_end ? want : s_end);
       async_commit();
     }
-    for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += kFramesPerIter) {
+    for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += iter_frames) {
       async_wait_all();
       __syncthreads();  // ring holds frames fa0 .. fa0+7; both groups are done with the previous eight
       {                 // prefetch what the next eight frames add: eight hops
-        const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (uint64_t)(kFramesPerIter - 1) * hop;
-        const uint64_t want = s0 + (uint64_t)kFramesPerIter * hop;
+        const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + (iter_frames - 1) * hop;
+        const uint64_t want = s0 + iter_frames * hop;
         const uint64_t s1 = want < s_end ? want : s_end;
         if (s0 < s1) k1_ring_fetch(ring, ring_mask, x, s0, s1);
         async_commit();
       }
-      const uint64_t fg = fa0 + (uint64_t)kFramesPerGroup * g;  // this group's frames: fg .. fg + 3
+#pragma unroll 1
+      for (uint32_t sp = 0; sp < fa.reps; ++sp) {
+      const uint64_t fg = fa0 + (uint64_t)kFramesPerIter * sp + (uint64_t)kFramesPerGroup * g;  // this group's frames: fg .. fg + 3
       if (fg < f_end) {
         // missing frames at the tail of a run are fed as zeros: the four frames share every transform, so stale ring
         // contents (possibly NaN bit patterns) would leak into the others
@@ -330,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast1k(Fast1kArgs fa
           }
         }
       }
+      }  // sp
     }
     async_wait_all();
     __syncthreads();
@@ -387,6 +392,11 @@ int launch_stft_fast1k(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) 
   fa.runs_per_lane = (uint32_t)((per_lane + fa.frames_per_run - 1) / fa.frames_per_run);
   const uint64_t total_runs = (uint64_t)fa.runs_per_lane * a.n_lanes;
   unsigned grid = (unsigned)std::min<uint64_t>(total_runs, ctas);
+  // iterations per CTA barrier: as many as fit the ring next to the following prefetch, H + (2 F reps - 1) hop <= ring (OMB_FAST1K_REPS pins)
+  static const int reps_env = [] { const char* e = getenv("OMB_FAST1K_REPS"); return e ? atoi(e) : 0; }();
+  uint32_t reps = (uint32_t)std::min<uint64_t>(8, ((uint64_t)fa.ring_len - 2 * (uint64_t)kN2 + a.hop) / (2ull * kFramesPerIter * a.hop));
+  if (reps_env > 0) reps = std::min<uint32_t>(reps, (uint32_t)reps_env);
+  fa.reps = std::max<uint32_t>(1, reps);
   // Large batches: one contiguous range of frames per CTA, primed once per lane touched (stft_fast2.cu; OMB_FAST1K_CONTIG=0: round-robin runs)
   static const bool contig_env = [] { const char* e = getenv("OMB_FAST1K_CONTIG"); return !(e && e[0] == '0'); }();
   const uint64_t total_frames = per_lane * a.n_lanes;
