@@ -5,7 +5,7 @@ import pytest
 
 from openmeters_b200 import _capi as capi
 from openmeters_b200 import batch, synth
-from openmeters_b200.processors import LoudnessConfig, SpectrogramConfig, SpectrumConfig
+from openmeters_b200.processors import AudioBlock, LoudnessConfig, SpectrogramConfig, SpectrumConfig
 from oracle import oracle_py
 from tests import cases, parity
 
@@ -293,3 +293,27 @@ def test_16k_kernel_on_chip(emu, hop, frames, window):
     lanes = synth.cfg2_lanes(2, (n + 64) / 48000.0)[:, :n]
     st = cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
     assert st["cols"] == 2 * frames and st["checked"] > 10000
+
+@pytest.mark.parametrize("n,hop,sr", [(4096, 1000, 48000.0), (16384, 4096, 48000.0), (8192, 1000, 96000.0)])
+def test_team_kernels_streaming_matches_batch(emu, n, hop, sr):
+    """The streaming processor over the team kernels (stft_r64.cu / stft_r64x.cu: hops off the ring kernels' grid): ragged blocks, so
+    calls start at first_frame > 0 and at FIFO offsets that are multiples of 4 floats only when the hop is; every column equals the
+    batch path's (same kernel, same frame) bit for bit, and the batch path matches the oracle."""
+    cfg = SpectrogramConfig(sample_rate=sr, fft_size=n, hop_size=hop, window=capi.WINDOW_HANN, use_reassignment=True, history_length=64)
+    frames = 7
+    S = 2 * n + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(1, (S + 64) / 48000.0)[:, :S]
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=emu.api)
+    assert plan.kernel_generation in (7, 8)
+    pts, cnt = plan.execute_host(lanes)
+    p = emu.Spectrogram(cfg)
+    cols = []
+    step = 4 * 997  # a multiple of 4: the device FIFO stays 16-byte aligned, so the specialised kernel keeps serving the stream
+    for s0 in range(0, S, step):
+        up = p.process_block(AudioBlock(lanes[0, s0:min(s0 + step, S)], 1, sr))
+        if up is not None:
+            cols += list(up.new_columns)
+    assert len(cols) == frames
+    for f, c in enumerate(cols):
+        assert np.array_equal(np.asarray(c), pts[0, f, :cnt[0, f]]), f
+    cases.stft_parity(emu.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)

@@ -258,6 +258,30 @@ def test_size_16384_specialised_and_generic_agree(product, monkeypatch):
     assert st["cols"] == 42 and st["checked"] > 100000
 
 
+@pytest.mark.parametrize("n,hop,sr", [(4096, 1000, 48000.0), (16384, 4096, 48000.0), (8192, 1000, 96000.0)])
+def test_team_kernels_streaming_matches_batch(product, n, hop, sr):
+    """Streaming processor over stft_r64.cu / stft_r64x.cu (hops off the ring kernels' grid): ragged blocks -> calls with first_frame > 0;
+    every column equals the batch path's bit for bit (so the same kernel served the stream), and the batch path matches the oracle."""
+    cfg = SpectrogramConfig(sample_rate=sr, fft_size=n, hop_size=hop, window=capi.WINDOW_HANN, use_reassignment=True, history_length=64)
+    frames = 23
+    S = 2 * n + (frames - 1) * hop
+    lanes = synth.cfg2_lanes(1, (S + 64) / 48000.0)[:, :S]
+    plan = batch.StftPlan(cfg, kernel=capi.KERNEL_FAST, api=product.api)
+    assert plan.kernel_generation in (7, 8)
+    pts, cnt = plan.execute_host(lanes)
+    p = product.Spectrogram(cfg)
+    cols = []
+    step = 4 * 997
+    for s0 in range(0, S, step):
+        up = p.process_block(AudioBlock(lanes[0, s0:min(s0 + step, S)], 1, sr))
+        if up is not None:
+            cols += list(up.new_columns)
+    assert len(cols) == frames
+    for f, c in enumerate(cols):
+        assert np.array_equal(np.asarray(c), pts[0, f, :cnt[0, f]]), f
+    cases.stft_parity(product.api, cfg, lanes, kernel=capi.KERNEL_FAST, expect_fast=True)
+
+
 # ---------------------------------------------------------------- N = 4096 at the UI's small hops (N/16 ... N/128)
 @pytest.mark.parametrize("hop", [256, 64, 32])
 def test_cfg2_small_hops(product, hop):
