@@ -42,7 +42,7 @@ constexpr int kThreads = kT * kGroupsPerCta;
 constexpr int kWarps = kT / 32;          // warps per group
 constexpr int kWSize = f16::phys_size(kM);
 constexpr int kBinGroups = 9;            // bins t + 256 j, j < 8, and bin 2048 (t = 0, j = 8)
-constexpr int kDefaultBulk = 3;          // OMB_FAST2_BULK default (see launch_stft_fast2)
+constexpr int kDefaultBulk = 3;          // OMB_FAST2_BULK default (see launch_stft_fast2); with it, the lagged barrier (variant bit 6)
 
 struct Fast2Args {
   StftKernelArgs a;
@@ -99,6 +99,11 @@ __device__ __forceinline__ void ring_fetch(float* ring, int ring_mask, const flo
 // kVariant bit 5 (kTmemTab): everything a thread reads from a TABLE — its 15 + 15 twiddles and its 16 + 16 window values — sits in the
 // thread's own tensor-memory columns (tcgen05.st once, one tcgen05.ld per pass / window): 95 shared-memory loads, 48 window loads
 // and 220 twiddle-product instructions per thread-frame become 13 TMEM loads.
+// kVariant bit 6 (kLagSync, needs kBulkIn): the CTA barrier at the top of an iteration only exists so that the ring prefetch does not
+// overwrite samples the slower group still reads.  It becomes a LAGGED barrier: every warp ARRIVES (bar.arrive, non-blocking) when it
+// has finished the previous iteration, and only the warp that issues the prefetch WAITS (bar.sync) — the groups drift up to one
+// iteration apart instead of being re-aligned every few frames.  Two named barriers and two mbarriers alternate by iteration
+// parity, so an early arrival / a completed phase of iteration i + 1 cannot be taken for iteration i.
 template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) {
   constexpr int kTw2 = kVariant & 1;
@@ -107,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   constexpr bool kBulkIn = (kVariant & 8) != 0;
   constexpr bool kBulkOut = (kVariant & 16) != 0;
   constexpr bool kTmemTab = (kVariant & 32) != 0;
+  constexpr bool kLagSync = (kVariant & 64) != 0 && kBulkIn;
   OMB_DYN_SMEM(unsigned char, smem_raw);
   Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
   float* ring = reinterpret_cast<float*>(smem_raw + sizeof(Smem2));
@@ -147,8 +153,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
   const float ramp0 = (float)t - (float)(kM - 1) * 0.5f;  // n - (N-1)/2 at j = 0
   const int pt = (kT - tf) & (kT - 1);
   const int pPartner = 273 * (pt & 15) + 17 * (pt >> 4);
-  if (kBulkIn && tid == 0) mbar_init(&sm.mbar[0], 1);
-  unsigned ring_phase = 0;  // parity of the mbarrier phase the next wait is for
+  if (kBulkIn && tid == 0) {
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
+  }
+  unsigned ring_phase = 0;  // parity of the mbarrier phase the next wait is for (!kLagSync: one mbarrier)
+  unsigned it = 0;          // kLagSync: iteration counter; iteration `it` uses mbarrier it & 1 (phase parity (it >> 1) & 1) and named barrier 3 + (it & 1)
   if (kTmemTab && tid < 32) tmem_alloc(&sm.tmem_base);
   if (kTmemTab) tmem_fence_before_sync();
   __syncthreads();
@@ -211,8 +221,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
       const uint64_t s1 = s0 + (uint64_t)H + iter_span < s_end ? s0 + (uint64_t)H + iter_span : s_end;
       if (kBulkIn) {
         if (tid == 0) {
-          mbar_expect_tx(&sm.mbar[0], ring_bytes(s0, s1));
-          ring_fetch_bulk(ring, ring_mask, x, s0, s1, &sm.mbar[0]);
+          uint64_t* mb = &sm.mbar[kLagSync ? (it & 1u) : 0u];
+          mbar_expect_tx(mb, ring_bytes(s0, s1));
+          ring_fetch_bulk(ring, ring_mask, x, s0, s1, mb);
         }
       } else {
         ring_fetch(ring, ring_mask, x, s0, s1);
@@ -220,21 +231,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
       }
     }
     for (uint64_t fa0 = f_begin; fa0 < f_end; fa0 += iter_frames) {
-      if (kBulkIn) {
+      if (kLagSync) {
+        mbar_wait(&sm.mbar[it & 1u], (it >> 1) & 1u);  // this iteration's samples have landed
+      } else if (kBulkIn) {
         mbar_wait(&sm.mbar[0], ring_phase);
         ring_phase ^= 1u;
       } else {
         async_wait_all();
       }
       if (kBulkOut && t == 0) bulk_wait_read();  // the previous column has left the transform buffer
-      __syncthreads();  // ring holds the frames of this iteration; both groups are done with the previous one
+      if (kLagSync) {
+        if (kBulkOut) group_sync(g);  // ... for every thread of the group
+        // everybody has finished iteration it - 1; only the prefetching warp needs to know
+#ifdef OMB_EMU
+        if ((tid >> 5) == 0) omb_emu::named_sync(3 + (int)(it & 1u), kThreads); else omb_emu::named_arrive(3 + (int)(it & 1u), kThreads);
+#else
+        if ((tid >> 5) == 0) asm volatile("bar.sync %0, %1;" ::"r"(3 + (int)(it & 1u)), "n"(kThreads) : "memory");
+        else asm volatile("bar.arrive %0, %1;" ::"r"(3 + (int)(it & 1u)), "n"(kThreads) : "memory");
+#endif
+      } else {
+        __syncthreads();  // ring holds the frames of this iteration; both groups are done with the previous one
+      }
       {                 // prefetch what the next iteration adds: 2 * pairs hops
         const uint64_t s0 = fa0 * (uint64_t)hop + (uint64_t)H + iter_span;
         const uint64_t s1 = s0 + iter_frames * hop < s_end ? s0 + iter_frames * hop : s_end;
         if (kBulkIn) {
           if (tid == 0) {  // every phase is armed (with 0 bytes at the end of a run) so the parity bookkeeping stays uniform
-            mbar_expect_tx(&sm.mbar[0], ring_bytes(s0, s1));
-            ring_fetch_bulk(ring, ring_mask, x, s0, s1, &sm.mbar[0]);
+            uint64_t* mb = &sm.mbar[kLagSync ? ((it + 1u) & 1u) : 0u];
+            mbar_expect_tx(mb, ring_bytes(s0, s1));
+            ring_fetch_bulk(ring, ring_mask, x, s0, s1, mb);
           }
         } else {
           if (s0 < s1) ring_fetch(ring, ring_mask, x, s0, s1);
@@ -413,8 +438,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_reassigned_fast2(Fast2Args fa) 
         }
       }
       }  // sp
+      ++it;
     }
-    if (kBulkIn) {
+    if (kLagSync) {
+      mbar_wait(&sm.mbar[it & 1u], (it >> 1) & 1u);  // the last (empty) phase armed inside the loop
+      ++it;
+    } else if (kBulkIn) {
       mbar_wait(&sm.mbar[0], ring_phase);  // the last (empty) phase armed inside the loop
       ring_phase ^= 1u;
     } else {
@@ -451,6 +480,8 @@ int stft_fast2_prepare(StftPlan& plan) {
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<26>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<90>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<94>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<58>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   OMB_CUDA_TRY(cudaFuncSetAttribute(k_reassigned_fast2<62>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OMB_OK;
@@ -496,11 +527,15 @@ int launch_stft_fast2(const StftPlan& plan, StftKernelArgs& a, cudaStream_t s) {
   static const int bulk = [] { const char* e = getenv("OMB_FAST2_BULK"); return e ? atoi(e) & 7 : kDefaultBulk; }();
   const size_t smem = smem_bytes(a.hop);
   const bool any_hop = (a.hop % 512) != 0;
+  // lagged cross-group barrier: measured +2.9 % on cfg2 (profiles/r02_notes.md); OMB_FAST2_LAG=0 restores the CTA barrier
+  static const bool lag_sync = [] { const char* e = getenv("OMB_FAST2_LAG"); return !(e && e[0] == '0'); }();
 #define OMB_FAST2_LAUNCH(V) OMB_LAUNCH(k_reassigned_fast2<V>, dim3(grid), dim3(kThreads), smem, s, fa)
   if (bulk == 0) {
     if (any_hop) OMB_FAST2_LAUNCH(6); else OMB_FAST2_LAUNCH(2);
   } else if (bulk == 1) {
     if (any_hop) OMB_FAST2_LAUNCH(14); else OMB_FAST2_LAUNCH(10);
+  } else if (bulk == 3 && lag_sync) {  // + lagged cross-group barrier
+    if (any_hop) OMB_FAST2_LAUNCH(94); else OMB_FAST2_LAUNCH(90);
   } else if (bulk == 7) {  // + tables in tensor memory
     if (any_hop) OMB_FAST2_LAUNCH(62); else OMB_FAST2_LAUNCH(58);
   } else {

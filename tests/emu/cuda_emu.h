@@ -134,6 +134,15 @@ inline void named_sync(int id, int count) {
   }
 }
 
+// bar.arrive id, count: counts like bar.sync but does not wait
+inline void named_arrive(int id, int count) {
+  NamedBar& nb = blk().named[id & 15];
+  if (++nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+  }
+}
+
 inline unsigned warp_lanes(const BlockState& b, unsigned warp) {
   const unsigned first = warp * 32;
   return std::min(32u, b.nthreads - first);
