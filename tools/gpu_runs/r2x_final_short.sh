@@ -10,5 +10,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_re
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2x_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/r2x_launches_bench.log 2>&1
 timeout 400 python bench.py > $O/r2x_bench_n1.json 2> $O/r2x_bench_n1.err
 python -c "import json; d=json.loads([l for l in open('$O/r2x_bench_n1.json') if l.startswith('{')][-1]); print('value', d['value'], 'e2e', d['e2e']['value'], 'e2e_image', d['e2e_image']['value'], 'frac', d['roofline']['frac']); print({k: (v['value'], v['hbm_frac']) for k, v in d['secondary'].items()})"
-timeout 300 python tools/bench_grid.py > $O/r2x_grid.json 2> $O/r2x_grid.err
-timeout 300 python tools/bench_configs.py > $O/r2x_configs.json 2> $O/r2x_configs.err
+
+
