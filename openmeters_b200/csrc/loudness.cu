@@ -915,6 +915,9 @@ int launch_loudness_stream(const LoudStreamArgs& a, cudaStream_t s, uint32_t n_s
 
 LoudnessPlan::~LoudnessPlan() {
   if (stream) cudaStreamDestroy(stream);
+  if (side) cudaStreamDestroy(side);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
 }
 
 int LoudnessPlan::init(const omb_loudness_config& c, uint32_t ch, const uint8_t* pos) {
@@ -997,6 +1000,39 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   a.out = d_out_snap;
   OMB_CUDA_TRY(cudaMemsetAsync(d_peak.ptr, 0, sizeof(unsigned) * n_streams * a.n_blocks * channels, s));
 
+  // True peak depends on the PCM (and the zeroed peak array) only: on a side stream, next to the K-weighting chain, joined before the
+  // snapshots (OMB_LOUDNESS_OVERLAP=0: one stream, round 1's order)
+  const char* ov_env = getenv("OMB_LOUDNESS_OVERLAP");
+  const bool overlap = !(ov_env && ov_env[0] == '0');
+  cudaStream_t ts = s;
+  if (overlap) {
+    if (!side) {
+      OMB_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      OMB_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      OMB_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    OMB_CUDA_TRY(cudaEventRecord(ev_fork, s));
+    OMB_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+    ts = side;
+  }
+  const unsigned gx = (unsigned)std::min<uint64_t>((block_frames + kTpTile - 1) / kTpTile, 64);
+  if (tp_delay_len == 12 && !getenv("OMB_NO_TRUE_PEAK4")) {
+    // enough (stream, block) pairs to fill the GPU: one CTA walks all tiles of its block (set-up and the final reduction
+    // are paid once per block instead of once per 256 frames)
+    const unsigned gy = (uint64_t)n_streams * a.n_blocks >= (uint64_t)std::max(dev.sm_count, 1) * 16 ? 1u : gx;
+    const dim3 grid((unsigned)((uint64_t)n_streams * a.n_blocks), gy);
+    if (channels == 8) {
+      OMB_LAUNCH(k_true_peak4<8>, grid, dim3(kTpTile), 0, ts, a, fir);
+    } else if (channels == 2) {
+      OMB_LAUNCH(k_true_peak4<2>, grid, dim3(kTpTile), 0, ts, a, fir);
+    } else {
+      OMB_LAUNCH(k_true_peak4<0>, grid, dim3(kTpTile), 0, ts, a, fir);
+    }
+  } else {
+    OMB_LAUNCH(k_true_peak, dim3((unsigned)((uint64_t)n_streams * a.n_blocks), gx), dim3(kTpTile), 0, ts, a, fir);
+  }
+  OMB_CHECK_LAUNCH();
+  if (overlap) OMB_CUDA_TRY(cudaEventRecord(ev_join, side));
   const uint64_t n_items = (uint64_t)n_streams * a.n_chunks * channels;
   const unsigned g1 = (unsigned)((n_items + 127) / 128);
   auto k_apply = k_kw_chunks<true>;
@@ -1030,26 +1066,10 @@ int LoudnessPlan::execute_device(const float* d_interleaved, uint32_t n_streams,
   }
   OMB_LAUNCH(k_apply, dim3(g1), dim3(128), 0, s, a);
   OMB_CHECK_LAUNCH();
-  const unsigned gx = (unsigned)std::min<uint64_t>((block_frames + kTpTile - 1) / kTpTile, 64);
-  if (tp_delay_len == 12 && !getenv("OMB_NO_TRUE_PEAK4")) {
-    // enough (stream, block) pairs to fill the GPU: one CTA walks all tiles of its block (set-up and the final reduction
-    // are paid once per block instead of once per 256 frames)
-    const unsigned gy = (uint64_t)n_streams * a.n_blocks >= (uint64_t)std::max(dev.sm_count, 1) * 16 ? 1u : gx;
-    const dim3 grid((unsigned)((uint64_t)n_streams * a.n_blocks), gy);
-    if (channels == 8) {
-      OMB_LAUNCH(k_true_peak4<8>, grid, dim3(kTpTile), 0, s, a, fir);
-    } else if (channels == 2) {
-      OMB_LAUNCH(k_true_peak4<2>, grid, dim3(kTpTile), 0, s, a, fir);
-    } else {
-      OMB_LAUNCH(k_true_peak4<0>, grid, dim3(kTpTile), 0, s, a, fir);
-    }
-  } else {
-    OMB_LAUNCH(k_true_peak, dim3((unsigned)((uint64_t)n_streams * a.n_blocks), gx), dim3(kTpTile), 0, s, a, fir);
-  }
-  OMB_CHECK_LAUNCH();
   OMB_LAUNCH(k_csum_prefix, dim3((unsigned)((uint64_t)n_streams * channels)), dim3(256), 0, s, a, d_cbase.ptr);
   OMB_CHECK_LAUNCH();
   a.cbase = d_cbase.ptr;
+  if (overlap) OMB_CUDA_TRY(cudaStreamWaitEvent(s, ev_join, 0));
   const uint64_t n_snap = (uint64_t)n_streams * a.n_blocks;
   OMB_LAUNCH(k_loud_snapshots, dim3((unsigned)((n_snap * 32 + 127) / 128)), dim3(128), 0, s, a);
   OMB_CHECK_LAUNCH();

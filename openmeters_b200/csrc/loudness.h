@@ -75,6 +75,9 @@ struct LoudnessPlan {
   DeviceBuffer<float> d_in;
   DeviceBuffer<omb_loudness_snapshot> d_out;
   cudaStream_t stream = nullptr;
+  // batch path: the true-peak kernel (FP32-bound, needs only the PCM) runs on `side` next to the K-weighting chain (FP64 / DRAM-bound)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   ~LoudnessPlan();
   int init(const omb_loudness_config& c, uint32_t channels, const uint8_t* positions);
   int execute_device(const float* d_interleaved, uint32_t n_streams, uint64_t frames, uint64_t stream_stride, uint64_t block_frames,
